@@ -1,0 +1,182 @@
+/* slsgp.h — C ABI of libslsgp, the B200 (sm_100a) implementation of the Gaussian-process hot path of
+ * yuki-koyama/sequential-line-search.
+ *
+ * The reference has no plugin / FFI seam for this path; its replaceable seams are C++-level
+ * (the `Regressor` virtuals, the L1 free functions of regressor.hpp, `acquisition_func::*`, the NLopt objective
+ * callbacks). Each entry point below names the reference code it stands in for (paths relative to the upstream
+ * repository). The host-side C++ that keeps the reference's class API calls these functions and nothing else;
+ * INTEGRATION.md shows the binding a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; all matrices column-major (Eigen's default); X is D x N, one observation per column;
+ *     theta = (a, l_1 .. l_D) is the reference's `kernel_hyperparams` vector, `noise` its `noise_level` b.
+ *   - every function returns an `slsgp_status`; nothing throws across the boundary; `slsgp_last_error(ctx)` gives
+ *     the message for the last non-zero status on that context.
+ *   - pointers named `*_out` may be NULL when the caller does not want that result copied back to the host.
+ *   - a context owns all device memory it uses and one CUDA stream; calls on one context are serialised by the
+ *     caller; distinct contexts may be used from distinct threads.
+ *   - there is NO CPU fallback: if no CUDA device is usable `slsgp_ctx_create` fails with SLSGP_ERR_CUDA.
+ */
+#ifndef SLSGP_H
+#define SLSGP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C"
+{
+#endif
+
+#define SLSGP_VERSION 100
+
+    typedef struct slsgp_ctx slsgp_ctx;
+
+    typedef enum
+    {
+        SLSGP_OK          = 0,
+        SLSGP_ERR_INVALID = 1, /* bad argument (null pointer, non-positive size, unknown enum value) */
+        SLSGP_ERR_STATE   = 2, /* call order: e.g. slsgp_factor before slsgp_gram */
+        SLSGP_ERR_NOT_SPD = 3, /* Cholesky met a non-positive pivot; slsgp_last_error names the index */
+        SLSGP_ERR_NAN     = 4, /* NaN / Inf in an input the reference would have asserted on */
+        SLSGP_ERR_CUDA    = 5, /* CUDA runtime error, or no usable device */
+        SLSGP_ERR_NOMEM   = 6
+    } slsgp_status;
+
+    /* sequential_line_search::KernelType (include/sequential-line-search/kernel-type.hpp:8-12), same order */
+    typedef enum
+    {
+        SLSGP_KERNEL_ARD_SQUARED_EXP = 0,
+        SLSGP_KERNEL_ARD_MATERN52    = 1
+    } slsgp_kernel_type;
+
+    /* sequential_line_search::AcquisitionFuncType (include/sequential-line-search/acquisition-function.hpp:11-15) */
+    typedef enum
+    {
+        SLSGP_ACQ_EXPECTED_IMPROVEMENT = 0,
+        SLSGP_ACQ_GP_UCB               = 1
+    } slsgp_acq_type;
+
+    /* Arithmetic used by the candidate sweep (slsgp_posterior_batch / slsgp_acq_batch / slsgp_acq_argmax).
+     * Gram build, factorisation, inverse, alpha and the MAP objectives are always IEEE double. */
+    typedef enum
+    {
+        SLSGP_SWEEP_FP64   = 0, /* IEEE double throughout; parity 1e-5 relative (north_star "FP64") */
+        SLSGP_SWEEP_TENSOR = 1  /* split-fp16 operands on the tcgen05 tensor pipe, fp32 accumulation; parity 1e-3 */
+    } slsgp_sweep_mode;
+
+    /* Reference quirks that parity has to reproduce; all on by default. */
+#define SLSGP_COMPAT_SE_XGRAD_2X 1u /* mathtoolbox kernel-functions.cpp:92 returns -2 k (x_a-x_b)/l^2 */
+
+    /* ---- context -------------------------------------------------------------------------------------------- */
+    slsgp_status slsgp_ctx_create(int device, slsgp_ctx** ctx_out);
+    slsgp_status slsgp_ctx_destroy(slsgp_ctx* ctx);
+    const char*  slsgp_last_error(const slsgp_ctx* ctx);
+    const char*  slsgp_status_string(slsgp_status s);
+    slsgp_status slsgp_set_compat_flags(slsgp_ctx* ctx, unsigned flags);
+    slsgp_status slsgp_set_sweep_mode(slsgp_ctx* ctx, slsgp_sweep_mode mode);
+    /* Use a caller-owned CUDA stream (a cudaStream_t passed as void*) instead of the context's own; NULL restores
+     * the context's stream. Lets a host framework order libslsgp work with its own copies and events. */
+    slsgp_status slsgp_set_stream(slsgp_ctx* ctx, void* cuda_stream);
+    slsgp_status slsgp_synchronize(slsgp_ctx* ctx);
+
+    /* ---- data ------------------------------------------------------------------------------------------------
+     * Replaces the regressors' `m_X` copy (src/preference-regressor.cpp:273, gaussian-process-regressor.cpp:203).
+     * Uploads X (D x N, column-major, host memory) and invalidates every derived quantity. */
+    slsgp_status slsgp_set_data(slsgp_ctx* ctx, const double* X, int N, int D);
+
+    /* ---- K1: Gram matrix --------------------------------------------------------------------------------------
+     * K_y = K_f + noise * I: CalcLargeKY / CalcLargeKF (src/regressor.cpp:61-89) with the per-pair kernels
+     * GetArdSquaredExpKernel / GetArdMatern52Kernel (external/mathtoolbox/src/kernel-functions.cpp:7-20, 95-112).
+     * Keeps (kernel_type, theta, noise) as the model's hyper-parameters. K_out: N x N or NULL. */
+    slsgp_status slsgp_gram(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, double noise,
+                            double* K_out);
+
+    /* ---- K2: Cholesky ------------------------------------------------------------------------------------------
+     * K_y = L L^T: Eigen::LLT at src/preference-regressor.cpp:162,290,370; logdet = 2 sum log L_ii:
+     * mathtoolbox CalcLogDetOfSymmetricPositiveDefiniteMatrix (src/log-determinant.cpp:8-11).
+     * L_out: N x N lower triangle (upper part zero) or NULL. Returns SLSGP_ERR_NOT_SPD on a bad pivot (the
+     * reference never checks LLT::info()). */
+    slsgp_status slsgp_factor(slsgp_ctx* ctx, double* logdet_out, double* L_out);
+
+    /* ---- K3: factor application --------------------------------------------------------------------------------
+     * Explicit K_y^-1: GaussianProcessRegressor::m_K_y_inv = m_K_y.inverse() (src/gaussian-process-regressor.cpp:
+     * 159,211,231) and LLT::solve(Identity) (src/preference-regressor.cpp:66). Computed from the Cholesky factor
+     * (L^-1, then L^-T L^-1). Needed by the sweep and by the MAP hyper-parameter gradient; computed on demand if
+     * the caller did not ask for it. Kinv_out: N x N or NULL. */
+    slsgp_status slsgp_inverse(slsgp_ctx* ctx, double* Kinv_out);
+
+    /* alpha = K_y^-1 y: the LLT::solve(m_y) that every PredictMu / PredictMuDerivative repeats
+     * (src/preference-regressor.cpp:296,320; `m_K_y_inv * m_y`, src/gaussian-process-regressor.cpp:238,262).
+     * Also caches f_best = max_i mu(X_i), i.e. mu(PredictMaximumPointFromData()) (src/regressor.cpp:29-43), which
+     * Expected Improvement needs. y: N goodness / observed values. */
+    slsgp_status slsgp_solve_alpha(slsgp_ctx* ctx, const double* y, double* alpha_out);
+    slsgp_status slsgp_get_f_best(slsgp_ctx* ctx, double* f_best_out, int* index_out);
+
+    /* ---- K4: batched posterior and acquisition sweep --------------------------------------------------------------
+     * For each of M query points (Xq: D x M, column-major, host memory):
+     *   mu      Regressor::PredictMu               (src/preference-regressor.cpp:293-297)
+     *   sigma   Regressor::PredictSigma            (:299-313; clamps sigma^2 < 0 to 0)
+     *   dmu     Regressor::PredictMuDerivative     (:315-321)            D x M
+     *   dsigma  Regressor::PredictSigmaDerivative  (:323-330; divides by sigma unguarded, as the reference) D x M
+     * through CalcSmallK / CalcSmallKSmallXDerivative (src/regressor.cpp:45-59, 91-108). */
+    slsgp_status slsgp_posterior_batch(slsgp_ctx* ctx, const double* Xq, int64_t M, double* mu_out,
+                                       double* sigma_out, double* dmu_out, double* dsigma_out);
+
+    /*   val   acquisition_func::CalcAcquisitionValue            (src/acquisition-function.cpp:170-198)
+     *   grad  acquisition_func::CalcAcquisitionValueDerivative  (:200-230)                                D x M
+     * with mathtoolbox GetExpectedImprovement{,Derivative} / GetGaussianProcessUpperConfidenceBound{,Derivative}
+     * (external/mathtoolbox/src/acquisition-functions.cpp:8-78). Returns 0 / zero vectors when the model holds no
+     * data (:176-179, :206-209). */
+    slsgp_status slsgp_acq_batch(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, const double* Xq,
+                                 int64_t M, double* val_out, double* grad_out);
+
+    /* Same sweep with every buffer already resident on the context's device (device pointers): no copies.
+     * Any output may be NULL. Asynchronous on the context's stream. */
+    slsgp_status slsgp_acq_batch_device(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta,
+                                        const double* d_Xq, int64_t M, double* d_mu, double* d_sigma,
+                                        double* d_dmu, double* d_dsigma, double* d_val, double* d_grad);
+
+    /* Global search stage of FindGlobalSolution (src/acquisition-function.cpp:112-167: DIRECT, or random-start
+     * multi-start) as a dense sweep: candidate i in [first, first + count) is the point of [0,1]^D produced by the
+     * counter-based generator slsgp_candidates(seed, i) — independent of how a range is split across GPUs. Evaluates
+     * the acquisition value (+ gradient when grad_best_out != NULL) for all of them in `count`-sized shards on this
+     * device and returns the arg-max (lowest index wins ties). x_best_out: D. */
+    slsgp_status slsgp_acq_argmax(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
+                                  int64_t first, int64_t count, double* x_best_out, double* val_best_out,
+                                  int64_t* index_best_out, double* grad_best_out);
+    /* The generator itself, for hosts that want the same candidates (D x count, host memory). */
+    slsgp_status slsgp_candidates(slsgp_ctx* ctx, uint64_t seed, int64_t first, int64_t count, double* Xq_out);
+
+    /* ---- K5/K6: MAP objectives ---------------------------------------------------------------------------------------
+     * Preference tuples in CSR form: tuple t = idx[offsets[t] .. offsets[t+1]), first member preferred
+     * (include/sequential-line-search/preference.hpp:9-19). */
+    slsgp_status slsgp_set_preferences(slsgp_ctx* ctx, const uint32_t* offsets, const uint32_t* idx, int P);
+
+    /* `objective` of PreferenceRegressor (src/preference-regressor.cpp:129-259): BTL log-likelihood
+     * (utils.hpp:25-52) + log N(y; 0, K_y) + log-normal hyper-priors, and its gradient
+     * (CalcObjectiveThetaDerivative :77-115, CalcObjectiveNoiseLevelDerivative :53-74).
+     * x = [y_1..y_N] or, when use_map_hyperparams, [y_1..y_N, a, b, r_1..r_D]; grad_out has the same length or is
+     * NULL (derivative-free caller, `grad.empty()` in NLopt). With use_map_hyperparams == 0 the kernel matrix is the
+     * one last built by slsgp_gram + slsgp_factor (the reference reuses m_K / m_K_llt, :160-162). */
+    slsgp_status slsgp_map_objective_pref(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* x, int n_x,
+                                          int use_map_hyperparams, double default_a, double default_r,
+                                          double default_b, double prior_var, double btl_scale, double* f_out,
+                                          double* grad_out);
+
+    /* `objective` of GaussianProcessRegressor (src/gaussian-process-regressor.cpp:141-193, calc_grad :108-127, priors
+     * :18-64): log marginal likelihood + fixed log-normal priors; x = (a, b, r_1..r_D); grad_out D+2 or NULL. */
+    slsgp_status slsgp_map_objective_gpr(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* y,
+                                         const double* x, double* f_out, double* grad_out);
+
+    /* ---- introspection (bench / tests) ----------------------------------------------------------------------------- */
+    /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+    uint64_t     slsgp_launch_count(const slsgp_ctx* ctx);
+    /* Milliseconds (CUDA events on the context's stream) spent in the most recent call of the named phase:
+     * "gram", "factor", "inverse", "alpha", "sweep", "map". Returns < 0 for an unknown name. */
+    double       slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SLSGP_H */

@@ -1,0 +1,235 @@
+"""ctypes binding of include/slsgp.h — the reference-side stub a Python host would use.
+
+Thin by design: numpy arrays in, numpy arrays out, every call goes straight to the C ABI. There is no CPU path:
+if libslsgp.so is missing it is built with nvcc; if no CUDA device is usable, creating a Context raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import LIB_PATH as _LIB_PATH, build as _build_library
+
+c_dp = C.POINTER(C.c_double)
+c_u32p = C.POINTER(C.c_uint32)
+
+OK, ERR_INVALID, ERR_STATE, ERR_NOT_SPD, ERR_NAN, ERR_CUDA, ERR_NOMEM = range(7)
+KERNEL_ARD_SQUARED_EXP, KERNEL_ARD_MATERN52 = 0, 1
+ACQ_EXPECTED_IMPROVEMENT, ACQ_GP_UCB = 0, 1
+SWEEP_FP64, SWEEP_TENSOR = 0, 1
+COMPAT_SE_XGRAD_2X = 1
+
+# every symbol include/slsgp.h declares: (name, restype, argtypes)
+_API = [
+    ("slsgp_ctx_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("slsgp_ctx_destroy", C.c_int, [C.c_void_p]),
+    ("slsgp_last_error", C.c_char_p, [C.c_void_p]),
+    ("slsgp_status_string", C.c_char_p, [C.c_int]),
+    ("slsgp_set_compat_flags", C.c_int, [C.c_void_p, C.c_uint]),
+    ("slsgp_set_sweep_mode", C.c_int, [C.c_void_p, C.c_int]),
+    ("slsgp_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("slsgp_synchronize", C.c_int, [C.c_void_p]),
+    ("slsgp_set_data", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
+    ("slsgp_gram", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_double, c_dp]),
+    ("slsgp_factor", C.c_int, [C.c_void_p, c_dp, c_dp]),
+    ("slsgp_inverse", C.c_int, [C.c_void_p, c_dp]),
+    ("slsgp_solve_alpha", C.c_int, [C.c_void_p, c_dp, c_dp]),
+    ("slsgp_get_f_best", C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int)]),
+    ("slsgp_posterior_batch", C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
+    ("slsgp_acq_batch", C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp, C.c_int64, c_dp, c_dp]),
+    ("slsgp_acq_batch_device", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
+    ("slsgp_acq_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, c_dp, c_dp,
+                                   C.POINTER(C.c_int64), c_dp]),
+    ("slsgp_candidates", C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, c_dp]),
+    ("slsgp_set_preferences", C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int]),
+    ("slsgp_map_objective_pref", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, C.c_double,
+                                           C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
+    ("slsgp_map_objective_gpr", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    ("slsgp_launch_count", C.c_uint64, [C.c_void_p]),
+    ("slsgp_last_phase_ms", C.c_double, [C.c_void_p, C.c_char_p]),
+]
+API_SYMBOLS = [name for name, _, _ in _API]
+
+_lib = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """dlopen libslsgp.so (building it first if needed) and declare every prototype."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise RuntimeError(f"{path} is missing; run `python __graft_entry__.py build`")
+        _build_library()
+    lib = C.CDLL(path)
+    for name, restype, argtypes in _API:
+        fn = getattr(lib, name)  # AttributeError here == header / library mismatch
+        fn.restype, fn.argtypes = restype, argtypes
+    _lib = lib
+    return lib
+
+
+class SlsgpError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__(f"libslsgp status {status}: {message}")
+        self.status = status
+
+
+def _f64(a, order="F"):
+    return np.require(np.asarray(a, dtype=np.float64), requirements=[order, "A"])
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+class Context:
+    """One libslsgp device context. Mirrors the C ABI one to one; see include/slsgp.h for semantics."""
+
+    def __init__(self, device: int = 0):
+        self.lib = load_library()
+        h = C.c_void_p()
+        st = self.lib.slsgp_ctx_create(device, C.byref(h))
+        if st != OK:
+            raise SlsgpError(st, "slsgp_ctx_create failed: no usable CUDA device (libslsgp has no CPU fallback)")
+        self.h = h
+        self.N = self.D = 0
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.slsgp_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, st):
+        if st != OK:
+            raise SlsgpError(st, self.lib.slsgp_last_error(self.h).decode())
+
+    # ---- configuration
+    def set_compat_flags(self, flags):
+        self._check(self.lib.slsgp_set_compat_flags(self.h, flags))
+
+    def set_sweep_mode(self, mode):
+        self._check(self.lib.slsgp_set_sweep_mode(self.h, mode))
+
+    def set_stream(self, cuda_stream):
+        self._check(self.lib.slsgp_set_stream(self.h, C.c_void_p(cuda_stream)))
+
+    def synchronize(self):
+        self._check(self.lib.slsgp_synchronize(self.h))
+
+    # ---- model
+    def set_data(self, X):
+        X = _f64(X)
+        self.D, self.N = X.shape
+        self._check(self.lib.slsgp_set_data(self.h, _p(X), self.N, self.D))
+
+    def gram(self, kernel_type, theta, noise, want=True):
+        theta = _f64(theta)
+        K = np.empty((self.N, self.N), order="F") if want else None
+        self._check(self.lib.slsgp_gram(self.h, kernel_type, _p(theta), noise, _p(K)))
+        return K
+
+    def factor(self, want_L=False):
+        logdet = C.c_double()
+        L = np.empty((self.N, self.N), order="F") if want_L else None
+        self._check(self.lib.slsgp_factor(self.h, C.byref(logdet), _p(L)))
+        return (logdet.value, L) if want_L else logdet.value
+
+    def inverse(self, want=True):
+        Kinv = np.empty((self.N, self.N), order="F") if want else None
+        self._check(self.lib.slsgp_inverse(self.h, _p(Kinv)))
+        return Kinv
+
+    def solve_alpha(self, y):
+        y = _f64(y)
+        alpha = np.empty(self.N)
+        self._check(self.lib.slsgp_solve_alpha(self.h, _p(y), _p(alpha)))
+        return alpha
+
+    def f_best(self):
+        f, i = C.c_double(), C.c_int()
+        self._check(self.lib.slsgp_get_f_best(self.h, C.byref(f), C.byref(i)))
+        return f.value, i.value
+
+    def fit(self, X, kernel_type, theta, noise, y):
+        """set_data + gram + factor + solve_alpha: what a regressor constructor does after MAP."""
+        self.set_data(X)
+        self.gram(kernel_type, theta, noise, want=False)
+        self.factor()
+        return self.solve_alpha(y)
+
+    # ---- sweep
+    def posterior_batch(self, Xq, grads=True):
+        Xq = _f64(Xq)
+        D, M = Xq.shape
+        mu, sigma = np.empty(M), np.empty(M)
+        dmu = np.empty((D, M), order="F") if grads else None
+        dsg = np.empty((D, M), order="F") if grads else None
+        self._check(self.lib.slsgp_posterior_batch(self.h, _p(Xq), M, _p(mu), _p(sigma), _p(dmu), _p(dsg)))
+        return mu, sigma, dmu, dsg
+
+    def acq_batch(self, acq_type, ucb_beta, Xq, grads=True):
+        Xq = _f64(Xq)
+        D, M = Xq.shape
+        val = np.empty(M)
+        grad = np.empty((D, M), order="F") if grads else None
+        self._check(self.lib.slsgp_acq_batch(self.h, acq_type, ucb_beta, _p(Xq), M, _p(val), _p(grad)))
+        return val, grad
+
+    def acq_batch_device(self, acq_type, ucb_beta, d_Xq, M, d_mu=0, d_sigma=0, d_dmu=0, d_dsigma=0, d_val=0, d_grad=0):
+        """All arguments are raw device addresses (ints), e.g. torch.Tensor.data_ptr(). Asynchronous."""
+        v = lambda a: C.c_void_p(a) if a else None
+        self._check(self.lib.slsgp_acq_batch_device(self.h, acq_type, ucb_beta, v(d_Xq), M, v(d_mu), v(d_sigma),
+                                                    v(d_dmu), v(d_dsigma), v(d_val), v(d_grad)))
+
+    def acq_argmax(self, acq_type, ucb_beta, seed, first, count, want_grad=False):
+        x = np.empty(self.D)
+        val, idx = C.c_double(), C.c_int64()
+        grad = np.empty(self.D) if want_grad else None
+        self._check(self.lib.slsgp_acq_argmax(self.h, acq_type, ucb_beta, seed, first, count, _p(x), C.byref(val),
+                                              C.byref(idx), _p(grad)))
+        return x, val.value, idx.value, grad
+
+    def candidates(self, seed, first, count):
+        Xq = np.empty((self.D, count), order="F")
+        self._check(self.lib.slsgp_candidates(self.h, seed, first, count, _p(Xq)))
+        return Xq
+
+    # ---- MAP objectives
+    def set_preferences(self, offsets, idx):
+        offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+        idx = np.ascontiguousarray(idx, dtype=np.uint32)
+        self._check(self.lib.slsgp_set_preferences(self.h, offsets.ctypes.data_as(c_u32p), idx.ctypes.data_as(c_u32p),
+                                                   len(offsets) - 1))
+
+    def map_objective_pref(self, kernel_type, x, use_map, a, r, b, prior_var, btl_scale, want_grad=True):
+        x = _f64(x)
+        f = C.c_double()
+        g = np.empty(len(x)) if want_grad else None
+        self._check(self.lib.slsgp_map_objective_pref(self.h, kernel_type, _p(x), len(x), int(use_map), a, r, b,
+                                                      prior_var, btl_scale, C.byref(f), _p(g)))
+        return f.value, g
+
+    def map_objective_gpr(self, kernel_type, y, x, want_grad=True):
+        y, x = _f64(y), _f64(x)
+        f = C.c_double()
+        g = np.empty(len(x)) if want_grad else None
+        self._check(self.lib.slsgp_map_objective_gpr(self.h, kernel_type, _p(y), _p(x), C.byref(f), _p(g)))
+        return f.value, g
+
+    # ---- introspection
+    def launch_count(self):
+        return int(self.lib.slsgp_launch_count(self.h))
+
+    def phase_ms(self, name):
+        return float(self.lib.slsgp_last_phase_ms(self.h, name.encode()))

@@ -1,0 +1,250 @@
+// FP64 dense building blocks: tiled GEMM with triangular k-range pruning, the 64x64 diagonal-block
+// Cholesky + inverse, and small matrix utilities. Everything works on column-major storage whose leading
+// dimension is a multiple of TILE (=64); matrices are padded with an identity block so that no kernel needs
+// ragged-edge handling.
+#pragma once
+
+#include "common.cuh"
+
+namespace slsgp
+{
+    struct GemmArgs
+    {
+        const double* A;
+        const double* B;
+        double*       C;
+        int           m, n, k; // m, n multiples of 64; k multiple of 16
+        int           lda, ldb, ldc;
+        double        alpha, beta;
+        long long     sA, sB, sC; // batch strides (elements), batch index = blockIdx.z
+        int           lower_only; // 1: skip tiles strictly above the diagonal (tn > tm)
+        int           k_lo_mode;  // 0: 0 | 1: tn*64 (B lower-triangular in (k, n)) | 2: max(tm, tn)*64
+        int           k_hi_mode;  // 0: k | 1: (tm+1)*64 (A lower-triangular in (m, k))
+        int           row0, row_step, row_limit; // tile exists iff row0 + z*row_step + tm*64 < row_limit
+    };
+
+    inline GemmArgs gemm_args(const double* A, const double* B, double* C, int m, int n, int k, int lda, int ldb,
+                              int ldc, double alpha, double beta)
+    {
+        GemmArgs g;
+        g.A = A, g.B = B, g.C = C, g.m = m, g.n = n, g.k = k, g.lda = lda, g.ldb = ldb, g.ldc = ldc;
+        g.alpha = alpha, g.beta = beta, g.sA = g.sB = g.sC = 0;
+        g.lower_only = 0, g.k_lo_mode = 0, g.k_hi_mode = 0, g.row0 = 0, g.row_step = 0, g.row_limit = 1 << 30;
+        return g;
+    }
+
+    // C = alpha * op(A) * op(B) + beta * C on 64 x 64 output tiles, 256 threads, 4 x 4 register micro-tile.
+    // op(A) is m x k: TA == false -> A[m + k*lda], TA == true -> A[k + m*lda]. op(B) is k x n likewise.
+    template <bool TA, bool TB> __global__ void __launch_bounds__(256) gemm64_kernel(const GemmArgs g)
+    {
+        const int tm = blockIdx.x, tn = blockIdx.y, z = blockIdx.z;
+        if (g.lower_only && tn > tm) return;
+        if (g.row0 + z * g.row_step + tm * TILE >= g.row_limit) return;
+
+        const double* __restrict__ A = g.A + z * g.sA;
+        const double* __restrict__ B = g.B + z * g.sB;
+        double* C                    = g.C + z * g.sC; // may alias A (in-place panel update)
+
+        int k_lo = 0, k_hi = g.k;
+        if (g.k_lo_mode == 1) k_lo = tn * TILE;
+        if (g.k_lo_mode == 2) k_lo = max(tm, tn) * TILE;
+        if (g.k_hi_mode == 1) k_hi = min(g.k, (tm + 1) * TILE);
+
+        __shared__ double As[16][TILE + 1];
+        __shared__ double Bs[16][TILE + 1];
+
+        const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+        double    acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+        for (int k0 = k_lo; k0 < k_hi; k0 += 16)
+        {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const int e = tid + r * 256;
+                if (!TA)
+                {
+                    const int mm = e & 63, kk = e >> 6;
+                    As[kk][mm]   = A[(size_t) (tm * TILE + mm) + (size_t) (k0 + kk) * g.lda];
+                }
+                else
+                {
+                    const int kk = e & 15, mm = e >> 4;
+                    As[kk][mm]   = A[(size_t) (k0 + kk) + (size_t) (tm * TILE + mm) * g.lda];
+                }
+                if (!TB)
+                {
+                    const int kk = e & 15, nn = e >> 4;
+                    Bs[kk][nn]   = B[(size_t) (k0 + kk) + (size_t) (tn * TILE + nn) * g.ldb];
+                }
+                else
+                {
+                    const int nn = e & 63, kk = e >> 6;
+                    Bs[kk][nn]   = B[(size_t) (tn * TILE + nn) + (size_t) (k0 + kk) * g.ldb];
+                }
+            }
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; ++kk)
+            {
+                double a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[kk][tx * 4 + i];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty * 4 + j];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+            __syncthreads();
+        }
+
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const size_t idx = (size_t) (tm * TILE + tx * 4 + i) + (size_t) (tn * TILE + ty * 4 + j) * g.ldc;
+                double       v   = g.alpha * acc[i][j];
+                if (g.beta != 0.0) v += g.beta * C[idx];
+                C[idx] = v;
+            }
+    }
+
+    // Cholesky of one 64 x 64 diagonal block (in place, lower; the strict upper part of the block is zeroed) and
+    // its inverse W = L^-1 (lower) written to Wd. info[0] receives 1 + global index of the first bad pivot.
+    //
+    // Right-looking on both: at step j, after column j of L is final, the same rank-1 sweep that updates the
+    // trailing part of A also advances the forward substitution L W = I
+    //     W[j][0..j] /= L[j][j];   W[i][0..j] -= L[i][j] * W[j][0..j]   (i > j),
+    // so the inverse costs no extra barriers. W (strictly lower) lives transposed in the unused strict upper
+    // triangle of the shared tile, its diagonal in wd.
+    __global__ void __launch_bounds__(256) potf2_inverse_kernel(double* Ad, int lda, double* Wd, int ldw, int diag0,
+                                                                int* __restrict__ info)
+    {
+        __shared__ double S[TILE][TILE + 1];
+        __shared__ double wd[TILE];
+        const int         tid = threadIdx.x;
+        for (int e = tid; e < TILE * TILE; e += 256)
+        {
+            const int r = e & 63, c = e >> 6;
+            S[r][c]     = (c <= r) ? Ad[(size_t) r + (size_t) c * lda] : 0.0;
+        }
+        __syncthreads();
+        for (int j = 0; j < TILE; ++j)
+        {
+            const double d  = S[j][j];
+            const double sd = sqrt(d);
+            if (tid == 0 && !(d > 0.0)) atomicCAS(info, 0, 1 + diag0 + j);
+            __syncthreads(); // everyone has read S[j][j]
+            if (tid == j) S[j][j] = sd, wd[j] = 1.0 / sd;
+            if (tid > j && tid < TILE) S[tid][j] = S[tid][j] / sd;                  // column j of L
+            if (tid >= TILE && tid - TILE < j) S[tid - TILE][j] = S[tid - TILE][j] / sd; // row j of W (c' < j)
+            __syncthreads();
+            const int w = TILE - 1 - j; // rows j+1 .. 63
+            for (int e = tid; e < w * TILE; e += 256)
+            {
+                const int    r = j + 1 + (e >> 6), cc = e & 63;
+                const double lrj = S[r][j];
+                if (cc <= j) // W[r][cc] -= L[r][j] * W[j][cc]
+                    S[cc][r] = fma(-lrj, (cc == j) ? wd[j] : S[cc][j], S[cc][r]);
+                else if (cc <= r) // A[r][cc] -= L[r][j] * L[cc][j]
+                    S[r][cc] = fma(-lrj, S[cc][j], S[r][cc]);
+            }
+            __syncthreads();
+        }
+        for (int e = tid; e < TILE * TILE; e += 256)
+        {
+            const int r = e & 63, c = e >> 6;
+            Ad[(size_t) r + (size_t) c * lda] = (c <= r) ? S[r][c] : 0.0;
+            Wd[(size_t) r + (size_t) c * ldw] = (c < r) ? S[c][r] : (c == r ? wd[r] : 0.0);
+        }
+    }
+
+    // Zero the strict upper triangle of an n x n matrix (after the blocked factorisation the upper tiles still hold
+    // the Gram matrix).
+    __global__ void zero_upper_kernel(double* __restrict__ A, int n, int lda)
+    {
+        const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
+        if (r < n && r < c) A[(size_t) r + (size_t) c * lda] = 0.0;
+    }
+
+    // Mirror the lower triangle into the upper one (64 x 64 tiles through shared memory so both sides coalesce).
+    __global__ void __launch_bounds__(256) symmetrize_kernel(double* __restrict__ A, int lda)
+    {
+        const int tm = blockIdx.x, tn = blockIdx.y;
+        if (tn >= tm) return;
+        __shared__ double S[TILE][TILE + 1];
+        for (int e = threadIdx.x; e < TILE * TILE; e += 256)
+        {
+            const int r = e & 63, c = e >> 6;
+            S[r][c]     = A[(size_t) (tm * TILE + r) + (size_t) (tn * TILE + c) * lda];
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < TILE * TILE; e += 256)
+        {
+            const int r = e & 63, c = e >> 6; // element (tn*64 + r, tm*64 + c) = lower (tm*64 + c, tn*64 + r)
+            A[(size_t) (tn * TILE + r) + (size_t) (tm * TILE + c) * lda] = S[c][r];
+        }
+    }
+    // Diagonal tiles: copy lower to upper inside the tile.
+    __global__ void __launch_bounds__(256) symmetrize_diag_kernel(double* __restrict__ A, int lda)
+    {
+        const int t = blockIdx.x;
+        for (int e = threadIdx.x; e < TILE * TILE; e += 256)
+        {
+            const int r = e & 63, c = e >> 6;
+            if (r < c)
+                A[(size_t) (t * TILE + r) + (size_t) (t * TILE + c) * lda] =
+                    A[(size_t) (t * TILE + c) + (size_t) (t * TILE + r) * lda];
+        }
+    }
+
+    // out[0] = 2 * sum_{i<n} log(L_ii)   (mathtoolbox log-determinant.cpp:8-11); single block, fixed order.
+    __global__ void __launch_bounds__(256) logdet_kernel(const double* __restrict__ L, int n, int ld,
+                                                         double* __restrict__ out)
+    {
+        __shared__ double part[256];
+        double            s = 0.0;
+        for (int i = threadIdx.x; i < n; i += 256) s += log(L[(size_t) i + (size_t) i * ld]);
+        part[threadIdx.x] = s;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1)
+        {
+            if (threadIdx.x < o) part[threadIdx.x] += part[threadIdx.x + o];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) out[0] = 2.0 * part[0];
+    }
+
+    // y = op(A) x for an n x n matrix, one warp per output element (deterministic shuffle reduction).
+    // TRANS == true:  y_i = sum_j A[j + i*lda] x_j (column dot: coalesced)  -> y = A^T x
+    // TRANS == false: y_i = sum_j A[i + j*lda] x_j (row dot: strided; used only for triangular W y)
+    // tri: 0 full | 1 A lower-triangular (row i uses j <= i; column i uses j >= i)
+    template <bool TRANS>
+    __global__ void __launch_bounds__(256) gemv_kernel(const double* __restrict__ A, int n, int lda,
+                                                       const double* __restrict__ x, double* __restrict__ y, int tri)
+    {
+        const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+        if (warp >= n) return;
+        const int i = warp;
+        double    s = 0.0;
+        if (TRANS)
+        {
+            const int j0 = tri ? i : 0;
+            for (int j = j0 + lane; j < n; j += 32) s = fma(A[(size_t) j + (size_t) i * lda], x[j], s);
+        }
+        else
+        {
+            const int j1 = tri ? i + 1 : n;
+            for (int j = lane; j < j1; j += 32) s = fma(A[(size_t) i + (size_t) j * lda], x[j], s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) y[i] = s;
+    }
+} // namespace slsgp

@@ -1,0 +1,956 @@
+// libslsgp: C-ABI entry points (include/slsgp.h) and the device context behind them. sm_100a only.
+//
+// Data layout in HBM (all FP64, column-major):
+//   X      D x N              observations, one per column (as Eigen stores the reference's m_X)
+//   Xpad   Dp x ld            zero-padded copy, Dp = round_up(D, 64)            (A operand of the P1/P2 GEMMs)
+//   XT1    ld x ldx           X^T in columns 0..D-1, ones in column D            (B operand of the MAP gradient GEMM)
+//   K, L, W, Kinv, T          ld x ld each, ld = round_up(N, 64); rows/cols >= N hold an identity block so every
+//                             kernel works on whole 64 x 64 tiles. L = chol(K) (lower), W = L^-1, Kinv = W^T W.
+//   sweep workspace           Kstar, Gstar, Beta: ld x Mcap;  P1, P2: Dp x Mcap;  stats: Mcap x 4
+#include "../../include/slsgp.h"
+
+#include "common.cuh"
+#include "dense.cuh"
+#include "gram.cuh"
+#include "map.cuh"
+#include "sweep.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace slsgp;
+
+namespace
+{
+    constexpr double kPi = 3.14159265358979323846;
+
+    struct DevBuf
+    {
+        void*  p     = nullptr;
+        size_t bytes = 0;
+    };
+
+    struct Phase
+    {
+        cudaEvent_t start = nullptr, stop = nullptr;
+        bool        valid = false;
+    };
+} // namespace
+
+struct slsgp_ctx
+{
+    int          device     = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string  err;
+    unsigned     compat     = SLSGP_COMPAT_SE_XGRAD_2X;
+    int          sweep_mode = SLSGP_SWEEP_FP64;
+    uint64_t     launches   = 0;
+
+    int    N = 0, D = 0, ld = 0, Dp = 0, ldx = 0;
+    int    kernel_type = 0;
+    double noise       = 0.0;
+    double logdet_host = 0.0;
+    bool   has_data = false, has_gram = false, has_factor = false, has_W = false, has_inverse = false,
+         has_alpha = false;
+    std::vector<double> theta_host;
+
+    DevBuf X, Xpad, XT1, theta, inv_l, K, L, W, Kinv, T, y, alpha, Kalpha, vec, scalars, info, fbest, fbest_idx;
+    DevBuf pref_off, pref_idx, slot_off, slot_list, loglik, contrib, grad_y, Ymat, g_l;
+    int    P = 0, pref_total = 0;
+    DevBuf Xq, Kstar, Gstar, Beta, P1, P2, stats, o_mu, o_sigma, o_dmu, o_dsigma, o_val, o_grad, am_part, am_acc;
+    long long Mcap = 0;
+
+    double* pinned       = nullptr; // small host staging area
+    size_t  pinned_bytes = 0;
+
+    std::map<std::string, Phase> phases;
+};
+
+namespace
+{
+    // ---------------------------------------------------------------------------------------------------------
+    // error plumbing
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status fail(slsgp_ctx* c, slsgp_status s, const std::string& msg)
+    {
+        if (c) c->err = msg;
+        return s;
+    }
+
+#define CUDA_TRY(expr)                                                                                             \
+    do                                                                                                             \
+    {                                                                                                              \
+        cudaError_t e_ = (expr);                                                                                   \
+        if (e_ != cudaSuccess)                                                                                     \
+            return fail(ctx, SLSGP_ERR_CUDA,                                                                       \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_) + " (" __FILE__ ":" +                  \
+                            std::to_string(__LINE__) + ")");                                                       \
+    } while (0)
+
+#define TRY(expr)                                                                                                  \
+    do                                                                                                             \
+    {                                                                                                              \
+        slsgp_status s_ = (expr);                                                                                  \
+        if (s_ != SLSGP_OK) return s_;                                                                             \
+    } while (0)
+
+#define LAUNCH_CHECK()                                                                                             \
+    do                                                                                                             \
+    {                                                                                                              \
+        ++ctx->launches;                                                                                           \
+        CUDA_TRY(cudaGetLastError());                                                                              \
+    } while (0)
+
+    slsgp_status ensure(slsgp_ctx* ctx, DevBuf& b, size_t bytes)
+    {
+        if (b.bytes >= bytes && b.p) return SLSGP_OK;
+        if (b.p) CUDA_TRY(cudaFree(b.p));
+        b.p = nullptr, b.bytes = 0;
+        cudaError_t e = cudaMalloc(&b.p, bytes);
+        if (e != cudaSuccess)
+        {
+            cudaGetLastError();
+            return fail(ctx, SLSGP_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
+        }
+        b.bytes = bytes;
+        return SLSGP_OK;
+    }
+    template <typename T> T* ptr(const DevBuf& b) { return static_cast<T*>(b.p); }
+    double*                  dp(const DevBuf& b) { return static_cast<double*>(b.p); }
+
+    slsgp_status phase_begin(slsgp_ctx* ctx, const char* name)
+    {
+        Phase& ph = ctx->phases[name];
+        if (!ph.start)
+        {
+            CUDA_TRY(cudaEventCreate(&ph.start));
+            CUDA_TRY(cudaEventCreate(&ph.stop));
+        }
+        ph.valid = false;
+        CUDA_TRY(cudaEventRecord(ph.start, ctx->stream));
+        return SLSGP_OK;
+    }
+    slsgp_status phase_end(slsgp_ctx* ctx, const char* name)
+    {
+        Phase& ph = ctx->phases[name];
+        CUDA_TRY(cudaEventRecord(ph.stop, ctx->stream));
+        ph.valid = true;
+        return SLSGP_OK;
+    }
+
+    // Strided device -> host copy of the leading n x n part of an ld x ld matrix.
+    slsgp_status copy_matrix_out(slsgp_ctx* ctx, const DevBuf& src, double* dst, int n)
+    {
+        if (!dst) return SLSGP_OK;
+        CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double) * n, src.p, sizeof(double) * ctx->ld, sizeof(double) * n, n,
+                                   cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    template <bool TA, bool TB> slsgp_status launch_gemm(slsgp_ctx* ctx, const GemmArgs& g, int batch = 1)
+    {
+        dim3 grid(g.m / TILE, g.n / TILE, batch);
+        gemm64_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // hyper-parameters -> device
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status upload_theta(slsgp_ctx* ctx, const double* theta)
+    {
+        const int D = ctx->D;
+        for (int i = 0; i <= D; ++i)
+            if (!std::isfinite(theta[i])) return fail(ctx, SLSGP_ERR_NAN, "non-finite kernel hyper-parameter");
+        ctx->theta_host.assign(theta, theta + D + 1);
+        double* h = ctx->pinned;
+        for (int i = 0; i <= D; ++i) h[i] = theta[i];
+        for (int i = 0; i < D; ++i) h[D + 1 + i] = 1.0 / theta[1 + i];
+        CUDA_TRY(cudaMemcpyAsync(ctx->theta.p, h, sizeof(double) * (D + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->inv_l.p, h + D + 1, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+        // the pinned staging area is reused by later calls: make sure the copies have consumed it
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    __global__ void pack_x_kernel(const double* __restrict__ X, int N, int D, int ld, int Dp, int ldx,
+                                  double* __restrict__ Xpad, double* __restrict__ XT1)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x; // point (column of X), 0 .. ld-1
+        if (i >= ld) return;
+        for (int d = 0; d < Dp; ++d) Xpad[(size_t) d + (size_t) i * Dp] = (i < N && d < D) ? X[(size_t) d + (size_t) i * D] : 0.0;
+        for (int t = 0; t < ldx; ++t)
+        {
+            double v = 0.0;
+            if (i < N) v = (t < D) ? X[(size_t) t + (size_t) i * D] : (t == D ? 1.0 : 0.0);
+            XT1[(size_t) i + (size_t) t * ld] = v;
+        }
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // K1 / K2 / K3 on the context's current data
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status do_gram(slsgp_ctx* ctx, int kernel_type, const double* theta, double noise)
+    {
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_gram before slsgp_set_data");
+        if (kernel_type != 0 && kernel_type != 1) return fail(ctx, SLSGP_ERR_INVALID, "unknown kernel_type");
+        if (!std::isfinite(noise)) return fail(ctx, SLSGP_ERR_NAN, "non-finite noise level");
+        TRY(upload_theta(ctx, theta));
+        ctx->kernel_type = kernel_type, ctx->noise = noise;
+        ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        TRY(phase_begin(ctx, "gram"));
+        const int nt = ctx->ld / TILE;
+        gram_tile_kernel<0><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld,
+                                                                         dp(ctx->theta), dp(ctx->inv_l), noise,
+                                                                         kernel_type, dp(ctx->K), nullptr, nullptr);
+        LAUNCH_CHECK();
+        TRY(phase_end(ctx, "gram"));
+        ctx->has_gram = true;
+        return SLSGP_OK;
+    }
+
+    slsgp_status do_factor(slsgp_ctx* ctx, double* logdet_out)
+    {
+        if (!ctx->has_gram) return fail(ctx, SLSGP_ERR_STATE, "slsgp_factor before slsgp_gram");
+        const int    ld = ctx->ld, nb = ld / TILE;
+        const size_t mat = sizeof(double) * (size_t) ld * ld;
+        ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        TRY(phase_begin(ctx, "factor"));
+        CUDA_TRY(cudaMemcpyAsync(ctx->L.p, ctx->K.p, mat, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->W.p, 0, mat, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->info.p, 0, sizeof(int), ctx->stream));
+        double* L = dp(ctx->L);
+        double* W = dp(ctx->W);
+        for (int kb = 0; kb < nb; ++kb)
+        {
+            const size_t dg = (size_t) kb * TILE * ((size_t) ld + 1);
+            potf2_inverse_kernel<<<1, 256, 0, ctx->stream>>>(L + dg, ld, W + dg, ld, kb * TILE, ptr<int>(ctx->info));
+            LAUNCH_CHECK();
+            const int rem = ld - (kb + 1) * TILE;
+            if (rem <= 0) break;
+            double* L21 = L + dg + TILE;                          // rows below the diagonal block
+            double* A22 = L + dg + TILE * ((size_t) ld + 1);      // trailing matrix
+            // panel: L21 <- A21 * W_kk^T   (== A21 * L_kk^-T)
+            GemmArgs p = gemm_args(L21, W + dg, L21, rem, TILE, TILE, ld, ld, ld, 1.0, 0.0);
+            TRY((launch_gemm<false, true>(ctx, p)));
+            // trailing update: A22 <- A22 - L21 * L21^T (lower tiles)
+            GemmArgs u   = gemm_args(L21, L21, A22, rem, rem, TILE, ld, ld, ld, -1.0, 1.0);
+            u.lower_only = 1;
+            TRY((launch_gemm<false, true>(ctx, u)));
+        }
+        zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
+        LAUNCH_CHECK();
+        logdet_kernel<<<1, 256, 0, ctx->stream>>>(L, ctx->N, ld, dp(ctx->scalars) + 8);
+        LAUNCH_CHECK();
+        TRY(phase_end(ctx, "factor"));
+        int    info = 0;
+        double logdet = 0.0;
+        CUDA_TRY(cudaMemcpyAsync(&info, ctx->info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(&logdet, dp(ctx->scalars) + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (info != 0)
+            return fail(ctx, SLSGP_ERR_NOT_SPD,
+                        "Cholesky: non-positive pivot at index " + std::to_string(info - 1) + " (K_y is not SPD)");
+        ctx->logdet_host = logdet;
+        if (logdet_out) *logdet_out = logdet;
+        ctx->has_factor = true;
+        return SLSGP_OK;
+    }
+
+    // W = L^-1 by recursive doubling over the already-inverted 64 x 64 diagonal blocks:
+    //   [L11 0; L21 L22]^-1 = [W11 0; -W22 L21 W11, W22]
+    slsgp_status do_trtri(slsgp_ctx* ctx)
+    {
+        if (ctx->has_W) return SLSGP_OK;
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "inverse requested before slsgp_factor");
+        const int ld = ctx->ld;
+        double *  L = dp(ctx->L), *W = dp(ctx->W), *T = dp(ctx->T);
+        for (int s = TILE; s < ld; s *= 2)
+        {
+            const int       npairs = (ld + 2 * s - 1) / (2 * s);
+            const long long stride = 2LL * s * ((long long) ld + 1);
+            GemmArgs        a      = gemm_args(L + s, W, T + s, s, s, s, ld, ld, ld, 1.0, 0.0); // T = L21 W11
+            a.sA = a.sB = a.sC = stride;
+            a.k_lo_mode        = 1;
+            a.row0 = s, a.row_step = 2 * s, a.row_limit = ld;
+            TRY((launch_gemm<false, false>(ctx, a, npairs)));
+            GemmArgs b = gemm_args(W + (size_t) s * ((size_t) ld + 1), T + s, W + s, s, s, s, ld, ld, ld, -1.0, 0.0);
+            b.sA = b.sB = b.sC = stride; // W21 = -W22 T
+            b.k_hi_mode        = 1;
+            b.row0 = s, b.row_step = 2 * s, b.row_limit = ld;
+            TRY((launch_gemm<false, false>(ctx, b, npairs)));
+        }
+        ctx->has_W = true;
+        return SLSGP_OK;
+    }
+
+    slsgp_status do_inverse(slsgp_ctx* ctx)
+    {
+        if (ctx->has_inverse) return SLSGP_OK;
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "slsgp_inverse before slsgp_factor");
+        TRY(phase_begin(ctx, "inverse"));
+        TRY(do_trtri(ctx));
+        const int ld = ctx->ld;
+        GemmArgs  g  = gemm_args(dp(ctx->W), dp(ctx->W), dp(ctx->Kinv), ld, ld, ld, ld, ld, ld, 1.0, 0.0);
+        g.lower_only = 1, g.k_lo_mode = 2; // Kinv = W^T W, lower tiles, k >= max(tile row, tile col)
+        TRY((launch_gemm<true, false>(ctx, g)));
+        symmetrize_kernel<<<dim3(ld / TILE, ld / TILE), 256, 0, ctx->stream>>>(dp(ctx->Kinv), ld);
+        LAUNCH_CHECK();
+        TRY(phase_end(ctx, "inverse"));
+        ctx->has_inverse = true;
+        return SLSGP_OK;
+    }
+
+    // alpha = Kinv y (y already on the device in ctx->y), then f_best.
+    slsgp_status do_alpha(slsgp_ctx* ctx)
+    {
+        TRY(do_inverse(ctx));
+        TRY(phase_begin(ctx, "alpha"));
+        const int ld = ctx->ld, blocks = (ld * 32 + 255) / 256;
+        gemv_kernel<true><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->Kinv), ld, ld, dp(ctx->y), dp(ctx->alpha), 0);
+        LAUNCH_CHECK();
+        gemv_kernel<true><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->K), ld, ld, dp(ctx->alpha), dp(ctx->Kalpha), 0);
+        LAUNCH_CHECK();
+        fbest_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->Kalpha), dp(ctx->alpha), ctx->noise, ctx->N, dp(ctx->fbest),
+                                                 ptr<int>(ctx->fbest_idx));
+        LAUNCH_CHECK();
+        TRY(phase_end(ctx, "alpha"));
+        ctx->has_alpha = true;
+        return SLSGP_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // K4: one shard of Mc <= Mcap candidates already in d_Xq (D x Mc, device). Outputs are device pointers.
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status ensure_sweep_workspace(slsgp_ctx* ctx, long long want)
+    {
+        long long cap = std::min<long long>(std::max<long long>(want, 64), 16384);
+        cap           = round_up64(cap, TILE);
+        if (ctx->Mcap >= cap) return SLSGP_OK;
+        const size_t col = sizeof(double) * (size_t) ctx->ld;
+        TRY(ensure(ctx, ctx->Kstar, col * cap));
+        TRY(ensure(ctx, ctx->Gstar, col * cap));
+        TRY(ensure(ctx, ctx->Beta, col * cap));
+        TRY(ensure(ctx, ctx->P1, sizeof(double) * (size_t) ctx->Dp * cap));
+        TRY(ensure(ctx, ctx->P2, sizeof(double) * (size_t) ctx->Dp * cap));
+        TRY(ensure(ctx, ctx->stats, sizeof(double4) * (size_t) cap));
+        TRY(ensure(ctx, ctx->Xq, sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_mu, sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_sigma, sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_val, sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_dmu, sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_dsigma, sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_grad, sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->am_part, sizeof(ArgMax) * 1024));
+        TRY(ensure(ctx, ctx->am_acc, sizeof(ArgMax)));
+        ctx->Mcap = cap;
+        return SLSGP_OK;
+    }
+
+    slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
+                             SweepOut out)
+    {
+        const int       ld = ctx->ld, D = ctx->D, Dp = ctx->Dp;
+        const long long Mp = round_up64(Mc, TILE);
+        const bool      want_grad = out.dmu || out.dsigma || out.grad;
+        const double    se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
+
+        kstar_tile_kernel<<<dim3(ld / TILE, (unsigned) (Mp / TILE)), 256, 0, ctx->stream>>>(
+            dp(ctx->X), ctx->N, D, ld, d_Xq, Mc, dp(ctx->theta), dp(ctx->inv_l), ctx->kernel_type, se_factor,
+            dp(ctx->Kstar), dp(ctx->Gstar));
+        LAUNCH_CHECK();
+        // Beta = Kinv * Kstar
+        GemmArgs g = gemm_args(dp(ctx->Kinv), dp(ctx->Kstar), dp(ctx->Beta), ld, (int) Mp, ld, ld, ld, ld, 1.0, 0.0);
+        TRY((launch_gemm<false, false>(ctx, g)));
+        column_reduce_kernel<<<(unsigned) ((Mc * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+            dp(ctx->Kstar), dp(ctx->Gstar), dp(ctx->Beta), dp(ctx->alpha), ld, Mc, ptr<double4>(ctx->stats));
+        LAUNCH_CHECK();
+        if (want_grad)
+        {
+            GemmArgs p1 = gemm_args(dp(ctx->Xpad), dp(ctx->Gstar), dp(ctx->P1), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
+            TRY((launch_gemm<false, false>(ctx, p1)));
+            GemmArgs p2 = gemm_args(dp(ctx->Xpad), dp(ctx->Beta), dp(ctx->P2), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
+            TRY((launch_gemm<false, false>(ctx, p2)));
+        }
+        sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
+            d_Xq, D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), Dp, dp(ctx->theta), dp(ctx->fbest),
+            acq_type, ucb_beta, out);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    slsgp_status require_model(slsgp_ctx* ctx)
+    {
+        if (!ctx->has_alpha)
+            return fail(ctx, SLSGP_ERR_STATE,
+                        "sweep needs a fitted model: slsgp_set_data, slsgp_gram, slsgp_factor, slsgp_solve_alpha");
+        return SLSGP_OK;
+    }
+} // namespace
+
+// =============================================================================================================
+// C ABI
+// =============================================================================================================
+extern "C"
+{
+    const char* slsgp_status_string(slsgp_status s)
+    {
+        switch (s)
+        {
+            case SLSGP_OK: return "ok";
+            case SLSGP_ERR_INVALID: return "invalid argument";
+            case SLSGP_ERR_STATE: return "call-order error";
+            case SLSGP_ERR_NOT_SPD: return "matrix is not symmetric positive definite";
+            case SLSGP_ERR_NAN: return "non-finite input";
+            case SLSGP_ERR_CUDA: return "CUDA error";
+            case SLSGP_ERR_NOMEM: return "out of device memory";
+        }
+        return "unknown";
+    }
+
+    slsgp_status slsgp_ctx_create(int device, slsgp_ctx** ctx_out)
+    {
+        if (!ctx_out) return SLSGP_ERR_INVALID;
+        *ctx_out = nullptr;
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0 || device < 0 || device >= count)
+        {
+            cudaGetLastError();
+            return SLSGP_ERR_CUDA; // no CPU fallback by design
+        }
+        slsgp_ctx* ctx = new slsgp_ctx;
+        ctx->device    = device;
+        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
+        {
+            delete ctx;
+            return SLSGP_ERR_CUDA;
+        }
+        ctx->stream       = ctx->own_stream;
+        ctx->pinned_bytes = 1 << 16;
+        if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess)
+        {
+            cudaStreamDestroy(ctx->own_stream);
+            delete ctx;
+            return SLSGP_ERR_CUDA;
+        }
+        *ctx_out = ctx;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_ctx_destroy(slsgp_ctx* ctx)
+    {
+        if (!ctx) return SLSGP_OK;
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        DevBuf* all[] = {&ctx->X, &ctx->Xpad, &ctx->XT1, &ctx->theta, &ctx->inv_l, &ctx->K, &ctx->L, &ctx->W,
+                         &ctx->Kinv, &ctx->T, &ctx->y, &ctx->alpha, &ctx->Kalpha, &ctx->vec, &ctx->scalars,
+                         &ctx->info, &ctx->fbest, &ctx->fbest_idx, &ctx->pref_off, &ctx->pref_idx, &ctx->slot_off,
+                         &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
+                         &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
+                         &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
+                         &ctx->am_acc};
+        for (DevBuf* b : all)
+            if (b->p) cudaFree(b->p);
+        for (auto& kv : ctx->phases)
+        {
+            if (kv.second.start) cudaEventDestroy(kv.second.start);
+            if (kv.second.stop) cudaEventDestroy(kv.second.stop);
+        }
+        if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        return SLSGP_OK;
+    }
+
+    const char* slsgp_last_error(const slsgp_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+    slsgp_status slsgp_set_compat_flags(slsgp_ctx* ctx, unsigned flags)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        ctx->compat = flags;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_set_sweep_mode(slsgp_ctx* ctx, slsgp_sweep_mode mode)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (mode != SLSGP_SWEEP_FP64)
+            return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR is not available in this build");
+        ctx->sweep_mode = mode;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_set_stream(slsgp_ctx* ctx, void* cuda_stream)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->own_stream;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_synchronize(slsgp_ctx* ctx)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    uint64_t slsgp_launch_count(const slsgp_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+    double slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase)
+    {
+        if (!ctx || !phase) return -1.0;
+        auto it = ctx->phases.find(phase);
+        if (it == ctx->phases.end() || !it->second.valid) return -1.0;
+        if (cudaEventSynchronize(it->second.stop) != cudaSuccess) return -1.0;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, it->second.start, it->second.stop) != cudaSuccess) return -1.0;
+        return (double) ms;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status slsgp_set_data(slsgp_ctx* ctx, const double* X, int N, int D)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!X || N <= 0 || D <= 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_set_data: X null or N, D not positive");
+        if ((size_t) (2 * D + 2) * sizeof(double) > ctx->pinned_bytes)
+            return fail(ctx, SLSGP_ERR_INVALID, "slsgp_set_data: D too large");
+        for (size_t i = 0; i < (size_t) N * D; ++i)
+            if (!std::isfinite(X[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_set_data: non-finite coordinate in X");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        ctx->N = N, ctx->D = D, ctx->ld = round_up(N, TILE), ctx->Dp = round_up(D, TILE), ctx->ldx = round_up(D + 1, TILE);
+        ctx->has_data = ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        ctx->Mcap = 0; // sweep workspace depends on ld
+        const size_t ld = ctx->ld, mat = sizeof(double) * ld * ld;
+        TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) N * D));
+        TRY(ensure(ctx, ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld));
+        TRY(ensure(ctx, ctx->XT1, sizeof(double) * ld * ctx->ldx));
+        TRY(ensure(ctx, ctx->theta, sizeof(double) * (D + 1)));
+        TRY(ensure(ctx, ctx->inv_l, sizeof(double) * D));
+        TRY(ensure(ctx, ctx->K, mat));
+        TRY(ensure(ctx, ctx->L, mat));
+        TRY(ensure(ctx, ctx->W, mat));
+        TRY(ensure(ctx, ctx->Kinv, mat));
+        TRY(ensure(ctx, ctx->T, mat));
+        TRY(ensure(ctx, ctx->y, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->alpha, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->Kalpha, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->vec, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->grad_y, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->Ymat, sizeof(double) * ld * ctx->ldx));
+        TRY(ensure(ctx, ctx->g_l, sizeof(double) * D));
+        TRY(ensure(ctx, ctx->scalars, sizeof(double) * 32));
+        TRY(ensure(ctx, ctx->info, sizeof(int)));
+        TRY(ensure(ctx, ctx->fbest, sizeof(double)));
+        TRY(ensure(ctx, ctx->fbest_idx, sizeof(int)));
+        CUDA_TRY(cudaMemcpyAsync(ctx->X.p, X, sizeof(double) * (size_t) N * D, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemsetAsync(ctx->y.p, 0, sizeof(double) * ld, ctx->stream));
+        pack_x_kernel<<<(ctx->ld + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), N, D, ctx->ld, ctx->Dp, ctx->ldx,
+                                                                     dp(ctx->Xpad), dp(ctx->XT1));
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->has_data = true;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_gram(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, double noise,
+                            double* K_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!theta) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_gram: theta is null");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(do_gram(ctx, (int) kernel_type, theta, noise));
+        return copy_matrix_out(ctx, ctx->K, K_out, ctx->N);
+    }
+
+    slsgp_status slsgp_factor(slsgp_ctx* ctx, double* logdet_out, double* L_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(do_factor(ctx, logdet_out));
+        return copy_matrix_out(ctx, ctx->L, L_out, ctx->N);
+    }
+
+    slsgp_status slsgp_inverse(slsgp_ctx* ctx, double* Kinv_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(do_inverse(ctx));
+        return copy_matrix_out(ctx, ctx->Kinv, Kinv_out, ctx->N);
+    }
+
+    slsgp_status slsgp_solve_alpha(slsgp_ctx* ctx, const double* y, double* alpha_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!y) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_solve_alpha: y is null");
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "slsgp_solve_alpha before slsgp_factor");
+        for (int i = 0; i < ctx->N; ++i)
+            if (!std::isfinite(y[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_solve_alpha: non-finite y");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(do_alpha(ctx));
+        if (alpha_out)
+            CUDA_TRY(cudaMemcpyAsync(alpha_out, ctx->alpha.p, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_get_f_best(slsgp_ctx* ctx, double* f_best_out, int* index_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        TRY(require_model(ctx));
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        if (f_best_out)
+            CUDA_TRY(cudaMemcpyAsync(f_best_out, ctx->fbest.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        if (index_out)
+            CUDA_TRY(cudaMemcpyAsync(index_out, ctx->fbest_idx.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // K4
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status slsgp_acq_batch_device(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta,
+                                        const double* d_Xq, int64_t M, double* d_mu, double* d_sigma,
+                                        double* d_dmu, double* d_dsigma, double* d_val, double* d_grad)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (M < 0 || (M > 0 && !d_Xq)) return fail(ctx, SLSGP_ERR_INVALID, "acq_batch: bad M or null Xq");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB)
+            return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        TRY(require_model(ctx));
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(ensure_sweep_workspace(ctx, M));
+        TRY(phase_begin(ctx, "sweep"));
+        const int D = ctx->D;
+        for (int64_t m0 = 0; m0 < M; m0 += ctx->Mcap)
+        {
+            const long long Mc = std::min<long long>(ctx->Mcap, M - m0);
+            SweepOut        o;
+            o.mu     = d_mu ? d_mu + m0 : nullptr;
+            o.sigma  = d_sigma ? d_sigma + m0 : nullptr;
+            o.val    = d_val ? d_val + m0 : nullptr;
+            o.dmu    = d_dmu ? d_dmu + (size_t) m0 * D : nullptr;
+            o.dsigma = d_dsigma ? d_dsigma + (size_t) m0 * D : nullptr;
+            o.grad   = d_grad ? d_grad + (size_t) m0 * D : nullptr;
+            TRY(sweep_shard(ctx, (int) acq_type, ucb_beta, d_Xq + (size_t) m0 * D, Mc, o));
+        }
+        TRY(phase_end(ctx, "sweep"));
+        return SLSGP_OK;
+    }
+
+    // Host-buffer form shared by slsgp_posterior_batch and slsgp_acq_batch: per shard, H2D the candidates, sweep,
+    // D2H whichever outputs were asked for.
+    static slsgp_status host_sweep(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* Xq, int64_t M,
+                                   double* mu, double* sigma, double* dmu, double* dsigma, double* val, double* grad)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (M < 0 || (M > 0 && !Xq)) return fail(ctx, SLSGP_ERR_INVALID, "batch: bad M or null Xq");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB)
+            return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        TRY(require_model(ctx));
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(ensure_sweep_workspace(ctx, M));
+        TRY(phase_begin(ctx, "sweep"));
+        const int D = ctx->D;
+        for (int64_t m0 = 0; m0 < M; m0 += ctx->Mcap)
+        {
+            const long long Mc = std::min<long long>(ctx->Mcap, M - m0);
+            CUDA_TRY(cudaMemcpyAsync(ctx->Xq.p, Xq + (size_t) m0 * D, sizeof(double) * (size_t) Mc * D,
+                                     cudaMemcpyHostToDevice, ctx->stream));
+            SweepOut o;
+            o.mu = mu ? dp(ctx->o_mu) : nullptr, o.sigma = sigma ? dp(ctx->o_sigma) : nullptr;
+            o.val = val ? dp(ctx->o_val) : nullptr, o.dmu = dmu ? dp(ctx->o_dmu) : nullptr;
+            o.dsigma = dsigma ? dp(ctx->o_dsigma) : nullptr, o.grad = grad ? dp(ctx->o_grad) : nullptr;
+            TRY(sweep_shard(ctx, acq_type, ucb_beta, dp(ctx->Xq), Mc, o));
+            const size_t sv = sizeof(double) * (size_t) Mc, sg = sv * D;
+            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + m0, o.mu, sv, cudaMemcpyDeviceToHost, ctx->stream));
+            if (sigma) CUDA_TRY(cudaMemcpyAsync(sigma + m0, o.sigma, sv, cudaMemcpyDeviceToHost, ctx->stream));
+            if (val) CUDA_TRY(cudaMemcpyAsync(val + m0, o.val, sv, cudaMemcpyDeviceToHost, ctx->stream));
+            if (dmu) CUDA_TRY(cudaMemcpyAsync(dmu + (size_t) m0 * D, o.dmu, sg, cudaMemcpyDeviceToHost, ctx->stream));
+            if (dsigma)
+                CUDA_TRY(cudaMemcpyAsync(dsigma + (size_t) m0 * D, o.dsigma, sg, cudaMemcpyDeviceToHost, ctx->stream));
+            if (grad) CUDA_TRY(cudaMemcpyAsync(grad + (size_t) m0 * D, o.grad, sg, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TRY(phase_end(ctx, "sweep"));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_posterior_batch(slsgp_ctx* ctx, const double* Xq, int64_t M, double* mu_out,
+                                       double* sigma_out, double* dmu_out, double* dsigma_out)
+    {
+        return host_sweep(ctx, SLSGP_ACQ_EXPECTED_IMPROVEMENT, 0.0, Xq, M, mu_out, sigma_out, dmu_out, dsigma_out,
+                          nullptr, nullptr);
+    }
+
+    slsgp_status slsgp_acq_batch(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, const double* Xq,
+                                 int64_t M, double* val_out, double* grad_out)
+    {
+        return host_sweep(ctx, (int) acq_type, ucb_beta, Xq, M, nullptr, nullptr, nullptr, nullptr, val_out, grad_out);
+    }
+
+    slsgp_status slsgp_candidates(slsgp_ctx* ctx, uint64_t seed, int64_t first, int64_t count, double* Xq_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data || !Xq_out || count < 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_candidates: bad arguments");
+        for (int64_t i = 0; i < count; ++i)
+            for (int d = 0; d < ctx->D; ++d) Xq_out[(size_t) i * ctx->D + d] = candidate_coord(seed, first + i, d);
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_acq_argmax(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
+                                  int64_t first, int64_t count, double* x_best_out, double* val_best_out,
+                                  int64_t* index_best_out, double* grad_best_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (count <= 0 || first < 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_acq_argmax: empty candidate range");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB)
+            return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        TRY(require_model(ctx));
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(ensure_sweep_workspace(ctx, count));
+        const int D = ctx->D;
+        ArgMax    init;
+        init.v = 0.0, init.i = -1;
+        std::memcpy(ctx->pinned, &init, sizeof(init));
+        CUDA_TRY(cudaMemcpyAsync(ctx->am_acc.p, ctx->pinned, sizeof(ArgMax), cudaMemcpyHostToDevice, ctx->stream));
+        TRY(phase_begin(ctx, "sweep"));
+        for (int64_t m0 = 0; m0 < count; m0 += ctx->Mcap)
+        {
+            const long long Mc = std::min<long long>(ctx->Mcap, count - m0);
+            candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, ctx->stream>>>(seed, first + m0, Mc, D,
+                                                                                         dp(ctx->Xq));
+            LAUNCH_CHECK();
+            SweepOut o;
+            o.mu = o.sigma = o.dmu = o.dsigma = nullptr;
+            o.val  = dp(ctx->o_val);
+            o.grad = nullptr; // the winner's gradient is evaluated once at the end
+            TRY(sweep_shard(ctx, (int) acq_type, ucb_beta, dp(ctx->Xq), Mc, o));
+            const int nblk = (int) std::min<long long>(1024, (Mc + 255) / 256);
+            argmax_partial_kernel<<<nblk, 256, 0, ctx->stream>>>(dp(ctx->o_val), Mc, first + m0, ptr<ArgMax>(ctx->am_part));
+            LAUNCH_CHECK();
+            argmax_final_kernel<<<1, 256, 0, ctx->stream>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
+            LAUNCH_CHECK();
+        }
+        TRY(phase_end(ctx, "sweep"));
+        ArgMax best;
+        CUDA_TRY(cudaMemcpyAsync(&best, ctx->am_acc.p, sizeof(ArgMax), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (best.i < 0) return fail(ctx, SLSGP_ERR_NAN, "slsgp_acq_argmax: every candidate evaluated to NaN");
+        std::vector<double> xb((size_t) D);
+        for (int d = 0; d < D; ++d) xb[(size_t) d] = candidate_coord(seed, best.i, d);
+        if (x_best_out) std::memcpy(x_best_out, xb.data(), sizeof(double) * (size_t) D);
+        if (val_best_out) *val_best_out = best.v;
+        if (index_best_out) *index_best_out = best.i;
+        if (grad_best_out) TRY(slsgp_acq_batch(ctx, acq_type, ucb_beta, xb.data(), 1, nullptr, grad_best_out));
+        return SLSGP_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // K5 / K6
+    // ---------------------------------------------------------------------------------------------------------
+    slsgp_status slsgp_set_preferences(slsgp_ctx* ctx, const uint32_t* offsets, const uint32_t* idx, int P)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_set_preferences before slsgp_set_data");
+        if (P < 0 || (P > 0 && (!offsets || !idx))) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_set_preferences: bad arguments");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const int total = P > 0 ? (int) offsets[P] : 0;
+        for (int t = 0; t < P; ++t)
+            if (offsets[t + 1] < offsets[t] + 2) return fail(ctx, SLSGP_ERR_INVALID, "preference tuple with fewer than 2 members");
+        std::vector<uint32_t> slot_off((size_t) ctx->N + 1, 0), slot_list((size_t) std::max(total, 1));
+        for (int s = 0; s < total; ++s)
+        {
+            if (idx[s] >= (uint32_t) ctx->N) return fail(ctx, SLSGP_ERR_INVALID, "preference index out of range");
+            ++slot_off[idx[s] + 1];
+        }
+        for (int i = 0; i < ctx->N; ++i) slot_off[(size_t) i + 1] += slot_off[(size_t) i];
+        std::vector<uint32_t> cursor(slot_off.begin(), slot_off.end() - 1);
+        for (int s = 0; s < total; ++s) slot_list[cursor[idx[s]]++] = (uint32_t) s;
+        TRY(ensure(ctx, ctx->pref_off, sizeof(uint32_t) * ((size_t) P + 1)));
+        TRY(ensure(ctx, ctx->pref_idx, sizeof(uint32_t) * (size_t) std::max(total, 1)));
+        TRY(ensure(ctx, ctx->slot_off, sizeof(uint32_t) * ((size_t) ctx->N + 1)));
+        TRY(ensure(ctx, ctx->slot_list, sizeof(uint32_t) * (size_t) std::max(total, 1)));
+        TRY(ensure(ctx, ctx->loglik, sizeof(double) * (size_t) std::max(P, 1)));
+        TRY(ensure(ctx, ctx->contrib, sizeof(double) * (size_t) std::max(total, 1)));
+        if (P > 0)
+        {
+            CUDA_TRY(cudaMemcpyAsync(ctx->pref_off.p, offsets, sizeof(uint32_t) * ((size_t) P + 1), cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->pref_idx.p, idx, sizeof(uint32_t) * (size_t) total, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(ctx->slot_list.p, slot_list.data(), sizeof(uint32_t) * (size_t) total, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->slot_off.p, slot_off.data(), sizeof(uint32_t) * ((size_t) ctx->N + 1), cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->P = P, ctx->pref_total = total;
+        return SLSGP_OK;
+    }
+
+    // GetLogOfLogNormalDist{,Derivative} (mathtoolbox probability-distributions.cpp:47-58): O(D) scalar prior terms,
+    // evaluated on the host from the caller's x.
+    static double log_lognormal(double x, double mu, double s2)
+    {
+        const double lx = std::log(x), r = lx - mu;
+        return -lx - 0.5 * std::log(2.0 * kPi * s2) - 0.5 * (r * r) / s2;
+    }
+    static double log_lognormal_derivative(double x, double mu, double s2) { return (mu - std::log(x) - s2) / (x * s2); }
+
+    // Shared GP part of both objectives, for y already in ctx->y and the model (K, L, [Kinv]) current:
+    //   alpha = Kinv y; returns -1/2 y.alpha - 1/2 logdet - N/2 log(2 pi); if want_hyper also the data-fit part of the
+    //   gradient wrt (a, b, l_1..l_D) into g_hyper (D + 2 values, reference ordering a, b, r).
+    static slsgp_status gp_term(slsgp_ctx* ctx, double logdet, bool want_hyper, double* value, double* g_hyper)
+    {
+        const int ld = ctx->ld, N = ctx->N, D = ctx->D;
+        TRY(do_alpha(ctx));
+        gp_scalars_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->y), dp(ctx->alpha), dp(ctx->Kinv), N, ld, dp(ctx->scalars));
+        LAUNCH_CHECK();
+        if (want_hyper)
+        {
+            const int nt = ld / TILE;
+            gram_tile_kernel<1><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(
+                dp(ctx->X), N, D, ld, dp(ctx->theta), dp(ctx->inv_l), ctx->noise, ctx->kernel_type, dp(ctx->T),
+                dp(ctx->Kinv), dp(ctx->alpha));
+            LAUNCH_CHECK();
+            GemmArgs g = gemm_args(dp(ctx->T), dp(ctx->XT1), dp(ctx->Ymat), ld, ctx->ldx, ld, ld, ld, ld, 1.0, 0.0);
+            TRY((launch_gemm<false, false>(ctx, g)));
+            lengthscale_grad_kernel<<<D, 256, 0, ctx->stream>>>(dp(ctx->XT1), dp(ctx->Ymat), N, ld, D, dp(ctx->theta), dp(ctx->g_l));
+            LAUNCH_CHECK();
+        }
+        double sc[3];
+        CUDA_TRY(cudaMemcpyAsync(sc, ctx->scalars.p, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
+        std::vector<double> gl((size_t) D);
+        if (want_hyper) CUDA_TRY(cudaMemcpyAsync(gl.data(), ctx->g_l.p, sizeof(double) * (size_t) D, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const double y_alpha = sc[0], alpha_alpha = sc[1], tr_kinv = sc[2];
+        *value = -0.5 * y_alpha + -0.5 * logdet + -0.5 * N * std::log(2.0 * kPi);
+        if (want_hyper)
+        {
+            const double a = ctx->theta_host[0], b = ctx->noise;
+            // dK/da = K_f / a and K_f = K_y - b I:  1/2 alpha^T K_f alpha - 1/2 tr(Kinv K_f), all over a
+            g_hyper[0] = 0.5 / a * ((y_alpha - b * alpha_alpha) - (N - b * tr_kinv));
+            g_hyper[1] = 0.5 * alpha_alpha - 0.5 * tr_kinv; // dK/db = I
+            for (int t = 0; t < D; ++t) g_hyper[2 + t] = gl[(size_t) t];
+        }
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_map_objective_pref(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* x, int n_x,
+                                          int use_map, double default_a, double default_r, double default_b,
+                                          double prior_var, double btl_scale, double* f_out, double* grad_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_map_objective_pref before slsgp_set_data");
+        const int N = ctx->N, D = ctx->D;
+        if (!x || !f_out || n_x != (use_map ? N + 2 + D : N))
+            return fail(ctx, SLSGP_ERR_INVALID, "slsgp_map_objective_pref: x/f_out null or n_x != N (+ 2 + D)");
+        for (int i = 0; i < n_x; ++i)
+            if (!std::isfinite(x[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_map_objective_pref: non-finite x");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(phase_begin(ctx, "map"));
+        double logdet = 0.0;
+        if (use_map)
+        {
+            std::vector<double> theta((size_t) D + 1);
+            theta[0] = x[N + 0];
+            for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[N + 2 + i];
+            TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[N + 1]));
+            TRY(do_factor(ctx, &logdet));
+        }
+        else
+        {
+            if (!ctx->has_factor)
+                return fail(ctx, SLSGP_ERR_STATE, "use_map_hyperparams == 0 needs slsgp_gram + slsgp_factor first");
+            logdet = ctx->logdet_host;
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        double              gp = 0.0;
+        std::vector<double> gh((size_t) D + 2);
+        const bool          want_hyper = grad_out && use_map;
+        TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
+
+        // BTL likelihood of the tuples
+        double loglik = 0.0;
+        if (ctx->P > 0)
+        {
+            btl_tuple_kernel<<<(ctx->P + 127) / 128, 128, 0, ctx->stream>>>(
+                dp(ctx->y), ptr<uint32_t>(ctx->pref_off), ptr<uint32_t>(ctx->pref_idx), ctx->P, btl_scale,
+                dp(ctx->loglik), dp(ctx->contrib), grad_out ? 1 : 0);
+            LAUNCH_CHECK();
+            sum_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->loglik), ctx->P, dp(ctx->scalars) + 4);
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(&loglik, dp(ctx->scalars) + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (grad_out)
+        {
+            btl_gather_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(
+                dp(ctx->contrib), ptr<uint32_t>(ctx->slot_off), ptr<uint32_t>(ctx->slot_list), dp(ctx->alpha), N,
+                dp(ctx->grad_y));
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(grad_out, ctx->grad_y.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        TRY(phase_end(ctx, "map"));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+
+        double obj = loglik + gp;
+        if (use_map) // log-normal hyper-priors centred on the defaults (:175-192) and their derivatives (:103-112, :69-73)
+        {
+            const double a = x[N], b = x[N + 1];
+            obj += log_lognormal(a, std::log(default_a), prior_var);
+            obj += log_lognormal(b, std::log(default_b), prior_var);
+            for (int i = 0; i < D; ++i) obj += log_lognormal(x[N + 2 + i], std::log(default_r), prior_var);
+            if (grad_out)
+            {
+                grad_out[N + 0] = gh[0] + log_lognormal_derivative(a, std::log(default_a), prior_var);
+                grad_out[N + 1] = gh[1] + log_lognormal_derivative(b, std::log(default_b), prior_var);
+                for (int i = 0; i < D; ++i)
+                    grad_out[N + 2 + i] = gh[(size_t) 2 + i] + log_lognormal_derivative(x[N + 2 + i], std::log(default_r), prior_var);
+            }
+        }
+        *f_out = obj;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_map_objective_gpr(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* y,
+                                         const double* x, double* f_out, double* grad_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_map_objective_gpr before slsgp_set_data");
+        if (!y || !x || !f_out) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_map_objective_gpr: null argument");
+        const int N = ctx->N, D = ctx->D;
+        for (int i = 0; i < D + 2; ++i)
+            if (!std::isfinite(x[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_map_objective_gpr: non-finite x");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(phase_begin(ctx, "map"));
+        std::vector<double> theta((size_t) D + 1);
+        theta[0] = x[0];
+        for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[2 + i];
+        double logdet = 0.0;
+        TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[1]));
+        TRY(do_factor(ctx, &logdet));
+        CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        double              gp = 0.0;
+        std::vector<double> gh((size_t) D + 2);
+        TRY(gp_term(ctx, logdet, grad_out != nullptr, &gp, gh.data()));
+        TRY(phase_end(ctx, "map"));
+        // fixed log-normal priors of src/gaussian-process-regressor.cpp:18-24
+        const double a_mu = std::log(0.500), a_s2 = 0.50, b_mu = std::log(1e-04), b_s2 = 0.50, r_mu = std::log(0.500), r_s2 = 0.50;
+        double       reg  = log_lognormal(x[0], a_mu, a_s2) + log_lognormal(x[1], b_mu, b_s2);
+        for (int i = 0; i < D; ++i) reg += log_lognormal(x[2 + i], r_mu, r_s2);
+        *f_out = gp + reg;
+        if (grad_out)
+        {
+            grad_out[0] = gh[0] + log_lognormal_derivative(x[0], a_mu, a_s2);
+            grad_out[1] = gh[1] + log_lognormal_derivative(x[1], b_mu, b_s2);
+            for (int i = 0; i < D; ++i) grad_out[2 + i] = gh[(size_t) 2 + i] + log_lognormal_derivative(x[2 + i], r_mu, r_s2);
+        }
+        return SLSGP_OK;
+    }
+}
