@@ -145,6 +145,10 @@ extern "C"
     slsgp_status slsgp_acq_argmax(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
                                   int64_t first, int64_t count, double* x_best_out, double* val_best_out,
                                   int64_t* index_best_out, double* grad_best_out);
+    /* Arg-max (lowest index wins ties, NaN never wins) of `count` values already on the device, e.g. the d_val of
+     * slsgp_acq_batch_device; index_best_out = index0 + position. Synchronises the context's stream. */
+    slsgp_status slsgp_argmax_device(slsgp_ctx* ctx, const double* d_val, int64_t count, int64_t index0,
+                                     double* val_best_out, int64_t* index_best_out);
     /* The generator itself, for hosts that want the same candidates (D x count, host memory). */
     slsgp_status slsgp_candidates(slsgp_ctx* ctx, uint64_t seed, int64_t first, int64_t count, double* Xq_out);
 
@@ -175,6 +179,12 @@ extern "C"
     /* Milliseconds (CUDA events on the context's stream) spent in the most recent call of the named phase:
      * "gram", "factor", "inverse", "alpha", "sweep", "map". Returns < 0 for an unknown name. */
     double       slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase);
+    /* Per-kernel device timing: while enabled, every launch of the named hot kernels is bracketed by CUDA events on
+     * the context's stream. slsgp_profile_read synchronises, returns the summed duration and launch count of
+     * `kernel` ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish", "gram",
+     * "potf2", "chol_panel", "chol_syrk") since the last read, and clears that kernel's records. */
+    slsgp_status slsgp_profile_enable(slsgp_ctx* ctx, int on);
+    slsgp_status slsgp_profile_read(slsgp_ctx* ctx, const char* kernel, double* total_ms_out, uint64_t* launches_out);
 
 #ifdef __cplusplus
 }

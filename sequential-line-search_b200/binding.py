@@ -42,6 +42,7 @@ _API = [
     ("slsgp_acq_batch_device", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
     ("slsgp_acq_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, c_dp, c_dp,
                                    C.POINTER(C.c_int64), c_dp]),
+    ("slsgp_argmax_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_dp, C.POINTER(C.c_int64)]),
     ("slsgp_candidates", C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, c_dp]),
     ("slsgp_set_preferences", C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int]),
     ("slsgp_map_objective_pref", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, C.c_double,
@@ -49,6 +50,8 @@ _API = [
     ("slsgp_map_objective_gpr", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     ("slsgp_launch_count", C.c_uint64, [C.c_void_p]),
     ("slsgp_last_phase_ms", C.c_double, [C.c_void_p, C.c_char_p]),
+    ("slsgp_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
+    ("slsgp_profile_read", C.c_int, [C.c_void_p, C.c_char_p, c_dp, C.POINTER(C.c_uint64)]),
 ]
 API_SYMBOLS = [name for name, _, _ in _API]
 
@@ -200,6 +203,11 @@ class Context:
                                               C.byref(idx), _p(grad)))
         return x, val.value, idx.value, grad
 
+    def argmax_device(self, d_val, count, index0=0):
+        val, idx = C.c_double(), C.c_int64()
+        self._check(self.lib.slsgp_argmax_device(self.h, C.c_void_p(d_val), count, index0, C.byref(val), C.byref(idx)))
+        return val.value, idx.value
+
     def candidates(self, seed, first, count):
         Xq = np.empty((self.D, count), order="F")
         self._check(self.lib.slsgp_candidates(self.h, seed, first, count, _p(Xq)))
@@ -230,6 +238,14 @@ class Context:
     # ---- introspection
     def launch_count(self):
         return int(self.lib.slsgp_launch_count(self.h))
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.slsgp_profile_enable(self.h, int(on)))
+
+    def profile_read(self, kernel):
+        ms, n = C.c_double(), C.c_uint64()
+        self._check(self.lib.slsgp_profile_read(self.h, kernel.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def phase_ms(self, name):
         return float(self.lib.slsgp_last_phase_ms(self.h, name.encode()))

@@ -69,6 +69,15 @@ struct slsgp_ctx
     size_t  pinned_bytes = 0;
 
     std::map<std::string, Phase> phases;
+
+    // per-kernel profiling (slsgp_profile_enable)
+    bool profile = false;
+    struct ProfRec
+    {
+        cudaEvent_t start, stop;
+    };
+    std::map<std::string, std::vector<ProfRec>> prof;
+    std::vector<ProfRec>                        prof_free;
 };
 
 namespace
@@ -143,6 +152,34 @@ namespace
         return SLSGP_OK;
     }
 
+    // Bracket the launches issued inside a scope with a pair of events (only while profiling is enabled).
+    struct ProfScope
+    {
+        slsgp_ctx*         ctx;
+        slsgp_ctx::ProfRec rec;
+        bool               on;
+        ProfScope(slsgp_ctx* c, const char* name) : ctx(c), on(c->profile)
+        {
+            if (!on) return;
+            if (!ctx->prof_free.empty())
+            {
+                rec = ctx->prof_free.back();
+                ctx->prof_free.pop_back();
+            }
+            else if (cudaEventCreate(&rec.start) != cudaSuccess || cudaEventCreate(&rec.stop) != cudaSuccess)
+            {
+                on = false;
+                return;
+            }
+            cudaEventRecord(rec.start, ctx->stream);
+            ctx->prof[name].push_back(rec);
+        }
+        ~ProfScope()
+        {
+            if (on) cudaEventRecord(rec.stop, ctx->stream);
+        }
+    };
+
     // Strided device -> host copy of the leading n x n part of an ld x ld matrix.
     slsgp_status copy_matrix_out(slsgp_ctx* ctx, const DevBuf& src, double* dst, int n)
     {
@@ -207,6 +244,7 @@ namespace
         ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
         TRY(phase_begin(ctx, "gram"));
         const int nt = ctx->ld / TILE;
+        ProfScope prof_scope(ctx, "gram");
         gram_tile_kernel<0><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld,
                                                                          dp(ctx->theta), dp(ctx->inv_l), noise,
                                                                          kernel_type, dp(ctx->K), nullptr, nullptr);
@@ -231,19 +269,28 @@ namespace
         for (int kb = 0; kb < nb; ++kb)
         {
             const size_t dg = (size_t) kb * TILE * ((size_t) ld + 1);
-            potf2_inverse_kernel<<<1, 256, 0, ctx->stream>>>(L + dg, ld, W + dg, ld, kb * TILE, ptr<int>(ctx->info));
-            LAUNCH_CHECK();
+            {
+                ProfScope ps(ctx, "potf2");
+                potf2_inverse_kernel<<<1, 256, 0, ctx->stream>>>(L + dg, ld, W + dg, ld, kb * TILE, ptr<int>(ctx->info));
+                LAUNCH_CHECK();
+            }
             const int rem = ld - (kb + 1) * TILE;
             if (rem <= 0) break;
             double* L21 = L + dg + TILE;                          // rows below the diagonal block
             double* A22 = L + dg + TILE * ((size_t) ld + 1);      // trailing matrix
             // panel: L21 <- A21 * W_kk^T   (== A21 * L_kk^-T)
             GemmArgs p = gemm_args(L21, W + dg, L21, rem, TILE, TILE, ld, ld, ld, 1.0, 0.0);
-            TRY((launch_gemm<false, true>(ctx, p)));
+            {
+                ProfScope ps(ctx, "chol_panel");
+                TRY((launch_gemm<false, true>(ctx, p)));
+            }
             // trailing update: A22 <- A22 - L21 * L21^T (lower tiles)
             GemmArgs u   = gemm_args(L21, L21, A22, rem, rem, TILE, ld, ld, ld, -1.0, 1.0);
             u.lower_only = 1;
-            TRY((launch_gemm<false, true>(ctx, u)));
+            {
+                ProfScope ps(ctx, "chol_syrk");
+                TRY((launch_gemm<false, true>(ctx, u)));
+            }
         }
         zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
         LAUNCH_CHECK();
@@ -362,27 +409,40 @@ namespace
         const bool      want_grad = out.dmu || out.dsigma || out.grad;
         const double    se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
 
-        kstar_tile_kernel<<<dim3(ld / TILE, (unsigned) (Mp / TILE)), 256, 0, ctx->stream>>>(
-            dp(ctx->X), ctx->N, D, ld, d_Xq, Mc, dp(ctx->theta), dp(ctx->inv_l), ctx->kernel_type, se_factor,
-            dp(ctx->Kstar), dp(ctx->Gstar));
-        LAUNCH_CHECK();
-        // Beta = Kinv * Kstar
-        GemmArgs g = gemm_args(dp(ctx->Kinv), dp(ctx->Kstar), dp(ctx->Beta), ld, (int) Mp, ld, ld, ld, ld, 1.0, 0.0);
-        TRY((launch_gemm<false, false>(ctx, g)));
-        column_reduce_kernel<<<(unsigned) ((Mc * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-            dp(ctx->Kstar), dp(ctx->Gstar), dp(ctx->Beta), dp(ctx->alpha), ld, Mc, ptr<double4>(ctx->stats));
-        LAUNCH_CHECK();
+        {
+            ProfScope ps(ctx, "sweep_kstar");
+            kstar_tile_kernel<<<dim3(ld / TILE, (unsigned) (Mp / TILE)), 256, 0, ctx->stream>>>(
+                dp(ctx->X), ctx->N, D, ld, d_Xq, Mc, dp(ctx->theta), dp(ctx->inv_l), ctx->kernel_type, se_factor,
+                dp(ctx->Kstar), dp(ctx->Gstar));
+            LAUNCH_CHECK();
+        }
+        {
+            // Beta = Kinv * Kstar
+            ProfScope ps(ctx, "sweep_gemm");
+            GemmArgs  g = gemm_args(dp(ctx->Kinv), dp(ctx->Kstar), dp(ctx->Beta), ld, (int) Mp, ld, ld, ld, ld, 1.0, 0.0);
+            TRY((launch_gemm<false, false>(ctx, g)));
+        }
+        {
+            ProfScope ps(ctx, "sweep_reduce");
+            column_reduce_kernel<<<(unsigned) ((Mc * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+                dp(ctx->Kstar), dp(ctx->Gstar), dp(ctx->Beta), dp(ctx->alpha), ld, Mc, ptr<double4>(ctx->stats));
+            LAUNCH_CHECK();
+        }
         if (want_grad)
         {
-            GemmArgs p1 = gemm_args(dp(ctx->Xpad), dp(ctx->Gstar), dp(ctx->P1), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
+            ProfScope ps(ctx, "sweep_grad_gemm");
+            GemmArgs  p1 = gemm_args(dp(ctx->Xpad), dp(ctx->Gstar), dp(ctx->P1), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
             TRY((launch_gemm<false, false>(ctx, p1)));
             GemmArgs p2 = gemm_args(dp(ctx->Xpad), dp(ctx->Beta), dp(ctx->P2), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
             TRY((launch_gemm<false, false>(ctx, p2)));
         }
-        sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
-            d_Xq, D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), Dp, dp(ctx->theta), dp(ctx->fbest),
-            acq_type, ucb_beta, out);
-        LAUNCH_CHECK();
+        {
+            ProfScope ps(ctx, "sweep_finish");
+            sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
+                d_Xq, D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), Dp, dp(ctx->theta), dp(ctx->fbest),
+                acq_type, ucb_beta, out);
+            LAUNCH_CHECK();
+        }
         return SLSGP_OK;
     }
 
@@ -463,6 +523,9 @@ extern "C"
             if (kv.second.start) cudaEventDestroy(kv.second.start);
             if (kv.second.stop) cudaEventDestroy(kv.second.stop);
         }
+        for (auto& kv : ctx->prof)
+            for (auto& r : kv.second) ctx->prof_free.push_back(r);
+        for (auto& r : ctx->prof_free) cudaEventDestroy(r.start), cudaEventDestroy(r.stop);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
@@ -513,6 +576,36 @@ extern "C"
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, it->second.start, it->second.stop) != cudaSuccess) return -1.0;
         return (double) ms;
+    }
+
+    slsgp_status slsgp_profile_enable(slsgp_ctx* ctx, int on)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        ctx->profile = on != 0;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_profile_read(slsgp_ctx* ctx, const char* kernel, double* total_ms_out, uint64_t* launches_out)
+    {
+        if (!ctx || !kernel) return SLSGP_ERR_INVALID;
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        double   total = 0.0;
+        uint64_t n     = 0;
+        auto     it    = ctx->prof.find(kernel);
+        if (it != ctx->prof.end())
+        {
+            for (auto& r : it->second)
+            {
+                float ms = 0.f;
+                CUDA_TRY(cudaEventElapsedTime(&ms, r.start, r.stop));
+                total += ms, ++n;
+                ctx->prof_free.push_back(r);
+            }
+            it->second.clear();
+        }
+        if (total_ms_out) *total_ms_out = total;
+        if (launches_out) *launches_out = n;
+        return SLSGP_OK;
     }
 
     // ---------------------------------------------------------------------------------------------------------
@@ -696,6 +789,32 @@ extern "C"
                                  int64_t M, double* val_out, double* grad_out)
     {
         return host_sweep(ctx, (int) acq_type, ucb_beta, Xq, M, nullptr, nullptr, nullptr, nullptr, val_out, grad_out);
+    }
+
+    slsgp_status slsgp_argmax_device(slsgp_ctx* ctx, const double* d_val, int64_t count, int64_t index0,
+                                     double* val_best_out, int64_t* index_best_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!d_val || count <= 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_argmax_device: null values or empty range");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(ensure(ctx, ctx->am_part, sizeof(ArgMax) * 1024));
+        TRY(ensure(ctx, ctx->am_acc, sizeof(ArgMax)));
+        ArgMax init;
+        init.v = 0.0, init.i = -1;
+        std::memcpy(ctx->pinned, &init, sizeof(init));
+        CUDA_TRY(cudaMemcpyAsync(ctx->am_acc.p, ctx->pinned, sizeof(ArgMax), cudaMemcpyHostToDevice, ctx->stream));
+        const int nblk = (int) std::min<long long>(1024, (count + 255) / 256);
+        argmax_partial_kernel<<<nblk, 256, 0, ctx->stream>>>(d_val, count, index0, ptr<ArgMax>(ctx->am_part));
+        LAUNCH_CHECK();
+        argmax_final_kernel<<<1, 256, 0, ctx->stream>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
+        LAUNCH_CHECK();
+        ArgMax best;
+        CUDA_TRY(cudaMemcpyAsync(&best, ctx->am_acc.p, sizeof(ArgMax), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (best.i < 0) return fail(ctx, SLSGP_ERR_NAN, "slsgp_argmax_device: every value is NaN");
+        if (val_best_out) *val_best_out = best.v;
+        if (index_best_out) *index_best_out = best.i;
+        return SLSGP_OK;
     }
 
     slsgp_status slsgp_candidates(slsgp_ctx* ctx, uint64_t seed, int64_t first, int64_t count, double* Xq_out)
