@@ -9,6 +9,8 @@ A step = one sweep of `--candidates` candidate points per GPU through the hot pa
 gradients for every candidate, then the arg-max; for N > 1 an NCCL all-gather of the per-rank (value, index) pair).
 `value` times the sweep with candidates and results resident in HBM; `e2e` times the same sweep through the
 host-buffer C-ABI call (slsgp_acq_batch) with pinned host candidates in and values + gradients back.
+The headline sweep arithmetic is --mode (default "tensor": tcgen05 split-fp16, parity 1e-3); `modes` in the JSON line
+holds a short run of every mode with its measured error against the FP64 sweep.
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
@@ -42,8 +44,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=8)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["graft", "reference"], default="graft")
-    ap.add_argument("--candidates", type=int, default=1 << 18, help="candidates per GPU per step")
-    ap.add_argument("--e2e-candidates", type=int, default=1 << 17)
+    ap.add_argument("--mode", choices=["tensor", "tensor_x2", "tensor_x1", "fp64"], default="tensor",
+                    help="sweep arithmetic of the headline number (include/slsgp.h slsgp_sweep_mode)")
+    ap.add_argument("--candidates", type=int, default=0, help="candidates per GPU per step (default 2^20; 2^18 for fp64)")
+    ap.add_argument("--e2e-candidates", type=int, default=0)
+    ap.add_argument("--no-mode-table", action="store_true", help="skip the short runs of the other sweep modes")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
 
@@ -222,7 +227,14 @@ def main_graft(args):
     ctx.set_stream(stream.cuda_stream)
 
     X, theta, y = fixed_model()
-    M = args.candidates
+    MODES = {"fp64": pkg.SWEEP_FP64, "tensor": pkg.SWEEP_TENSOR, "tensor_x2": pkg.SWEEP_TENSOR_X2, "tensor_x1": pkg.SWEEP_TENSOR_X1}
+    PASSES = {"fp64": 1, "tensor": 3, "tensor_x2": 2, "tensor_x1": 1}
+    M = args.candidates or ((1 << 18) if args.mode == "fp64" else (1 << 20))
+    Me = args.e2e_candidates or M // 2
+    if args.mode == "fp64":
+        gemm_key, kernels = "sweep_gemm", ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish")
+    else:
+        gemm_key, kernels = "tc_gemm", ("tc_gemm", "tc_kstar", "sweep_finish")
 
     # ---- model build: Gram + Cholesky (+ inverse, alpha), timed per phase with CUDA events (median of 7 after 3)
     ctx.set_data(X)
@@ -247,10 +259,10 @@ def main_graft(args):
     gather = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
     torch.cuda.synchronize()
 
-    def step(i):
+    def step(i, m=M):
         q = Xq[i % nb]
-        ctx.acq_batch_device(ACQ_EI, 1.0, q.data_ptr(), M, d_val=val.data_ptr(), d_grad=grad.data_ptr())
-        v, idx = ctx.argmax_device(val.data_ptr(), M, index0=rank * M)  # synchronises this rank's stream
+        ctx.acq_batch_device(ACQ_EI, 1.0, q.data_ptr(), m, d_val=val.data_ptr(), d_grad=grad.data_ptr())
+        v, idx = ctx.argmax_device(val.data_ptr(), m, index0=rank * M)  # synchronises this rank's stream
         if world > 1:  # the only collective on the path: (value, index) of every rank's winner
             mine = torch.tensor([v, float(idx)], dtype=torch.float64, device="cuda")
             dist.all_gather(gather, mine)
@@ -259,19 +271,43 @@ def main_graft(args):
             return float(allv[w, 0]), int(allv[w, 1])
         return v, idx
 
-    for i in range(args.warmup):
-        step(i)
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # ---- the other sweep modes on a short run (rank 0's table; not the headline): throughput + error vs FP64
+    mode_table = {}
+    if not args.no_mode_table:
+        Mt = min(M, 1 << 17)
+        ctx.set_sweep_mode(pkg.SWEEP_FP64)
+        step(0, Mt)
+        ref_val, ref_grad = val[:Mt].clone(), grad[:Mt].clone()
+        for name, mode in MODES.items():
+            ctx.set_sweep_mode(mode)
+            step(0, Mt)
+            ev_v = float((val[:Mt] - ref_val).abs().max() / ref_val.abs().max())
+            ev_g = float((grad[:Mt] - ref_grad).abs().max() / ref_grad.abs().max())
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            t0.record(stream)
+            reps = 2 if name == "fp64" else 6
+            for r in range(reps):
+                step(r + 1, Mt)
+            t1.record(stream)
+            torch.cuda.synchronize()
+            mode_table[name] = {"evals_per_s": reps * Mt / (t0.elapsed_time(t1) * 1e-3), "mma_passes": PASSES[name],
+                                "ei_max_err_vs_fp64": ev_v, "grad_max_err_vs_fp64": ev_g}
+
+    ctx.set_sweep_mode(MODES[args.mode])
+    for i in range(args.warmup):
+        step(i)
+
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     ctx.profile_enable(True)
-    for k in ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish"):
+    for k in kernels:
         ctx.profile_read(k)
     launches0 = ctx.launch_count()
     barrier()
@@ -283,12 +319,11 @@ def main_graft(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = ctx.launch_count() - launches0
-    prof = {k: ctx.profile_read(k) for k in ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish")}
+    prof = {k: ctx.profile_read(k) for k in kernels}
     ctx.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end through the host-buffer C-ABI call: pinned candidates in, values + gradients out
-    Me = args.e2e_candidates
     hq = [torch.rand((Me, DIM), dtype=torch.float64, generator=torch.Generator().manual_seed(77 + rank + 10 * b)).pin_memory()
           for b in range(2)]
     hval = torch.empty(Me, dtype=torch.float64).pin_memory()
@@ -322,31 +357,41 @@ def main_graft(args):
 
     if rank == 0:
         peaks, peak_src = measured_peaks()
-        gemm_ms, gemm_n = prof["sweep_gemm"]
-        shard = min(M, 16384)
-        flops_per_launch = 2.0 * N_OBS * N_OBS * shard  # algorithmic: beta = K^-1 k* for every candidate of the shard
-        achieved = flops_per_launch / (gemm_ms / max(gemm_n, 1) * 1e-3) / 1e12 if gemm_n else None
+        gemm_ms, gemm_n = prof[gemm_key]
+        shard = min(M, 16384 if args.mode == "fp64" else 148 * 128 * 2)
+        # algorithmic work per candidate = 2 N^2 (beta = K^-1 k*) + 7 N D + 2 N  FLOP
+        flop_per_cand = 2.0 * N_OBS * N_OBS + 7.0 * N_OBS * DIM + 2.0 * N_OBS
+        cands_per_launch = M * args.steps / max(gemm_n, 1)
+        achieved = flop_per_cand * cands_per_launch / (gemm_ms / max(gemm_n, 1) * 1e-3) / 1e12 if gemm_n else None
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         sweep_total = sum(v[0] for v in prof.values())
+        if args.mode == "fp64":
+            kname = "gemm64_kernel<NN> (beta = K^-1 k*, FP64 DFMA)"
+            note = "the kernel runs on the FP64 pipe; the tensor peak is quoted for scale only"
+        else:
+            kname = f"tc_sweep_gemm_kernel<20> (tcgen05.mma kind::f16, {PASSES[args.mode]} split-fp16 pass(es), fused epilogue)"
+            note = (f"achieved counts ALGORITHMIC flops; the tensor pipe executes {PASSES[args.mode]}x the 2N^2 term "
+                    f"(executed ~{PASSES[args.mode] * achieved:.0f} TFLOP/s)") if achieved else ""
         line = {
             "metric": METRIC, "value": world * M * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.mode == "fp64" else "f16x2-split/f32-acc",
+            "data": "synthetic",
             "config": {"workload": WORKLOAD, "candidates_per_gpu_per_step": M, "n_obs": N_OBS, "dim": DIM,
-                       "sweep_mode": "fp64", "collective": "all_gather(value,index) per step" if world > 1 else "none",
-                       "l2": "per-step working set (k*/g*/beta shards 805 MB + K^-1 33.5 MB + 4 rotating candidate "
-                             "batches) exceeds the 126 MB L2; no explicit flush"},
-            "gram_chol_ms": aux["gram_chol_ms"], "aux": aux,
+                       "sweep_mode": args.mode, "shard_candidates": shard,
+                       "collective": "all_gather(value,index) per step" if world > 1 else "none",
+                       "l2": "4 rotating candidate batches; per-step working set (candidates, values, gradients, per-shard "
+                             "k* operands) exceeds the 126 MB L2; no explicit flush"},
+            "gram_chol_ms": aux["gram_chol_ms"], "aux": aux, "modes": mode_table,
             "e2e": {"value": world * Me * args.steps / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": Me * DIM * 8, "d2h_bytes_per_step": Me * (DIM + 1) * 8,
                     "candidates_per_gpu_per_step": Me, "api": "slsgp_acq_batch (host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "gemm64_kernel<NN> (beta = K^-1 k*, FP64 DFMA)",
+            "roofline": {"bound": "tensor", "kernel": kname,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": None,
-                         "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json); the kernel runs on the "
-                                        "FP64 pipe, see DESIGN.md",
+                         "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)", "note": note,
                          "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                          "share_of_sweep": gemm_ms / sweep_total if sweep_total else None,
                          "kernel_ms": {k: v[0] for k, v in prof.items()}},

@@ -61,8 +61,15 @@ extern "C"
      * Gram build, factorisation, inverse, alpha and the MAP objectives are always IEEE double. */
     typedef enum
     {
-        SLSGP_SWEEP_FP64   = 0, /* IEEE double throughout; parity 1e-5 relative (north_star "FP64") */
-        SLSGP_SWEEP_TENSOR = 1  /* split-fp16 operands on the tcgen05 tensor pipe, fp32 accumulation; parity 1e-3 */
+        SLSGP_SWEEP_FP64      = 0, /* IEEE double throughout; parity 1e-5 relative (north_star "FP64") */
+        /* fp16 operands on the tcgen05 tensor pipe, fp32 accumulation in TMEM (ARD squared-exponential kernel, D <= 67).
+         * K^-1 and k* are each split into two fp16 terms; the contraction is evaluated as
+         *   TENSOR     k16.A16 + k16.A_lo + k_lo.A16   fp32-class result, parity 1e-3 on every test distribution
+         *   TENSOR_X2  k16.A16 + k16.A_lo              sigma / EI value fp32-class, gradients limited by k16 (~2e-3)
+         *   TENSOR_X1  k16.A16                          fastest; 1e-3 only for well-conditioned K (cond <~ 1e3) */
+        SLSGP_SWEEP_TENSOR    = 1,
+        SLSGP_SWEEP_TENSOR_X2 = 2,
+        SLSGP_SWEEP_TENSOR_X1 = 3
     } slsgp_sweep_mode;
 
     /* Reference quirks that parity has to reproduce; all on by default. */

@@ -18,7 +18,7 @@ c_u32p = C.POINTER(C.c_uint32)
 OK, ERR_INVALID, ERR_STATE, ERR_NOT_SPD, ERR_NAN, ERR_CUDA, ERR_NOMEM = range(7)
 KERNEL_ARD_SQUARED_EXP, KERNEL_ARD_MATERN52 = 0, 1
 ACQ_EXPECTED_IMPROVEMENT, ACQ_GP_UCB = 0, 1
-SWEEP_FP64, SWEEP_TENSOR = 0, 1
+SWEEP_FP64, SWEEP_TENSOR, SWEEP_TENSOR_X2, SWEEP_TENSOR_X1 = 0, 1, 2, 3
 COMPAT_SE_XGRAD_2X = 1
 
 # every symbol include/slsgp.h declares: (name, restype, argtypes)

@@ -14,10 +14,12 @@
 #include "gram.cuh"
 #include "map.cuh"
 #include "sweep.cuh"
+#include "tc_sweep.cuh"
 
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -64,6 +66,13 @@ struct slsgp_ctx
     int    P = 0, pref_total = 0;
     DevBuf Xq, Kstar, Gstar, Beta, P1, P2, stats, o_mu, o_sigma, o_dmu, o_dsigma, o_val, o_grad, am_part, am_acc;
     long long Mcap = 0;
+
+    // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
+    DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err;
+    CUtensorMap tmA, tmB;
+    int         ldt = 0, XP = 0;
+    bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
+    long long   tc_Mcap = 0;      // rows of Ks (multiple of 128)
 
     double* pinned       = nullptr; // small host staging area
     size_t  pinned_bytes = 0;
@@ -359,6 +368,7 @@ namespace
     slsgp_status do_alpha(slsgp_ctx* ctx)
     {
         TRY(do_inverse(ctx));
+        ctx->tc_ready = false;
         TRY(phase_begin(ctx, "alpha"));
         const int ld = ctx->ld, blocks = (ld * 32 + 255) / 256;
         gemv_kernel<true><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->Kinv), ld, ld, dp(ctx->y), dp(ctx->alpha), 0);
@@ -376,15 +386,34 @@ namespace
     // ---------------------------------------------------------------------------------------------------------
     // K4: one shard of Mc <= Mcap candidates already in d_Xq (D x Mc, device). Outputs are device pointers.
     // ---------------------------------------------------------------------------------------------------------
+    long long tc_shard_cap();
+    bool      is_tensor_mode(int mode);
+    slsgp_status prepare_tensor(slsgp_ctx* ctx);
+    slsgp_status tensor_map_2d(slsgp_ctx* ctx, CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows);
+
+    // Per-shard scratch. FP64 mode: Kstar / Gstar / Beta (ld x cap each) dominate, so cap <= 16384 candidates;
+    // tensor mode: the fp16 Ks operand (cap x ldt), cap = SLSGP_TC_SHARD (default two waves of 148 x 128).
     slsgp_status ensure_sweep_workspace(slsgp_ctx* ctx, long long want)
     {
-        long long cap = std::min<long long>(std::max<long long>(want, 64), 16384);
-        cap           = round_up64(cap, TILE);
+        const bool tensor = is_tensor_mode(ctx->sweep_mode);
+        if (tensor) TRY(prepare_tensor(ctx));
+        long long cap = std::min<long long>(std::max<long long>(want, 64), tensor ? tc_shard_cap() : 16384);
+        cap           = round_up64(cap, tensor ? TC_BM : TILE);
+        if (tensor && ctx->tc_Mcap < cap)
+        {
+            // rows [0, cap): k16, rows [cap, 2 cap): its fp16 rounding residual (read only by the split-precision passes)
+            TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 2 * (size_t) cap * ctx->ldt));
+            TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 2 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
+            ctx->tc_Mcap = cap;
+        }
         if (ctx->Mcap >= cap) return SLSGP_OK;
         const size_t col = sizeof(double) * (size_t) ctx->ld;
-        TRY(ensure(ctx, ctx->Kstar, col * cap));
-        TRY(ensure(ctx, ctx->Gstar, col * cap));
-        TRY(ensure(ctx, ctx->Beta, col * cap));
+        if (!tensor)
+        {
+            TRY(ensure(ctx, ctx->Kstar, col * cap));
+            TRY(ensure(ctx, ctx->Gstar, col * cap));
+            TRY(ensure(ctx, ctx->Beta, col * cap));
+        }
         TRY(ensure(ctx, ctx->P1, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->P2, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->stats, sizeof(double4) * (size_t) cap));
@@ -401,9 +430,166 @@ namespace
         return SLSGP_OK;
     }
 
+    // ---------------------------------------------------------------------------------------------------------
+    // K4, tensor-core path (tc_sweep.cuh)
+    // ---------------------------------------------------------------------------------------------------------
+    bool is_tensor_mode(int mode) { return mode == SLSGP_SWEEP_TENSOR || mode == SLSGP_SWEEP_TENSOR_X2 || mode == SLSGP_SWEEP_TENSOR_X1; }
+    int  tensor_passes(int mode) { return mode == SLSGP_SWEEP_TENSOR ? 3 : (mode == SLSGP_SWEEP_TENSOR_X2 ? 2 : 1); }
+
+    int tc_xp(int D) // epilogue register-tile width: smallest instantiated XP >= D + 1
+    {
+        const int want = D + 1;
+        for (int xp : {8, 12, 20, 36, 68})
+            if (want <= xp) return xp;
+        return 0;
+    }
+
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                      const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                      CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+    // fp16 row-major [rows x cols] matrix, boxes of box_rows x 64 elements (128 bytes), 128-byte swizzle.
+    slsgp_status tensor_map_2d(slsgp_ctx* ctx, CUtensorMap* map, void* base, uint64_t rows, uint64_t cols, uint32_t box_rows)
+    {
+        static EncodeTiledFn encode = nullptr;
+        if (!encode)
+        {
+            void*                           fn = nullptr;
+            cudaDriverEntryPointQueryResult qr;
+            CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+            if (qr != cudaDriverEntryPointSuccess || !fn)
+                return fail(ctx, SLSGP_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            encode = reinterpret_cast<EncodeTiledFn>(fn);
+        }
+        const cuuint64_t dims[2]    = {cols, rows};
+        const cuuint64_t strides[1] = {cols * sizeof(__half)};
+        const cuuint32_t box[2]     = {(cuuint32_t) TC_BK, box_rows};
+        const cuuint32_t estr[2]    = {1, 1};
+        const CUresult   r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(ctx, SLSGP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int) r));
+        return SLSGP_OK;
+    }
+
+    // fp16 operands derived from the fitted model (Kinv, alpha, X, theta): once per model.
+    slsgp_status prepare_tensor(slsgp_ctx* ctx)
+    {
+        if (ctx->tc_ready) return SLSGP_OK;
+        if (ctx->kernel_type != SLSGP_KERNEL_ARD_SQUARED_EXP)
+            return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR supports the ARD squared-exponential kernel only");
+        const int XP = tc_xp(ctx->D);
+        if (!XP) return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR supports D <= 67");
+        const int ldt = round_up(ctx->N, TC_BN);
+        ctx->XP = XP, ctx->ldt = ldt;
+        const size_t brows = 2 * (size_t) ldt + TC_BN;
+        TRY(ensure(ctx, ctx->Bmat, sizeof(__half) * brows * ldt));
+        TRY(ensure(ctx, ctx->Xt, sizeof(float) * (size_t) ldt * XP));
+        TRY(ensure(ctx, ctx->Xs32, sizeof(float) * (size_t) ldt * ctx->D));
+        TRY(ensure(ctx, ctx->tcs, sizeof(TcScales)));
+        if (!ctx->tc_err.p)
+        {
+            TRY(ensure(ctx, ctx->tc_err, sizeof(int)));
+            CUDA_TRY(cudaMemsetAsync(ctx->tc_err.p, 0, sizeof(int), ctx->stream));
+        }
+        tc_scales_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->Kinv), ctx->ld, ctx->N, dp(ctx->alpha), dp(ctx->X), ctx->D,
+                                                     dp(ctx->theta), ptr<TcScales>(ctx->tcs));
+        LAUNCH_CHECK();
+        tc_pack_b_kernel<<<dim3(ldt / 256, (unsigned) brows), 256, 0, ctx->stream>>>(
+            dp(ctx->Kinv), ctx->ld, ctx->N, ctx->D, XP, ldt, dp(ctx->alpha), dp(ctx->X), ptr<TcScales>(ctx->tcs),
+            ptr<__half>(ctx->Bmat));
+        LAUNCH_CHECK();
+        tc_pack_x_kernel<<<(ldt + 255) / 256, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, XP, ldt, dp(ctx->inv_l),
+                                                                    ptr<float>(ctx->Xt), ptr<float>(ctx->Xs32));
+        LAUNCH_CHECK();
+        TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN));
+        ctx->tc_ready = true;
+        return SLSGP_OK;
+    }
+
+    long long tc_shard_cap()
+    {
+        static long long cap = 0;
+        if (!cap)
+        {
+            const char* e = std::getenv("SLSGP_TC_SHARD");
+            cap           = e ? std::atoll(e) : 148LL * TC_BM * 2;
+            cap           = std::max<long long>(TC_BM, round_up64(cap, TC_BM));
+        }
+        return cap;
+    }
+
+    template <int XP> slsgp_status launch_tc_gemm(slsgp_ctx* ctx, const TcGemmParams& prm_in, int n_sm)
+    {
+        TcGemmParams prm   = prm_in;
+        const size_t fixed = (size_t) TC_BN * XP * sizeof(float) + 1024;
+        prm.stages         = (int) std::min<size_t>(TC_MAX_STAGES, (232448 - 512 - fixed) / TC_STAGE_BYTES);
+        const size_t smem  = (size_t) prm.stages * TC_STAGE_BYTES + fixed;
+        static bool  attr_set = false;
+        if (!attr_set)
+        {
+            CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_set = true;
+        }
+        const int grid = std::min(prm.n_cand_blocks, n_sm);
+        tc_sweep_gemm_kernel<XP><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out)
+    {
+        ProfScope ps(ctx, "sweep_finish");
+        sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
+            d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
+            acq_type, ucb_beta, out);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    slsgp_status sweep_shard_tensor(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
+                                    SweepOut out)
+    {
+        const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
+        const long long Mpad = round_up64(Mc, TC_BM);
+        __half*         Ks_lo = passes > 1 ? ptr<__half>(ctx->Ks) + (size_t) ctx->tc_Mcap * ldt : nullptr;
+        static int      n_sm = 0;
+        if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+        {
+            ProfScope    ps(ctx, "tc_kstar");
+            const size_t smem = sizeof(float) * (size_t) (64 * (D + 1) + D * 128);
+            kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, ctx->stream>>>(
+                d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs),
+                ptr<__half>(ctx->Ks), Ks_lo);
+            LAUNCH_CHECK();
+        }
+        {
+            ProfScope    ps(ctx, "tc_gemm");
+            TcGemmParams prm;
+            prm.ldt = ldt, prm.kb = round_up(ctx->N, TC_BK) / TC_BK, prm.ncb = ldt / TC_BN, prm.D = D, prm.stages = 0;
+            prm.n_cand_blocks = (int) (Mpad / TC_BM), prm.Mc = Mc;
+            prm.passes = passes, prm.a_lo_row = (int) ctx->tc_Mcap, prm.b_lo_row = ldt + TC_BN, prm.Ks_lo = Ks_lo;
+            prm.Ks = ptr<__half>(ctx->Ks), prm.Xt = ptr<float>(ctx->Xt), prm.sc = ptr<TcScales>(ctx->tcs);
+            prm.se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
+            prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2), prm.ldp = ctx->Dp;
+            prm.err = ptr<int>(ctx->tc_err);
+            switch (ctx->XP)
+            {
+                case 8: TRY(launch_tc_gemm<8>(ctx, prm, n_sm)); break;
+                case 12: TRY(launch_tc_gemm<12>(ctx, prm, n_sm)); break;
+                case 20: TRY(launch_tc_gemm<20>(ctx, prm, n_sm)); break;
+                case 36: TRY(launch_tc_gemm<36>(ctx, prm, n_sm)); break;
+                case 68: TRY(launch_tc_gemm<68>(ctx, prm, n_sm)); break;
+                default: return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: unsupported D");
+            }
+        }
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out);
+    }
+
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
                              SweepOut out)
     {
+        if (is_tensor_mode(ctx->sweep_mode)) return sweep_shard_tensor(ctx, acq_type, ucb_beta, d_Xq, Mc, out);
         const int       ld = ctx->ld, D = ctx->D, Dp = ctx->Dp;
         const long long Mp = round_up64(Mc, TILE);
         const bool      want_grad = out.dmu || out.dsigma || out.grad;
@@ -436,14 +622,7 @@ namespace
             GemmArgs p2 = gemm_args(dp(ctx->Xpad), dp(ctx->Beta), dp(ctx->P2), Dp, (int) Mp, ld, Dp, ld, Dp, 1.0, 0.0);
             TRY((launch_gemm<false, false>(ctx, p2)));
         }
-        {
-            ProfScope ps(ctx, "sweep_finish");
-            sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
-                d_Xq, D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), Dp, dp(ctx->theta), dp(ctx->fbest),
-                acq_type, ucb_beta, out);
-            LAUNCH_CHECK();
-        }
-        return SLSGP_OK;
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out);
     }
 
     slsgp_status require_model(slsgp_ctx* ctx)
@@ -515,7 +694,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc};
+                         &ctx->am_acc, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)
@@ -544,8 +723,8 @@ extern "C"
     slsgp_status slsgp_set_sweep_mode(slsgp_ctx* ctx, slsgp_sweep_mode mode)
     {
         if (!ctx) return SLSGP_ERR_INVALID;
-        if (mode != SLSGP_SWEEP_FP64)
-            return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR is not available in this build");
+        if (mode != SLSGP_SWEEP_FP64 && !is_tensor_mode(mode)) return fail(ctx, SLSGP_ERR_INVALID, "unknown sweep mode");
+        if (is_tensor_mode(mode) != is_tensor_mode(ctx->sweep_mode)) ctx->Mcap = 0; // the per-shard scratch differs between the two modes
         ctx->sweep_mode = mode;
         return SLSGP_OK;
     }
@@ -621,6 +800,7 @@ extern "C"
         ctx->N = N, ctx->D = D, ctx->ld = round_up(N, TILE), ctx->Dp = round_up(D, TILE), ctx->ldx = round_up(D + 1, TILE);
         ctx->has_data = ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
         ctx->Mcap = 0; // sweep workspace depends on ld
+        ctx->tc_Mcap = 0, ctx->tc_ready = false;
         const size_t ld = ctx->ld, mat = sizeof(double) * ld * ld;
         TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) N * D));
         TRY(ensure(ctx, ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld));

@@ -1,0 +1,454 @@
+// K4 (tensor-core path, SLSGP_SWEEP_TENSOR): the acquisition sweep with the N x N contraction on tcgen05.
+//
+// Same algebra as sweep.cuh (reference: src/preference-regressor.cpp:293-330, src/regressor.cpp:45-59,91-108), for the
+// ARD squared-exponential kernel, where the x-gradient weight is g_i = -c k_i (c = 2 in the reference,
+// external/mathtoolbox/src/kernel-functions.cpp:92):
+//   u  = K^-1 k                         (N x N x M contraction: tcgen05.mma, fp16 operands, fp32 accumulation in TMEM)
+//   q  = sum_i k_i u_i                  sigma^2 = a - q
+//   P2_d = -c sum_i X_di k_i u_i        (epilogue of the same kernel, fp32 FMA on the accumulator tile)
+//   mu = sum_j k_j alpha_j,  P1_d = -c sum_j X_dj k_j alpha_j
+//                                       (extra B columns alpha_j * [1, X_dj], split into fp16 hi + lo, same MMA stream)
+// Operands in HBM (fp16, K-major = contiguous along the contraction index j):
+//   Ks   [Mpad x ldt]        Ks[m][j]   = sK * k(x_m, X_j)                 written by kstar16_kernel per shard
+//   Bmat [(ldt+256) x ldt]   Bmat[i][j] = sA * Kinv[i][j]       (i < N)     rows ldt + 2c / 2c+1: extras hi / lo
+// and, for the epilogue, Xt [ldt x XP] fp32 with Xt[i] = (1, X_0i .. X_{D-1}i, 0 ..).
+// One CTA owns 128 candidates (TMEM lanes) and walks the ldt/256 column blocks of Kinv plus the extras block; the
+// accumulator is double-buffered in TMEM (2 x 256 columns) so the epilogue of block b overlaps the MMAs of b+1.
+#pragma once
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace slsgp
+{
+    constexpr int TC_BM          = 128; // candidates per CTA tile (UMMA M)
+    constexpr int TC_BN          = 256; // Kinv columns per accumulator (UMMA N)
+    constexpr int TC_BK          = 64;  // contraction elements per pipeline stage (128 bytes of fp16 = one swizzle row)
+    constexpr int TC_A_BYTES     = TC_BM * TC_BK * 2;
+    constexpr int TC_B_BYTES     = TC_BN * TC_BK * 2;
+    constexpr int TC_STAGE_BYTES = TC_A_BYTES + TC_B_BYTES;
+    constexpr int TC_MAX_STAGES  = 8;
+    constexpr int TC_THREADS     = 256; // warp 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4..7 epilogue
+
+    struct TcScales
+    {
+        float sK, sA, sE; // power-of-two multipliers putting k, Kinv and the extras into fp16 range
+        float c0;         // log2(a * sK): k16 = exp2(-0.5 log2(e) r2 + c0)
+        float inv_u;      // 1 / (sA sK^2): accumulator * k16 -> k_i u_i
+        float inv_e;      // 1 / (sK sE)
+    };
+
+    __device__ __forceinline__ float pow2_floor_scale(float target, float maxabs)
+    {
+        if (!(maxabs > 0.f)) return 1.f;
+        return exp2f(floorf(log2f(target / maxabs)));
+    }
+
+    // One block. |Kinv_ij| <= max_i Kinv_ii for an SPD matrix, so the diagonal bounds the whole operand.
+    __global__ void __launch_bounds__(256)
+        tc_scales_kernel(const double* __restrict__ Kinv, int ld, int N, const double* __restrict__ alpha,
+                         const double* __restrict__ X, int D, const double* __restrict__ theta, TcScales* __restrict__ out)
+    {
+        __shared__ double sm[3][256];
+        double            md = 0.0, ma = 0.0, mx = 1.0;
+        for (int i = threadIdx.x; i < N; i += 256)
+        {
+            md = fmax(md, fabs(Kinv[(size_t) i + (size_t) i * ld]));
+            ma = fmax(ma, fabs(alpha[i]));
+            for (int d = 0; d < D; ++d) mx = fmax(mx, fabs(X[(size_t) d + (size_t) i * D]));
+        }
+        sm[0][threadIdx.x] = md, sm[1][threadIdx.x] = ma, sm[2][threadIdx.x] = mx;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1)
+        {
+            if (threadIdx.x < o)
+                for (int r = 0; r < 3; ++r) sm[r][threadIdx.x] = fmax(sm[r][threadIdx.x], sm[r][threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0)
+        {
+            const float a = (float) theta[0];
+            TcScales    s;
+            s.sK    = pow2_floor_scale(32768.f, a);
+            s.sA    = pow2_floor_scale(32768.f, (float) sm[0][0]);
+            s.sE    = pow2_floor_scale(32768.f, (float) (sm[1][0] * sm[2][0]));
+            s.c0    = log2f(a * s.sK);
+            s.inv_u = 1.f / (s.sA * s.sK * s.sK);
+            s.inv_e = 1.f / (s.sK * s.sE);
+            *out    = s;
+        }
+    }
+
+    // Bmat rows (see header). grid: (ldt / 256, 2 * ldt + 256), 256 threads: one thread per element, j fastest.
+    //   [0, ldt)               hi part of sA * Kinv
+    //   [ldt, ldt + 256)       extras: row 2c = hi, 2c + 1 = lo of sE * alpha_j * (1, X_0j, ..)[c]
+    //   [ldt + 256, 2ldt+256)  lo part of sA * Kinv (the fp16 rounding residual of the hi part)
+    __global__ void __launch_bounds__(256)
+        tc_pack_b_kernel(const double* __restrict__ Kinv, int ld, int N, int D, int XP, int ldt,
+                         const double* __restrict__ alpha, const double* __restrict__ X,
+                         const TcScales* __restrict__ sc, __half* __restrict__ Bmat)
+    {
+        const int j = blockIdx.x * 256 + threadIdx.x, i = blockIdx.y;
+        float     v = 0.f;
+        if (i < ldt || i >= ldt + TC_BN)
+        {
+            const int  r  = i < ldt ? i : i - ldt - TC_BN;
+            if (r < N && j < N)
+            {
+                const float full = (float) (Kinv[(size_t) j + (size_t) r * ld] * (double) sc->sA); // symmetric
+                const float hi   = __half2float(__float2half_rn(full));
+                v                = i < ldt ? hi : full - hi;
+            }
+        }
+        else if (j < N)
+        {
+            const int e = i - ldt, c = e >> 1;
+            if (c <= D)
+            {
+                const double xhat = c == 0 ? 1.0 : X[(size_t) (c - 1) + (size_t) j * D];
+                const float  full = (float) (alpha[j] * xhat * (double) sc->sE);
+                const float  hi   = __half2float(__float2half_rn(full));
+                v                 = (e & 1) ? full - hi : hi;
+            }
+        }
+        Bmat[(size_t) i * ldt + j] = __float2half_rn(v);
+    }
+
+    // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = (X_dj - 1/2) / l_d for kstar16.
+    __global__ void __launch_bounds__(256)
+        tc_pack_x_kernel(const double* __restrict__ X, int N, int D, int XP, int ldt, const double* __restrict__ inv_l,
+                         float* __restrict__ Xt, float* __restrict__ Xs32)
+    {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i >= ldt) return;
+        for (int c = 0; c < XP; ++c)
+        {
+            float v = 0.f;
+            if (i < N) v = c == 0 ? 1.f : (c <= D ? (float) X[(size_t) (c - 1) + (size_t) i * D] : 0.f);
+            Xt[(size_t) i * XP + c] = v;
+        }
+        for (int d = 0; d < D; ++d)
+            Xs32[(size_t) d * ldt + i] = i < N ? (float) ((X[(size_t) d + (size_t) i * D] - 0.5) * inv_l[d]) : 0.f;
+    }
+
+    // Ks[m][j] = fp16(sK * a * exp(-r2/2)), r2 by direct differences of the length-scaled coordinates in fp32.
+    // Tile: 64 candidates x 128 observations per CTA; thread = 4 candidates x 8 consecutive j (one 16-byte store per row).
+    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * (D + 1) + D * 128) floats.
+    __global__ void __launch_bounds__(256)
+        kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
+                       const float* __restrict__ Xs32, const double* __restrict__ inv_l,
+                       const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo)
+    {
+        extern __shared__ float ksm[];
+        float*                  sq = ksm;                 // [64][D + 1]
+        float*                  sx = ksm + 64 * (D + 1);  // [D][128]
+        const int               tid = threadIdx.x, j_base = blockIdx.x * 128;
+        const long long         m_base = (long long) blockIdx.y * 64;
+        for (int e = tid; e < 64 * D; e += 256)
+        {
+            const int       p = e / D, d = e - p * D;
+            const long long m = m_base + p;
+            sq[p * (D + 1) + d] = m < Mc ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
+        }
+        for (int e = tid; e < D * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
+        __syncthreads();
+
+        const int tj = tid & 15, tm = tid >> 4;
+        float     r2[4][8];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) r2[i][jj] = 0.f;
+        for (int d = 0; d < D; ++d)
+        {
+            const float4 xa = *reinterpret_cast<const float4*>(&sx[d * 128 + tj * 8]);
+            const float4 xb = *reinterpret_cast<const float4*>(&sx[d * 128 + tj * 8 + 4]);
+            const float  x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+            {
+                const float qv = sq[(tm * 4 + i) * (D + 1) + d];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj)
+                {
+                    const float df = qv - x[jj];
+                    r2[i][jj]      = fmaf(df, df, r2[i][jj]);
+                }
+            }
+        }
+        const float c1 = -0.72134752044448170368f; // -0.5 * log2(e)
+        const float c0 = sc->c0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+        {
+            const long long m = m_base + tm * 4 + i;
+            __half2         h[4], hl[4];
+#pragma unroll
+            for (int jj = 0; jj < 8; jj += 2)
+            {
+                const int   j  = j_base + tj * 8 + jj;
+                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(fmaf(r2[i][jj], c1, c0)) : 0.f;
+                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(fmaf(r2[i][jj + 1], c1, c0)) : 0.f;
+                h[jj >> 1]     = __floats2half2_rn(v0, v1);
+                const float2 b = __half22float2(h[jj >> 1]);
+                hl[jj >> 1]    = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)
+            }
+            const size_t off = (size_t) m * ldt + j_base + tj * 8;
+            *reinterpret_cast<uint4*>(Ks + off) = *reinterpret_cast<const uint4*>(h);
+            if (Ks_lo) *reinterpret_cast<uint4*>(Ks_lo + off) = *reinterpret_cast<const uint4*>(hl);
+        }
+    }
+
+    struct TcGemmParams
+    {
+        int              ldt;           // row length (elements) of Ks and Bmat; multiple of 256
+        int              kb;            // pipeline steps along the contraction = round_up(N, 64) / 64
+        int              ncb;           // regular column blocks = ldt / 256
+        int              D;
+        int              stages;        // shared-memory pipeline depth
+        int              n_cand_blocks; // ceil(Mc / 128)
+        long long        Mc;
+        int              passes;    // 1: k16 x A16 | 2: + k16 x A_lo | 3: + k_lo x A16 (split-fp16, fp32-class result)
+        int              a_lo_row;  // row offset of the k residuals inside the Ks tensor map
+        int              b_lo_row;  // row offset of the Kinv residuals inside the Bmat tensor map
+        const __half*    Ks_lo;     // k residuals (null when passes == 1)
+        const __half*    Ks;
+        const float*     Xt;
+        const TcScales*  sc;
+        double           se_factor; // c
+        double4*         stats;     // per candidate (mu, q, ga, gb), as column_reduce_kernel writes them
+        double*          P1;        // ldp x Mc
+        double*          P2;
+        int              ldp;
+        int*             err;
+    };
+
+    template <int XP>
+    __global__ void __launch_bounds__(TC_THREADS, 1)
+        tc_sweep_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                             const TcGemmParams p)
+    {
+        constexpr int EC = (2 * XP + 15) / 16 * 16; // extras columns: (hi, lo) pairs
+        extern __shared__ uint8_t smem_raw[];
+        __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
+        __shared__ uint32_t tmem_base_smem;
+
+        const uint32_t raw_addr = tc::smem_u32(smem_raw);
+        const uint32_t pad      = ((raw_addr + 1023u) & ~1023u) - raw_addr;
+        uint8_t*       smem     = smem_raw + pad; // 1024-byte aligned: required by the 128-byte swizzle
+        const uint32_t smem_a0  = raw_addr + pad;
+        float*         Xs       = reinterpret_cast<float*>(smem + (size_t) p.stages * TC_STAGE_BYTES); // [256][XP]
+
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+        if (warp == 0 && lane == 0)
+        {
+            tc::tma_prefetch_desc(&tmA);
+            tc::tma_prefetch_desc(&tmB);
+        }
+        if (warp == 1 && lane == 0)
+        {
+            for (int s = 0; s < p.stages; ++s)
+            {
+                tc::mbar_init(tc::smem_u32(&full_bar[s]), 1);
+                tc::mbar_init(tc::smem_u32(&empty_bar[s]), 1);
+            }
+            for (int s = 0; s < 2; ++s)
+            {
+                tc::mbar_init(tc::smem_u32(&tfull_bar[s]), 1);
+                tc::mbar_init(tc::smem_u32(&tempty_bar[s]), 128);
+            }
+            tc::fence_mbar_init();
+        }
+        if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_smem), 512);
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        const uint32_t tmem_base = tmem_base_smem;
+
+        if (warp == 0)
+        {
+            // ===== TMA producer =====
+            if (lane == 0)
+            {
+                uint32_t it = 0;
+                for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
+                    for (int cb = 0; cb <= p.ncb; ++cb)
+                        for (int ps = 0; ps < p.passes; ++ps)
+                        {
+                            if (cb == p.ncb && ps == 1) continue; // the extras carry their own lo rows
+                            const int a_row = cbk * TC_BM + (ps == 2 ? p.a_lo_row : 0);
+                            const int b_row = cb * TC_BN + (ps == 1 ? p.b_lo_row : 0);
+                            for (int k = 0; k < p.kb; ++k, ++it)
+                            {
+                                const uint32_t s = it % p.stages, n = it / p.stages;
+                                tc::mbar_wait(tc::smem_u32(&empty_bar[s]), (n & 1) ^ 1, p.err, 1);
+                                const uint32_t fb = tc::smem_u32(&full_bar[s]);
+                                tc::mbar_arrive_expect_tx(fb, TC_STAGE_BYTES);
+                                const uint32_t sa = smem_a0 + s * TC_STAGE_BYTES;
+                                tc::tma_load_2d(sa, &tmA, fb, k * TC_BK, a_row);
+                                tc::tma_load_2d(sa + TC_A_BYTES, &tmB, fb, k * TC_BK, b_row);
+                            }
+                        }
+            }
+        }
+        else if (warp == 1)
+        {
+            // ===== MMA issuer (one thread) =====
+            if (lane == 0)
+            {
+                const uint32_t idesc_full = tc::instr_desc_f16(TC_BM, TC_BN), idesc_extra = tc::instr_desc_f16(TC_BM, EC);
+                uint32_t       it = 0, t = 0;
+                for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
+                    for (int cb = 0; cb <= p.ncb; ++cb, ++t)
+                    {
+                        const uint32_t slot = t & 1, use = t >> 1;
+                        tc::mbar_wait(tc::smem_u32(&tempty_bar[slot]), (use & 1) ^ 1, p.err, 2);
+                        tc::fence_after_sync();
+                        const uint32_t d_tmem = tmem_base + slot * TC_BN;
+                        const uint32_t idesc  = cb < p.ncb ? idesc_full : idesc_extra;
+                        const int n_k = ((cb == p.ncb && p.passes > 1) ? p.passes - 1 : p.passes) * p.kb;
+                        for (int k = 0; k < n_k; ++k, ++it)
+                        {
+                            const uint32_t s = it % p.stages, n = it / p.stages;
+                            tc::mbar_wait(tc::smem_u32(&full_bar[s]), n & 1, p.err, 3);
+                            tc::fence_after_sync();
+                            const uint32_t sa = smem_a0 + s * TC_STAGE_BYTES;
+                            const uint64_t da = tc::smem_desc_k_sw128(sa), db = tc::smem_desc_k_sw128(sa + TC_A_BYTES);
+#pragma unroll
+                            for (int kk = 0; kk < TC_BK / 16; ++kk) // 16 fp16 = 32 bytes = 2 descriptor units per UMMA_K
+                                tc::umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
+                            tc::umma_commit(tc::smem_u32(&empty_bar[s])); // frees the stage once these MMAs have read it
+                        }
+                        tc::umma_commit(tc::smem_u32(&tfull_bar[slot])); // accumulator complete
+                    }
+            }
+        }
+        else if (warp >= 4)
+        {
+            // ===== epilogue: thread <-> candidate (TMEM lane) =====
+            const int      quad = warp & 3, row = quad * 32 + lane, et = threadIdx.x - 128;
+            const float    inv_u = p.sc->inv_u, inv_e = p.sc->inv_e;
+            uint32_t       t = 0;
+            for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
+            {
+                const long long m    = (long long) cbk * TC_BM + row;
+                const __half*   krow = p.Ks + (size_t) m * p.ldt;
+                const __half*   lrow = p.Ks_lo ? p.Ks_lo + (size_t) m * p.ldt : nullptr;
+                // passes == 2: u lacks A * dk, so q takes the first-order term 2 dk.u (q = k.A.k is symmetric in k)
+                const float     qw = p.passes == 2 ? 2.f : 1.f;
+                float           acc[XP];
+#pragma unroll
+                for (int c = 0; c < XP; ++c) acc[c] = 0.f;
+
+                for (int cb = 0; cb < p.ncb; ++cb, ++t)
+                {
+                    // stage this block's rows of Xt (256 x XP floats)
+                    tc::named_bar_sync(1, 128);
+                    {
+                        const float4* src = reinterpret_cast<const float4*>(p.Xt + (size_t) cb * TC_BN * XP);
+                        float4*       dst = reinterpret_cast<float4*>(Xs);
+                        for (int e = et; e < TC_BN * XP / 4; e += 128) dst[e] = src[e];
+                    }
+                    tc::named_bar_sync(1, 128);
+
+                    const uint32_t slot = t & 1, use = t >> 1;
+                    tc::mbar_wait(tc::smem_u32(&tfull_bar[slot]), use & 1, p.err, 4);
+                    tc::fence_after_sync();
+                    const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + slot * TC_BN;
+                    const uint4*   kptr  = reinterpret_cast<const uint4*>(krow + (size_t) cb * TC_BN);
+                    const uint4*   lptr  = lrow ? reinterpret_cast<const uint4*>(lrow + (size_t) cb * TC_BN) : nullptr;
+#pragma unroll 1
+                    for (int ch = 0; ch < TC_BN / 32; ++ch)
+                    {
+                        uint32_t r[32];
+                        tc::tmem_ld_x32(taddr + ch * 32, r);
+                        uint4 kv[4], lv[4];
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) kv[v] = __ldg(kptr + ch * 4 + v);
+#pragma unroll
+                        for (int v = 0; v < 4; ++v) lv[v] = lrow ? __ldg(lptr + ch * 4 + v) : make_uint4(0, 0, 0, 0);
+                        tc::tmem_ld_wait();
+                        const __half2* kh = reinterpret_cast<const __half2*>(kv);
+                        const __half2* lh = reinterpret_cast<const __half2*>(lv);
+#pragma unroll
+                        for (int c2 = 0; c2 < 16; ++c2)
+                        {
+                            const float2 kf = __half22float2(kh[c2]), lf = __half22float2(lh[c2]);
+#pragma unroll
+                            for (int h = 0; h < 2; ++h)
+                            {
+                                const int     c  = c2 * 2 + h;
+                                const float   u  = __uint_as_float(r[c]);
+                                const float   k1 = h ? kf.y : kf.x, dk = h ? lf.y : lf.x;
+                                const float   tv = (k1 + dk) * u;            // gradient sums
+                                const float   tq = fmaf(qw * dk, u, k1 * u); // quadratic form
+                                const float4* xr = reinterpret_cast<const float4*>(Xs + (ch * 32 + c) * XP);
+#pragma unroll
+                                for (int q4 = 0; q4 < XP / 4; ++q4)
+                                {
+                                    const float4 xv = xr[q4];
+                                    acc[q4 * 4 + 0] = fmaf(xv.x, q4 == 0 ? tq : tv, acc[q4 * 4 + 0]);
+                                    acc[q4 * 4 + 1] = fmaf(xv.y, tv, acc[q4 * 4 + 1]);
+                                    acc[q4 * 4 + 2] = fmaf(xv.z, tv, acc[q4 * 4 + 2]);
+                                    acc[q4 * 4 + 3] = fmaf(xv.w, tv, acc[q4 * 4 + 3]);
+                                }
+                            }
+                        }
+                    }
+                    tc::fence_before_sync();
+                    tc::mbar_arrive(tc::smem_u32(&tempty_bar[slot]));
+                }
+
+                const bool   live = m < p.Mc;
+                const double c    = p.se_factor;
+                const double q    = (double) acc[0] * (double) inv_u;
+                if (live)
+                {
+#pragma unroll
+                    for (int d = 0; d < XP - 1; ++d)
+                        if (d < p.D) p.P2[(size_t) d + (size_t) m * p.ldp] = -c * (double) acc[1 + d] * (double) inv_u;
+                }
+
+                // extras block: column 2c = hi, 2c + 1 = lo of sum_j k_mj alpha_j (1, X_0j, ..)[c]
+                {
+                    const uint32_t slot = t & 1, use = t >> 1;
+                    tc::mbar_wait(tc::smem_u32(&tfull_bar[slot]), use & 1, p.err, 5);
+                    tc::fence_after_sync();
+                    const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + slot * TC_BN;
+#pragma unroll
+                    for (int ch = 0; ch < EC / 16; ++ch)
+                    {
+                        uint32_t r[16];
+                        tc::tmem_ld_x16(taddr + ch * 16, r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i)
+                        {
+                            const int    cc = ch * 8 + i;
+                            const double S  = (double) (__uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1])) * (double) inv_e;
+                            if (live)
+                            {
+                                if (cc == 0)
+                                    p.stats[m] = make_double4(S, q, -c * S, -c * q);
+                                else if (cc <= p.D)
+                                    p.P1[(size_t) (cc - 1) + (size_t) m * p.ldp] = -c * S;
+                            }
+                        }
+                    }
+                    tc::fence_before_sync();
+                    tc::mbar_arrive(tc::smem_u32(&tempty_bar[slot]));
+                    ++t;
+                }
+            }
+        }
+
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 2)
+        {
+            tc::fence_after_sync();
+            tc::tmem_dealloc(tmem_base, 512);
+        }
+    }
+} // namespace slsgp
