@@ -188,8 +188,8 @@ extern "C"
     double       slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase);
     /* Per-kernel device timing: while enabled, every launch of the named hot kernels is bracketed by CUDA events on
      * the context's stream. slsgp_profile_read synchronises, returns the summed duration and launch count of
-     * `kernel` ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish", "gram",
-     * "potf2", "chol_panel", "chol_syrk") since the last read, and clears that kernel's records. */
+     * `kernel` ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish", "tc_kstar",
+     * "tc_gemm", "gram", "chol_step") since the last read, and clears that kernel's records. */
     slsgp_status slsgp_profile_enable(slsgp_ctx* ctx, int on);
     slsgp_status slsgp_profile_read(slsgp_ctx* ctx, const char* kernel, double* total_ms_out, uint64_t* launches_out);
 

@@ -1,0 +1,259 @@
+// K2: blocked right-looking Cholesky (FP64) with look-ahead, one launch per 64-wide block column.
+//
+// Launch k (k = -1 .. nb-2) owns the trailing matrix that starts at block k+1. Every CTA updates one 64 x 64 tile
+//     A[tm,tn] -= L[tm,k] L[tn,k]^T                       (skipped for k = -1)
+// and the tiles of the FIRST trailing block column then finish that column inside the same launch:
+//     CTA 0        (tile (k+1,k+1)): Cholesky of the updated diagonal tile and its inverse W, written to L / W,
+//                   then publishes flag[k+1];
+//     CTAs 1..rem-1 (tiles (tm,k+1)): keep their updated tile in shared memory, wait for flag[k+1] and write
+//                   L[tm,k+1] = tile * W^T.
+// So when launch k retires, block column k+1 of L is final and launch k+1 can start: the diagonal factorisation
+// (the only serial part) overlaps with the bulk of the trailing update instead of sitting between two launches.
+// The waiting CTAs are the lowest-numbered ones of the grid together with the CTA they wait for, so they are
+// always co-resident.
+//
+// Thread (tx, ty) of the 16 x 16 thread grid owns the INTERLEAVED micro-tile rows tx + 16 i, columns ty + 16 j
+// (i, j < 4): the shared-memory operand reads of a half-warp are then 16 consecutive doubles (conflict-free) and
+// its global accesses 128-byte segments.
+//
+// Replaces Eigen::LLT (reference call sites src/preference-regressor.cpp:162,290,370); W (the inverted diagonal
+// blocks) seeds the recursive-doubling triangular inverse of slsgp.cu:do_trtri.
+#pragma once
+
+#include "common.cuh"
+#include "gram.cuh" // lower_tile
+
+namespace slsgp
+{
+    constexpr int CHOL_LDS        = TILE + 2; // shared-memory leading dimension (even: keeps rows 16-byte aligned)
+    constexpr int CHOL_SMEM_BYTES = 2 * TILE * CHOL_LDS * (int) sizeof(double);
+
+    // Cholesky + inverse of a 64 x 64 SPD tile held in REGISTERS, c[i][q] = S[tx + 16 i][ty + 16 q], lower triangle =
+    // the tile, strict upper triangle = 0.
+    // Works on the UNSCALED Schur complement: at step j, with d = S[j][j] and column j broadcast through shared memory,
+    //     S[p][q] -= S[p][j] S[q][j] / d        (j < q <= p)        trailing update
+    //     R[q][p] -= S[q][j] R[j][p] / d        (p <= j < q)        forward substitution L R = I, R[j][j] = 1
+    // where R (strictly lower) lives transposed in the strict upper triangle (R[q][p] at S[p][q], p < q), so both
+    // cases read  S[p][q] -= col[p] col[q] / d  with col[j] := 1. One barrier per step (the column buffer is
+    // double-buffered), at most 16 predicated FMAs per thread, no shared-memory traffic besides the 64-value broadcast.
+    // Afterwards L[p][q] = S[p][q] rs[q] (q <= p) and W[q][p] = S[p][q] rs[q] (p < q), rs[q] = d_q^-1/2 in rs[].
+    // info receives 1 + global index of the first non-positive pivot.
+    __device__ __forceinline__ void potf2_inverse_regs(double c[4][4], double* colbuf /* [2][TILE + 2] */, double* dv,
+                                                       double* rs, int* sbad, int tx, int ty, int diag0, int* info)
+    {
+        if (threadIdx.x == 0) *sbad = 0x7fffffff;
+        int first_bad = 0x7fffffff;
+#pragma unroll
+        for (int jq = 0; jq < 4; ++jq)
+        {
+            for (int jt = 0; jt < 16; ++jt)
+            {
+                // pivot j = jt + 16 jq. With p = tx + 16 i and q = ty + 16 qq the predicate
+                //   on = (q > j) && (p >= q || p <= j)
+                // reduces to compile-time comparisons of i, qq, jq plus these three thread-level facts
+                const int  j     = jt + 16 * jq;
+                const bool ty_gt = ty > jt, tx_le = tx <= jt, tx_ge_ty = tx >= ty;
+                double*    col   = colbuf + (j & 1) * (TILE + 2);
+                if (ty == jt) // the 16 threads that own column j
+                {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        double v = c[i][jq];
+                        if (i == jq && tx == jt) // the pivot itself
+                        {
+                            col[TILE] = v, dv[j] = v;
+                            if (!(v > 0.0)) first_bad = min(first_bad, j);
+                            v = 1.0;
+                        }
+                        col[tx + 16 * i] = v;
+                    }
+                }
+                __syncthreads();
+                const double inv_d = 1.0 / col[TILE];
+                double       rowv[4], colv[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rowv[i] = col[tx + 16 * i] * inv_d;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) colv[q] = col[ty + 16 * q];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        const bool q_gt_j = q > jq || (q == jq && ty_gt);
+                        const bool p_ge_q = i > q || (i == q && tx_ge_ty);
+                        const bool p_le_j = i < jq || (i == jq && tx_le);
+                        if (q_gt_j && (p_ge_q || p_le_j)) c[i][q] = fma(-rowv[i], colv[q], c[i][q]);
+                    }
+            }
+        }
+        if (first_bad != 0x7fffffff) atomicMin(sbad, first_bad);
+        __syncthreads();
+        if (threadIdx.x < TILE) rs[threadIdx.x] = rsqrt(dv[threadIdx.x]);
+        if (threadIdx.x == 0 && *sbad != 0x7fffffff) atomicCAS(info, 0, 1 + diag0 + *sbad);
+        __syncthreads();
+    }
+
+    // acc[i][j] += sum_k As[k][tx + 16 i] * Bs[k][ty + 16 j], k in [0, 64).
+    __device__ __forceinline__ void tile_mma_64(double (*As)[CHOL_LDS], double (*Bs)[CHOL_LDS], int tx, int ty,
+                                                double acc[4][4])
+    {
+#pragma unroll 8
+        for (int kk = 0; kk < TILE; ++kk)
+        {
+            double a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+
+    // dst[kk][m] = src[m + kk * ld] for a 64 x 64 column-major tile: 16 independent 8-byte loads in flight per thread.
+    __device__ __forceinline__ void load_tile_64(double (*dst)[CHOL_LDS], const double* src, int ld, int tid, bool cg)
+    {
+        double v[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+        {
+            const int     e = tid + r * 256, m = e & 63, kk = e >> 6;
+            const double* p = src + (size_t) m + (size_t) kk * ld;
+            v[r]            = cg ? __ldcg(p) : *p;
+        }
+#pragma unroll
+        for (int r = 0; r < 16; ++r)
+        {
+            const int e = tid + r * 256;
+            dst[e >> 6][e & 63] = v[r];
+        }
+    }
+
+    // grid: rem (rem + 1) / 2 CTAs for k >= 0, rem CTAs for k = -1 (rem = nb - k - 1); 256 threads;
+    // dynamic shared memory CHOL_SMEM_BYTES.
+    __global__ void __launch_bounds__(256)
+        chol_step_kernel(double* L, double* W, int ld, int k, int nb, int* flags, int* info)
+    {
+        extern __shared__ __align__(16) double csm[];
+        double(*As)[CHOL_LDS] = reinterpret_cast<double(*)[CHOL_LDS]>(csm);
+        double(*Bs)[CHOL_LDS] = As + TILE;
+
+        const int rem = nb - k - 1, t = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+        int       tm, tn;
+        if (t < rem)
+            tm = k + 1 + t, tn = k + 1;
+        else
+        {
+            int a, b;
+            lower_tile(t - rem, a, b);
+            tm = k + 2 + a, tn = k + 2 + b;
+        }
+        double* Ct = L + (size_t) tm * TILE + (size_t) tn * TILE * ld;
+
+        double c[4][4]; // the tile itself first (independent of the operand loads), then tile - update
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c[i][j] = Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld];
+        if (k >= 0)
+        {
+            load_tile_64(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            load_tile_64(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            __syncthreads();
+            double acc[4][4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+            tile_mma_64(As, Bs, tx, ty, acc);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) c[i][j] -= acc[i][j];
+        }
+
+        if (t >= rem) // plain trailing tile
+        {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld] = c[i][j];
+            return;
+        }
+
+        __syncthreads(); // everyone is done reading As / Bs
+        if (t == 0)
+        {
+            // next diagonal tile: factorise + invert in registers, publish L, W and the flag
+            double* colbuf = csm;
+            double* dv     = csm + 2 * (TILE + 2);
+            double* rs     = dv + TILE;
+            int*    sbad   = reinterpret_cast<int*>(rs + TILE);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (ty + 16 * j > tx + 16 * i) c[i][j] = 0.0;
+            potf2_inverse_regs(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
+            double* Wt = W + (size_t) tn * TILE * ((size_t) ld + 1);
+            // L[p][q] = S[p][q] rs[q] for q <= p (the diagonal is d * d^-1/2), 0 above; written straight from registers
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                {
+                    const int p = tx + 16 * i, q = ty + 16 * j;
+                    Ct[(size_t) p + (size_t) q * ld] = q <= p ? c[i][j] * rs[q] : 0.0;
+                }
+            // W[q][p] = R[q][p] rs[q] = S[p][q] rs[q] for p < q: transpose through shared memory so the store coalesces
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                {
+                    const int p = tx + 16 * i, q = ty + 16 * j;
+                    Bs[p][q]    = q > p ? c[i][j] * rs[q] : (q == p ? rs[q] : 0.0); // Bs[column of W][row of W]
+                }
+            __syncthreads();
+#pragma unroll
+            for (int r = 0; r < 16; ++r)
+            {
+                const int e = tid + r * 256, row = e & 63, cl = e >> 6;
+                Wt[(size_t) row + (size_t) cl * ld] = Bs[cl][row];
+            }
+            __threadfence();
+            __syncthreads();
+            if (tid == 0) atomicExch(&flags[tn], 1);
+            return;
+        }
+
+        // panel tile below the next diagonal: L[tm,tn] = C * W^T once W is published
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) As[ty + 16 * j][tx + 16 * i] = c[i][j]; // As[n][m] = C(m, n)
+        if (tid == 0)
+        {
+            while (atomicAdd(&flags[tn], 0) == 0) __nanosleep(32);
+            __threadfence();
+        }
+        __syncthreads();
+        // Bs[n][cc] = W(cc, n): W is column-major, so row n of Bs is column n of W
+        load_tile_64(Bs, W + (size_t) tn * TILE * ((size_t) ld + 1), ld, tid, true);
+        __syncthreads();
+        double acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        tile_mma_64(As, Bs, tx, ty, acc);
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld] = acc[i][j];
+    }
+} // namespace slsgp

@@ -10,6 +10,7 @@
 #include "../../include/slsgp.h"
 
 #include "common.cuh"
+#include "chol.cuh"
 #include "dense.cuh"
 #include "gram.cuh"
 #include "map.cuh"
@@ -61,7 +62,7 @@ struct slsgp_ctx
          has_alpha = false;
     std::vector<double> theta_host;
 
-    DevBuf X, Xpad, XT1, theta, inv_l, K, L, W, Kinv, T, y, alpha, Kalpha, vec, scalars, info, fbest, fbest_idx;
+    DevBuf X, Xpad, XT1, theta, inv_l, K, L, W, Kinv, T, y, alpha, Kalpha, vec, scalars, info, fbest, fbest_idx, chol_flags;
     DevBuf pref_off, pref_idx, slot_off, slot_list, loglik, contrib, grad_y, Ymat, g_l;
     int    P = 0, pref_total = 0;
     DevBuf Xq, Kstar, Gstar, Beta, P1, P2, stats, o_mu, o_sigma, o_dmu, o_dsigma, o_val, o_grad, am_part, am_acc;
@@ -275,31 +276,23 @@ namespace
         CUDA_TRY(cudaMemsetAsync(ctx->info.p, 0, sizeof(int), ctx->stream));
         double* L = dp(ctx->L);
         double* W = dp(ctx->W);
-        for (int kb = 0; kb < nb; ++kb)
+        TRY(ensure(ctx, ctx->chol_flags, sizeof(int) * (size_t) nb));
+        CUDA_TRY(cudaMemsetAsync(ctx->chol_flags.p, 0, sizeof(int) * (size_t) nb, ctx->stream));
+        static bool chol_attr = false;
+        if (!chol_attr)
         {
-            const size_t dg = (size_t) kb * TILE * ((size_t) ld + 1);
-            {
-                ProfScope ps(ctx, "potf2");
-                potf2_inverse_kernel<<<1, 256, 0, ctx->stream>>>(L + dg, ld, W + dg, ld, kb * TILE, ptr<int>(ctx->info));
-                LAUNCH_CHECK();
-            }
-            const int rem = ld - (kb + 1) * TILE;
-            if (rem <= 0) break;
-            double* L21 = L + dg + TILE;                          // rows below the diagonal block
-            double* A22 = L + dg + TILE * ((size_t) ld + 1);      // trailing matrix
-            // panel: L21 <- A21 * W_kk^T   (== A21 * L_kk^-T)
-            GemmArgs p = gemm_args(L21, W + dg, L21, rem, TILE, TILE, ld, ld, ld, 1.0, 0.0);
-            {
-                ProfScope ps(ctx, "chol_panel");
-                TRY((launch_gemm<false, true>(ctx, p)));
-            }
-            // trailing update: A22 <- A22 - L21 * L21^T (lower tiles)
-            GemmArgs u   = gemm_args(L21, L21, A22, rem, rem, TILE, ld, ld, ld, -1.0, 1.0);
-            u.lower_only = 1;
-            {
-                ProfScope ps(ctx, "chol_syrk");
-                TRY((launch_gemm<false, true>(ctx, u)));
-            }
+            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+            chol_attr = true;
+        }
+        // launch k finishes block column k+1 (diagonal factor + panel) while updating the rest of the trailing matrix
+        for (int k = -1; k <= nb - 2; ++k)
+        {
+            const int rem  = nb - k - 1;
+            const int grid = k < 0 ? rem : rem * (rem + 1) / 2;
+            ProfScope ps(ctx, "chol_step");
+            chol_step_kernel<<<grid, 256, CHOL_SMEM_BYTES, ctx->stream>>>(L, W, ld, k, nb, ptr<int>(ctx->chol_flags),
+                                                                          ptr<int>(ctx->info));
+            LAUNCH_CHECK();
         }
         zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
         LAUNCH_CHECK();
@@ -558,6 +551,13 @@ namespace
         {
             ProfScope    ps(ctx, "tc_kstar");
             const size_t smem = sizeof(float) * (size_t) (64 * (D + 1) + D * 128);
+            static bool  kstar_attr = false;
+            if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
+            {
+                CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int) (sizeof(float) * (64 * 68 + 67 * 128))));
+                kstar_attr = true;
+            }
             kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, ctx->stream>>>(
                 d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs),
                 ptr<__half>(ctx->Ks), Ks_lo);
@@ -694,7 +694,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err};
+                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)
