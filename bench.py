@@ -256,7 +256,6 @@ def main_graft(args):
     Xq = [torch.rand((M, DIM), dtype=torch.float64, device="cuda", generator=gen) for _ in range(nb)]
     val = torch.empty(M, dtype=torch.float64, device="cuda")
     grad = torch.empty((M, DIM), dtype=torch.float64, device="cuda")
-    gather = [torch.zeros(2, dtype=torch.float64, device="cuda") for _ in range(world)]
     torch.cuda.synchronize()
 
     def step(i, m=M):
@@ -264,11 +263,7 @@ def main_graft(args):
         ctx.acq_batch_device(ACQ_EI, 1.0, q.data_ptr(), m, d_val=val.data_ptr(), d_grad=grad.data_ptr())
         v, idx = ctx.argmax_device(val.data_ptr(), m, index0=rank * M)  # synchronises this rank's stream
         if world > 1:  # the only collective on the path: (value, index) of every rank's winner
-            mine = torch.tensor([v, float(idx)], dtype=torch.float64, device="cuda")
-            dist.all_gather(gather, mine)
-            allv = torch.stack(gather).cpu().numpy()
-            w = int(np.lexsort((allv[:, 1], -allv[:, 0]))[0])
-            return float(allv[w, 0]), int(allv[w, 1])
+            return pkg.sharding.all_gather_winner(v, idx, device="cuda")
         return v, idx
 
     def barrier():

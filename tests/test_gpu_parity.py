@@ -231,3 +231,11 @@ def test_full_size_properties(ctx):
         vm, _ = ctx.acq_batch(1, 2.0, Q - e, grads=False)
         np.testing.assert_allclose(grad[d_], (vp - vm) / (2 * eps), rtol=2e-5, atol=1e-8)
     ctx.set_compat_flags(1)
+
+
+def test_numpy_candidate_generator_matches_the_library(ctx, slsb):
+    """sharding.candidate_coords (used by the CPU multi-rank tests) is the same sequence as slsgp_candidates."""
+    X = S.make_X(10, 7, "uniform")
+    ctx.set_data(X)
+    for seed, first, count in ((0, 0, 100), (1234, 10**9, 257), (2**63 + 5, 3, 64)):
+        np.testing.assert_array_equal(ctx.candidates(seed, first, count), slsb.sharding.candidate_coords(seed, first, count, 7))

@@ -170,7 +170,10 @@ def test_tensor_mode_tracks_model_updates(ctx, slsb):
         ctx.set_sweep_mode(slsb.SWEEP_FP64)
         v0, g0 = ctx.acq_batch(1, 2.0, Q)
         check("UCB", v, v0)
-        check("grad UCB", g, g0)
+        # stale operands would be O(1) off; the gradient bound is looser than RT32 here because with D = 5 many of the
+        # candidates sit next to data (sigma ~ 0.1) under length scales down to 0.2, and grad sigma amplifies the
+        # fp32-class error of the contraction (~1e-5) by 1 / (sigma l^2) ~ 250
+        check("grad UCB", g, g0, 1e-2)
 
 
 def test_tensor_mode_limits_are_reported(ctx, slsb):
