@@ -63,7 +63,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _LIB_PATH
+    path = os.environ.get("SLSGP_LIB", _LIB_PATH)  # override: A/B runs of two builds on the GPU box
     if not os.path.exists(path):
         if not build_if_missing:
             raise RuntimeError(f"{path} is missing; run `python __graft_entry__.py build`")

@@ -73,7 +73,8 @@ struct slsgp_ctx
     CUtensorMap tmA, tmB;
     int         ldt = 0, XP = 0;
     bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
-    long long   tc_Mcap = 0;      // rows of Ks (multiple of 128)
+    long long   tc_Mcap = 0;      // rows of Ks (multiple of 128 * tc_ncta)
+    int         tc_ncta = 2;      // CTAs per UMMA (1: cta_group::1, 2: CTA pair); SLSGP_TC_PAIR=0 selects 1
 
     double* pinned       = nullptr; // small host staging area
     size_t  pinned_bytes = 0;
@@ -391,7 +392,7 @@ namespace
         const bool tensor = is_tensor_mode(ctx->sweep_mode);
         if (tensor) TRY(prepare_tensor(ctx));
         long long cap = std::min<long long>(std::max<long long>(want, 64), tensor ? tc_shard_cap() : 16384);
-        cap           = round_up64(cap, tensor ? TC_BM : TILE);
+        cap           = round_up64(cap, tensor ? TC_BM * ctx->tc_ncta : TILE);
         if (tensor && ctx->tc_Mcap < cap)
         {
             // rows [0, cap): k16, rows [cap, 2 cap): its fp16 rounding residual (read only by the split-precision passes)
@@ -495,7 +496,7 @@ namespace
         tc_pack_x_kernel<<<(ldt + 255) / 256, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, XP, ldt, dp(ctx->inv_l),
                                                                     ptr<float>(ctx->Xt), ptr<float>(ctx->Xs32));
         LAUNCH_CHECK();
-        TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN));
+        TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN / ctx->tc_ncta));
         ctx->tc_ready = true;
         return SLSGP_OK;
     }
@@ -512,22 +513,41 @@ namespace
         return cap;
     }
 
-    template <int XP> slsgp_status launch_tc_gemm(slsgp_ctx* ctx, const TcGemmParams& prm_in, int n_sm)
+    template <int XP, int NCTA> slsgp_status launch_tc_gemm_n(slsgp_ctx* ctx, const TcGemmParams& prm_in, int n_sm)
     {
         TcGemmParams prm   = prm_in;
-        const size_t fixed = (size_t) TC_BN * XP * sizeof(float) + 1024;
-        prm.stages         = (int) std::min<size_t>(TC_MAX_STAGES, (232448 - 512 - fixed) / TC_STAGE_BYTES);
-        const size_t smem  = (size_t) prm.stages * TC_STAGE_BYTES + fixed;
-        static bool  attr_set = false;
-        if (!attr_set)
+        const size_t fixed = (size_t) tc_xs_cols(XP) * XP * sizeof(float) + 1024;
+        prm.stage_bytes    = tc_stage_bytes(prm.passes, NCTA);
+        prm.stages         = (int) std::min<size_t>(TC_MAX_STAGES, (232448 - 512 - fixed) / prm.stage_bytes);
+        if (prm.stages < 2) return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: pipeline does not fit in shared memory");
+        const size_t smem  = (size_t) prm.stages * prm.stage_bytes + fixed;
+        static size_t attr_smem = 0;
+        if (attr_smem < smem)
         {
-            CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
-            attr_set = true;
+            CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            attr_smem = smem;
         }
-        const int grid = std::min(prm.n_cand_blocks, n_sm);
-        tc_sweep_gemm_kernel<XP><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
+        const int groups = prm.n_cand_blocks / NCTA;
+        const int grid   = std::min(groups, n_sm / NCTA) * NCTA;
+        if (NCTA == 1)
+            tc_sweep_gemm_kernel<XP, NCTA><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
+        else
+        {
+            cudaLaunchConfig_t  cfg = {};
+            cudaLaunchAttribute attr[1];
+            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(TC_THREADS), cfg.dynamicSmemBytes = smem, cfg.stream = ctx->stream;
+            attr[0].id               = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = NCTA, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr, cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_sweep_gemm_kernel<XP, NCTA>, ctx->tmA, ctx->tmB, prm));
+        }
         LAUNCH_CHECK();
         return SLSGP_OK;
+    }
+
+    template <int XP> slsgp_status launch_tc_gemm(slsgp_ctx* ctx, const TcGemmParams& prm, int n_sm)
+    {
+        return ctx->tc_ncta == 2 ? launch_tc_gemm_n<XP, 2>(ctx, prm, n_sm) : launch_tc_gemm_n<XP, 1>(ctx, prm, n_sm);
     }
 
     slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out)
@@ -544,7 +564,7 @@ namespace
                                     SweepOut out)
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
-        const long long Mpad = round_up64(Mc, TC_BM);
+        const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
         __half*         Ks_lo = passes > 1 ? ptr<__half>(ctx->Ks) + (size_t) ctx->tc_Mcap * ldt : nullptr;
         static int      n_sm = 0;
         if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
@@ -672,6 +692,7 @@ extern "C"
             return SLSGP_ERR_CUDA;
         }
         ctx->stream       = ctx->own_stream;
+        if (const char* e = std::getenv("SLSGP_TC_PAIR")) ctx->tc_ncta = std::atoi(e) ? 2 : 1;
         ctx->pinned_bytes = 1 << 16;
         if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess)
         {

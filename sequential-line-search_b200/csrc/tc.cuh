@@ -132,6 +132,97 @@ namespace slsgp
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
         }
 
+        // ---- CTA pair (cta_group::2) variants: the leader CTA (cluster rank 0) issues the MMAs for both SMs ----------
+        __device__ __forceinline__ uint32_t cluster_ctarank()
+        {
+            uint32_t r;
+            asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+            return r;
+        }
+        // shared::cluster address of `smem_addr` (a shared::cta address of this CTA) inside CTA `rank` of the cluster
+        __device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank)
+        {
+            uint32_t r;
+            asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+            return r;
+        }
+        __device__ __forceinline__ void cluster_sync_all() // every thread of every CTA of the cluster
+        {
+            asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+            asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        }
+        __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) // bar given as a shared::cluster address
+        {
+            asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+        }
+        // TMA load whose completion bytes are posted on a barrier that may live in the peer CTA of the pair
+        __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* map, uint32_t cluster_bar, int c0, int c1)
+        {
+            asm volatile(
+                "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+                : "memory");
+        }
+        __device__ __forceinline__ void tmem_alloc_pair(uint32_t smem_dst, uint32_t ncols) // same warp id in both CTAs
+        {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        }
+        __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols)
+        {
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+        }
+        // D (256 x N, rows split over the two CTAs' TMEM) (+)= A (128 rows per CTA) * B^T (N/2 rows per CTA)
+        __device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                      uint32_t accumulate)
+        {
+            asm volatile(
+                "{\n\t"
+                ".reg .pred p;\n\t"
+                "setp.ne.b32 p, %4, 0;\n\t"
+                "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+                "}"
+                ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+                : "memory");
+        }
+        // arrive on the barrier at the same shared-memory offset in every CTA of `mask` once the issued UMMAs are done
+        __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t mask)
+        {
+            asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                         ::"r"(bar), "h"(mask)
+                         : "memory");
+        }
+
+        template <int NCTA>
+        __device__ __forceinline__ void umma_f16_n(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate)
+        {
+            if (NCTA == 2)
+                umma_f16_pair(tmem_d, desc_a, desc_b, idesc, accumulate);
+            else
+                umma_f16(tmem_d, desc_a, desc_b, idesc, accumulate);
+        }
+        template <int NCTA> __device__ __forceinline__ void umma_commit_n(uint32_t bar)
+        {
+            if (NCTA == 2)
+                umma_commit_pair(bar, 3);
+            else
+                umma_commit(bar);
+        }
+        // One lane of a converged warp (elect.sync): true in exactly one lane.
+        __device__ __forceinline__ bool elect_one()
+        {
+            uint32_t pred = 0;
+            asm volatile(
+                "{\n\t"
+                ".reg .b32 rx;\n\t"
+                ".reg .pred px;\n\t"
+                "elect.sync rx|px, 0xFFFFFFFF;\n\t"
+                "selp.u32 %0, 1, 0, px;\n\t"
+                "}"
+                : "=r"(pred));
+            return pred != 0;
+        }
+
         // ---- tcgen05: TMEM -> registers ----------------------------------------------------------------------------------
         // Each thread of the warp receives N consecutive 32-bit columns of its own lane (warp w may only touch lanes
         // 32 * (w % 4) .. + 31). Asynchronous: tmem_ld_wait() before the registers are read.

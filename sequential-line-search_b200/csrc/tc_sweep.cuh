@@ -206,7 +206,8 @@ namespace slsgp
         int              ncb;           // regular column blocks = ldt / 256
         int              D;
         int              stages;        // shared-memory pipeline depth
-        int              n_cand_blocks; // ceil(Mc / 128)
+        int              stage_bytes;   // bytes of one pipeline stage in ONE CTA (see tc_stage_bytes)
+        int              n_cand_blocks; // ceil(Mc / 128), rounded up to the CTAs per cluster
         long long        Mc;
         int              passes;    // 1: k16 x A16 | 2: + k16 x A_lo | 3: + k_lo x A16 (split-fp16, fp32-class result)
         int              a_lo_row;  // row offset of the k residuals inside the Ks tensor map
@@ -223,12 +224,29 @@ namespace slsgp
         int*             err;
     };
 
-    template <int XP>
+    // One pipeline stage = one 64-wide step of the contraction with EVERY operand tile the split-precision passes need,
+    // so each tile is fetched from L2 once per step and reused by up to three UMMA groups:
+    //   [k16 128x64] [k_lo 128x64 if passes == 3] [A_hi (256/NCTA)x64] [A_lo (256/NCTA)x64 if passes >= 2]
+    // (L2 -> SM bytes per UMMA: 12 KB with one pass per stage, 8 KB here, 5.3 KB with the CTA pair.)
+    __host__ __device__ inline int tc_stage_bytes(int passes, int ncta)
+    {
+        return TC_A_BYTES * (passes == 3 ? 2 : 1) + (TC_B_BYTES / ncta) * (passes >= 2 ? 2 : 1);
+    }
+    // columns of Xt staged in shared memory at a time (<= 20 KB whatever XP is)
+    __host__ __device__ constexpr int tc_xs_cols(int XP) { return XP <= 20 ? 256 : (XP <= 36 ? 128 : 64); }
+
+    // NCTA = 1: one CTA per SM, UMMA 128 x 256. NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on 256
+    // candidates with UMMA 256 x 256; each CTA stages its own 128 k rows and HALF of every Kinv tile, the leader (cluster
+    // rank 0) issues the MMAs for both SMs, and each CTA runs the epilogue of its own 128 TMEM lanes.
+    template <int XP, int NCTA>
     __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_sweep_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const TcGemmParams p)
     {
-        constexpr int EC = (2 * XP + 15) / 16 * 16; // extras columns: (hi, lo) pairs
+        constexpr int EC       = (2 * XP + 15) / 16 * 16; // extras columns: (hi, lo) pairs
+        constexpr int XS_COLS  = tc_xs_cols(XP);
+        constexpr int BH_BYTES = TC_B_BYTES / NCTA;       // this CTA's share of a Kinv tile
+        constexpr int BH_ROWS  = TC_BN / NCTA;
         extern __shared__ uint8_t smem_raw[];
         __shared__ __align__(8) uint64_t full_bar[TC_MAX_STAGES], empty_bar[TC_MAX_STAGES], tfull_bar[2], tempty_bar[2];
         __shared__ uint32_t tmem_base_smem;
@@ -237,9 +255,15 @@ namespace slsgp
         const uint32_t pad      = ((raw_addr + 1023u) & ~1023u) - raw_addr;
         uint8_t*       smem     = smem_raw + pad; // 1024-byte aligned: required by the 128-byte swizzle
         const uint32_t smem_a0  = raw_addr + pad;
-        float*         Xs       = reinterpret_cast<float*>(smem + (size_t) p.stages * TC_STAGE_BYTES); // [256][XP]
+        float*         Xs       = reinterpret_cast<float*>(smem + (size_t) p.stages * p.stage_bytes); // [XS_COLS][XP]
 
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const int      warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        const uint32_t rank = NCTA == 2 ? tc::cluster_ctarank() : 0u;
+        const int      cid = blockIdx.x / NCTA, ncl = gridDim.x / NCTA, n_groups = p.n_cand_blocks / NCTA;
+        const int      P       = p.passes;
+        const uint32_t off_a1  = TC_A_BYTES;                       // k_lo tile (passes == 3)
+        const uint32_t off_b0  = TC_A_BYTES * (P == 3 ? 2 : 1);    // Kinv hi (or the extras)
+        const uint32_t off_b1  = off_b0 + BH_BYTES;                // Kinv lo (passes >= 2)
 
         if (warp == 0 && lane == 0)
         {
@@ -256,71 +280,120 @@ namespace slsgp
             for (int s = 0; s < 2; ++s)
             {
                 tc::mbar_init(tc::smem_u32(&tfull_bar[s]), 1);
-                tc::mbar_init(tc::smem_u32(&tempty_bar[s]), 128);
+                tc::mbar_init(tc::smem_u32(&tempty_bar[s]), 128 * NCTA);
             }
             tc::fence_mbar_init();
         }
-        if (warp == 2) tc::tmem_alloc(tc::smem_u32(&tmem_base_smem), 512);
+        if (warp == 2)
+        {
+            if (NCTA == 2)
+                tc::tmem_alloc_pair(tc::smem_u32(&tmem_base_smem), 512);
+            else
+                tc::tmem_alloc(tc::smem_u32(&tmem_base_smem), 512);
+        }
         tc::fence_before_sync();
         __syncthreads();
+        if (NCTA == 2) tc::cluster_sync_all(); // the peer's barriers are initialised before anything is posted on them
         tc::fence_after_sync();
         const uint32_t tmem_base = tmem_base_smem;
 
         if (warp == 0)
         {
-            // ===== TMA producer =====
-            if (lane == 0)
+            // ===== TMA producer: the whole warp walks the loop (warp-uniform control flow keeps the addresses in uniform
+            // registers); one elected lane issues. Both CTAs of a pair post their bytes on the leader's barrier. =====
+            const bool elected = tc::elect_one();
+            uint32_t   it = 0;
+            for (int g = cid; g < n_groups; g += ncl)
             {
-                uint32_t it = 0;
-                for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
-                    for (int cb = 0; cb <= p.ncb; ++cb)
-                        for (int ps = 0; ps < p.passes; ++ps)
+                const int cbk = g * NCTA + (int) rank;
+                for (int cb = 0; cb <= p.ncb; ++cb)
+                {
+                    const bool     extras = cb == p.ncb;
+                    const bool     two_b  = P >= 2 && !extras;
+                    const int      b_row  = extras ? p.ldt + (int) rank * (EC / NCTA) : cb * TC_BN + (int) rank * BH_ROWS;
+                    const uint32_t tx     = (uint32_t) NCTA * (TC_A_BYTES * (P == 3 ? 2 : 1) + BH_BYTES * (two_b ? 2 : 1));
+                    for (int k = 0; k < p.kb; ++k, ++it)
+                    {
+                        const uint32_t s = it % p.stages, n = it / p.stages;
+                        tc::mbar_wait(tc::smem_u32(&empty_bar[s]), (n & 1) ^ 1, p.err, 1);
+                        const uint32_t sa = smem_a0 + s * p.stage_bytes;
+                        if (elected)
                         {
-                            if (cb == p.ncb && ps == 1) continue; // the extras carry their own lo rows
-                            const int a_row = cbk * TC_BM + (ps == 2 ? p.a_lo_row : 0);
-                            const int b_row = cb * TC_BN + (ps == 1 ? p.b_lo_row : 0);
-                            for (int k = 0; k < p.kb; ++k, ++it)
+                            if (NCTA == 1)
                             {
-                                const uint32_t s = it % p.stages, n = it / p.stages;
-                                tc::mbar_wait(tc::smem_u32(&empty_bar[s]), (n & 1) ^ 1, p.err, 1);
                                 const uint32_t fb = tc::smem_u32(&full_bar[s]);
-                                tc::mbar_arrive_expect_tx(fb, TC_STAGE_BYTES);
-                                const uint32_t sa = smem_a0 + s * TC_STAGE_BYTES;
-                                tc::tma_load_2d(sa, &tmA, fb, k * TC_BK, a_row);
-                                tc::tma_load_2d(sa + TC_A_BYTES, &tmB, fb, k * TC_BK, b_row);
+                                tc::mbar_arrive_expect_tx(fb, tx);
+                                tc::tma_load_2d(sa, &tmA, fb, k * TC_BK, cbk * TC_BM);
+                                if (P == 3) tc::tma_load_2d(sa + off_a1, &tmA, fb, k * TC_BK, cbk * TC_BM + p.a_lo_row);
+                                tc::tma_load_2d(sa + off_b0, &tmB, fb, k * TC_BK, b_row);
+                                if (two_b) tc::tma_load_2d(sa + off_b1, &tmB, fb, k * TC_BK, b_row + p.b_lo_row);
+                            }
+                            else
+                            {
+                                const uint32_t fb = tc::map_to_cta(tc::smem_u32(&full_bar[s]), 0);
+                                if (rank == 0) tc::mbar_arrive_expect_tx(tc::smem_u32(&full_bar[s]), tx);
+                                tc::tma_load_2d_pair(sa, &tmA, fb, k * TC_BK, cbk * TC_BM);
+                                if (P == 3) tc::tma_load_2d_pair(sa + off_a1, &tmA, fb, k * TC_BK, cbk * TC_BM + p.a_lo_row);
+                                tc::tma_load_2d_pair(sa + off_b0, &tmB, fb, k * TC_BK, b_row);
+                                if (two_b) tc::tma_load_2d_pair(sa + off_b1, &tmB, fb, k * TC_BK, b_row + p.b_lo_row);
                             }
                         }
+                        __syncwarp();
+                    }
+                }
             }
         }
         else if (warp == 1)
         {
-            // ===== MMA issuer (one thread) =====
-            if (lane == 0)
+            // ===== MMA issuer (the leader CTA only when paired): warp-uniform loop, one elected lane issues =====
+            if (rank == 0)
             {
-                const uint32_t idesc_full = tc::instr_desc_f16(TC_BM, TC_BN), idesc_extra = tc::instr_desc_f16(TC_BM, EC);
+                const bool     elected    = tc::elect_one();
+                const uint32_t idesc_full = tc::instr_desc_f16(TC_BM * NCTA, TC_BN), idesc_extra = tc::instr_desc_f16(TC_BM * NCTA, EC);
                 uint32_t       it = 0, t = 0;
-                for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
+                for (int g = cid; g < n_groups; g += ncl)
                     for (int cb = 0; cb <= p.ncb; ++cb, ++t)
                     {
+                        const bool     extras = cb == p.ncb;
+                        const bool     two_b = P >= 2 && !extras, two_a = P == 3;
                         const uint32_t slot = t & 1, use = t >> 1;
                         tc::mbar_wait(tc::smem_u32(&tempty_bar[slot]), (use & 1) ^ 1, p.err, 2);
                         tc::fence_after_sync();
                         const uint32_t d_tmem = tmem_base + slot * TC_BN;
-                        const uint32_t idesc  = cb < p.ncb ? idesc_full : idesc_extra;
-                        const int n_k = ((cb == p.ncb && p.passes > 1) ? p.passes - 1 : p.passes) * p.kb;
-                        for (int k = 0; k < n_k; ++k, ++it)
+                        const uint32_t idesc  = extras ? idesc_extra : idesc_full;
+                        for (int k = 0; k < p.kb; ++k, ++it)
                         {
                             const uint32_t s = it % p.stages, n = it / p.stages;
                             tc::mbar_wait(tc::smem_u32(&full_bar[s]), n & 1, p.err, 3);
                             tc::fence_after_sync();
-                            const uint32_t sa = smem_a0 + s * TC_STAGE_BYTES;
-                            const uint64_t da = tc::smem_desc_k_sw128(sa), db = tc::smem_desc_k_sw128(sa + TC_A_BYTES);
+                            if (elected)
+                            {
+                                const uint32_t sa  = smem_a0 + s * p.stage_bytes;
+                                const uint64_t da0 = tc::smem_desc_k_sw128(sa), da1 = tc::smem_desc_k_sw128(sa + off_a1);
+                                const uint64_t db0 = tc::smem_desc_k_sw128(sa + off_b0), db1 = tc::smem_desc_k_sw128(sa + off_b1);
+                                const uint32_t acc0 = k != 0 ? 1u : 0u;
+                                // 16 fp16 = 32 bytes = 2 descriptor units per UMMA_K; groups: k16 x A_hi, k16 x A_lo, k_lo x A_hi
 #pragma unroll
-                            for (int kk = 0; kk < TC_BK / 16; ++kk) // 16 fp16 = 32 bytes = 2 descriptor units per UMMA_K
-                                tc::umma_f16(d_tmem, da + 2 * kk, db + 2 * kk, idesc, (k | kk) != 0 ? 1u : 0u);
-                            tc::umma_commit(tc::smem_u32(&empty_bar[s])); // frees the stage once these MMAs have read it
+                                for (int kk = 0; kk < TC_BK / 16; ++kk)
+                                    tc::umma_f16_n<NCTA>(d_tmem, da0 + 2 * kk, db0 + 2 * kk, idesc, kk ? 1u : acc0);
+                                if (two_b)
+                                {
+#pragma unroll
+                                    for (int kk = 0; kk < TC_BK / 16; ++kk)
+                                        tc::umma_f16_n<NCTA>(d_tmem, da0 + 2 * kk, db1 + 2 * kk, idesc, 1u);
+                                }
+                                if (two_a)
+                                {
+#pragma unroll
+                                    for (int kk = 0; kk < TC_BK / 16; ++kk)
+                                        tc::umma_f16_n<NCTA>(d_tmem, da1 + 2 * kk, db0 + 2 * kk, idesc, 1u);
+                                }
+                                // frees the stage (in both CTAs) once these MMAs have read it
+                                tc::umma_commit_n<NCTA>(tc::smem_u32(&empty_bar[s]));
+                                if (k == p.kb - 1) tc::umma_commit_n<NCTA>(tc::smem_u32(&tfull_bar[slot])); // accumulator complete
+                            }
+                            __syncwarp();
                         }
-                        tc::umma_commit(tc::smem_u32(&tfull_bar[slot])); // accumulator complete
                     }
             }
         }
@@ -330,8 +403,12 @@ namespace slsgp
             const int      quad = warp & 3, row = quad * 32 + lane, et = threadIdx.x - 128;
             const float    inv_u = p.sc->inv_u, inv_e = p.sc->inv_e;
             uint32_t       t = 0;
-            for (int cbk = blockIdx.x; cbk < p.n_cand_blocks; cbk += gridDim.x)
+            // the accumulator-free barriers live in the leader CTA
+            const uint32_t tempty0 = NCTA == 2 ? tc::map_to_cta(tc::smem_u32(&tempty_bar[0]), 0) : tc::smem_u32(&tempty_bar[0]);
+            const uint32_t tempty1 = NCTA == 2 ? tc::map_to_cta(tc::smem_u32(&tempty_bar[1]), 0) : tc::smem_u32(&tempty_bar[1]);
+            for (int g = cid; g < n_groups; g += ncl)
             {
+                const int       cbk  = g * NCTA + (int) rank;
                 const long long m    = (long long) cbk * TC_BM + row;
                 const __half*   krow = p.Ks + (size_t) m * p.ldt;
                 const __half*   lrow = p.Ks_lo ? p.Ks_lo + (size_t) m * p.ldt : nullptr;
@@ -343,61 +420,71 @@ namespace slsgp
 
                 for (int cb = 0; cb < p.ncb; ++cb, ++t)
                 {
-                    // stage this block's rows of Xt (256 x XP floats)
-                    tc::named_bar_sync(1, 128);
-                    {
-                        const float4* src = reinterpret_cast<const float4*>(p.Xt + (size_t) cb * TC_BN * XP);
-                        float4*       dst = reinterpret_cast<float4*>(Xs);
-                        for (int e = et; e < TC_BN * XP / 4; e += 128) dst[e] = src[e];
-                    }
-                    tc::named_bar_sync(1, 128);
-
                     const uint32_t slot = t & 1, use = t >> 1;
-                    tc::mbar_wait(tc::smem_u32(&tfull_bar[slot]), use & 1, p.err, 4);
-                    tc::fence_after_sync();
                     const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + slot * TC_BN;
                     const uint4*   kptr  = reinterpret_cast<const uint4*>(krow + (size_t) cb * TC_BN);
                     const uint4*   lptr  = lrow ? reinterpret_cast<const uint4*>(lrow + (size_t) cb * TC_BN) : nullptr;
 #pragma unroll 1
-                    for (int ch = 0; ch < TC_BN / 32; ++ch)
+                    for (int xs = 0; xs < TC_BN / XS_COLS; ++xs)
                     {
-                        uint32_t r[32];
-                        tc::tmem_ld_x32(taddr + ch * 32, r);
-                        uint4 kv[4], lv[4];
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) kv[v] = __ldg(kptr + ch * 4 + v);
-#pragma unroll
-                        for (int v = 0; v < 4; ++v) lv[v] = lrow ? __ldg(lptr + ch * 4 + v) : make_uint4(0, 0, 0, 0);
-                        tc::tmem_ld_wait();
-                        const __half2* kh = reinterpret_cast<const __half2*>(kv);
-                        const __half2* lh = reinterpret_cast<const __half2*>(lv);
-#pragma unroll
-                        for (int c2 = 0; c2 < 16; ++c2)
+                        // stage the matching rows of Xt (XS_COLS x XP floats)
+                        tc::named_bar_sync(1, 128);
                         {
-                            const float2 kf = __half22float2(kh[c2]), lf = __half22float2(lh[c2]);
+                            const float4* src = reinterpret_cast<const float4*>(p.Xt + ((size_t) cb * TC_BN + (size_t) xs * XS_COLS) * XP);
+                            float4*       dst = reinterpret_cast<float4*>(Xs);
+                            for (int e = et; e < XS_COLS * XP / 4; e += 128) dst[e] = src[e];
+                        }
+                        tc::named_bar_sync(1, 128);
+                        if (xs == 0)
+                        {
+                            tc::mbar_wait(tc::smem_u32(&tfull_bar[slot]), use & 1, p.err, 4);
+                            tc::fence_after_sync();
+                        }
+#pragma unroll 1
+                        for (int chl = 0; chl < XS_COLS / 32; ++chl)
+                        {
+                            const int ch = xs * (XS_COLS / 32) + chl;
+                            uint32_t  r[32];
+                            tc::tmem_ld_x32(taddr + ch * 32, r);
+                            uint4 kv[4], lv[4];
 #pragma unroll
-                            for (int h = 0; h < 2; ++h)
+                            for (int v = 0; v < 4; ++v) kv[v] = __ldg(kptr + ch * 4 + v);
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) lv[v] = lrow ? __ldg(lptr + ch * 4 + v) : make_uint4(0, 0, 0, 0);
+                            tc::tmem_ld_wait();
+                            const __half2* kh = reinterpret_cast<const __half2*>(kv);
+                            const __half2* lh = reinterpret_cast<const __half2*>(lv);
+#pragma unroll
+                            for (int c2 = 0; c2 < 16; ++c2)
                             {
-                                const int     c  = c2 * 2 + h;
-                                const float   u  = __uint_as_float(r[c]);
-                                const float   k1 = h ? kf.y : kf.x, dk = h ? lf.y : lf.x;
-                                const float   tv = (k1 + dk) * u;            // gradient sums
-                                const float   tq = fmaf(qw * dk, u, k1 * u); // quadratic form
-                                const float4* xr = reinterpret_cast<const float4*>(Xs + (ch * 32 + c) * XP);
+                                const float2 kf = __half22float2(kh[c2]), lf = __half22float2(lh[c2]);
 #pragma unroll
-                                for (int q4 = 0; q4 < XP / 4; ++q4)
+                                for (int h = 0; h < 2; ++h)
                                 {
-                                    const float4 xv = xr[q4];
-                                    acc[q4 * 4 + 0] = fmaf(xv.x, q4 == 0 ? tq : tv, acc[q4 * 4 + 0]);
-                                    acc[q4 * 4 + 1] = fmaf(xv.y, tv, acc[q4 * 4 + 1]);
-                                    acc[q4 * 4 + 2] = fmaf(xv.z, tv, acc[q4 * 4 + 2]);
-                                    acc[q4 * 4 + 3] = fmaf(xv.w, tv, acc[q4 * 4 + 3]);
+                                    const int     c  = c2 * 2 + h;
+                                    const float   u  = __uint_as_float(r[c]);
+                                    const float   k1 = h ? kf.y : kf.x, dk = h ? lf.y : lf.x;
+                                    const float   tv = (k1 + dk) * u;            // gradient sums
+                                    const float   tq = fmaf(qw * dk, u, k1 * u); // quadratic form
+                                    const float4* xr = reinterpret_cast<const float4*>(Xs + (chl * 32 + c) * XP);
+#pragma unroll
+                                    for (int q4 = 0; q4 < XP / 4; ++q4)
+                                    {
+                                        const float4 xv = xr[q4];
+                                        acc[q4 * 4 + 0] = fmaf(xv.x, q4 == 0 ? tq : tv, acc[q4 * 4 + 0]);
+                                        acc[q4 * 4 + 1] = fmaf(xv.y, tv, acc[q4 * 4 + 1]);
+                                        acc[q4 * 4 + 2] = fmaf(xv.z, tv, acc[q4 * 4 + 2]);
+                                        acc[q4 * 4 + 3] = fmaf(xv.w, tv, acc[q4 * 4 + 3]);
+                                    }
                                 }
                             }
                         }
                     }
                     tc::fence_before_sync();
-                    tc::mbar_arrive(tc::smem_u32(&tempty_bar[slot]));
+                    if (NCTA == 2)
+                        tc::mbar_arrive_cluster(slot ? tempty1 : tempty0);
+                    else
+                        tc::mbar_arrive(slot ? tempty1 : tempty0);
                 }
 
                 const bool   live = m < p.Mc;
@@ -437,7 +524,10 @@ namespace slsgp
                         }
                     }
                     tc::fence_before_sync();
-                    tc::mbar_arrive(tc::smem_u32(&tempty_bar[slot]));
+                    if (NCTA == 2)
+                        tc::mbar_arrive_cluster(slot ? tempty1 : tempty0);
+                    else
+                        tc::mbar_arrive(slot ? tempty1 : tempty0);
                     ++t;
                 }
             }
@@ -445,10 +535,14 @@ namespace slsgp
 
         tc::fence_before_sync();
         __syncthreads();
+        if (NCTA == 2) tc::cluster_sync_all(); // the leader's MMAs read the peer's shared memory until the very end
         if (warp == 2)
         {
             tc::fence_after_sync();
-            tc::tmem_dealloc(tmem_base, 512);
+            if (NCTA == 2)
+                tc::tmem_dealloc_pair(tmem_base, 512);
+            else
+                tc::tmem_dealloc(tmem_base, 512);
         }
     }
 } // namespace slsgp
