@@ -49,6 +49,9 @@ struct slsgp_ctx
 {
     int          device     = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    // shard pipeline (run_sweep): candidates in + k* on `pre`, contraction + finish on `stream`, results out on `post`
+    cudaStream_t pre_stream = nullptr, post_stream = nullptr;
+    cudaEvent_t  ev_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     std::string  err;
     unsigned     compat     = SLSGP_COMPAT_SE_XGRAD_2X;
     int          sweep_mode = SLSGP_SWEEP_FP64;
@@ -169,7 +172,8 @@ namespace
         slsgp_ctx*         ctx;
         slsgp_ctx::ProfRec rec;
         bool               on;
-        ProfScope(slsgp_ctx* c, const char* name) : ctx(c), on(c->profile)
+        cudaStream_t       st;
+        ProfScope(slsgp_ctx* c, const char* name, cudaStream_t stream = nullptr) : ctx(c), on(c->profile), st(stream ? stream : c->stream)
         {
             if (!on) return;
             if (!ctx->prof_free.empty())
@@ -182,12 +186,12 @@ namespace
                 on = false;
                 return;
             }
-            cudaEventRecord(rec.start, ctx->stream);
+            cudaEventRecord(rec.start, st);
             ctx->prof[name].push_back(rec);
         }
         ~ProfScope()
         {
-            if (on) cudaEventRecord(rec.stop, ctx->stream);
+            if (on) cudaEventRecord(rec.stop, st);
         }
     };
 
@@ -395,9 +399,10 @@ namespace
         cap           = round_up64(cap, tensor ? TC_BM * ctx->tc_ncta : TILE);
         if (tensor && ctx->tc_Mcap < cap)
         {
-            // rows [0, cap): k16, rows [cap, 2 cap): its fp16 rounding residual (read only by the split-precision passes)
-            TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 2 * (size_t) cap * ctx->ldt));
-            TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 2 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
+            // two shard buffers (the k* of shard s + 1 is generated while shard s is contracted), each: rows [0, cap)
+            // k16, rows [cap, 2 cap) its fp16 rounding residual (read only by the split-precision passes)
+            TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 4 * (size_t) cap * ctx->ldt));
+            TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 4 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
             ctx->tc_Mcap = cap;
         }
         if (ctx->Mcap >= cap) return SLSGP_OK;
@@ -411,13 +416,14 @@ namespace
         TRY(ensure(ctx, ctx->P1, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->P2, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->stats, sizeof(double4) * (size_t) cap));
-        TRY(ensure(ctx, ctx->Xq, sizeof(double) * (size_t) ctx->D * cap));
-        TRY(ensure(ctx, ctx->o_mu, sizeof(double) * cap));
-        TRY(ensure(ctx, ctx->o_sigma, sizeof(double) * cap));
-        TRY(ensure(ctx, ctx->o_val, sizeof(double) * cap));
-        TRY(ensure(ctx, ctx->o_dmu, sizeof(double) * (size_t) ctx->D * cap));
-        TRY(ensure(ctx, ctx->o_dsigma, sizeof(double) * (size_t) ctx->D * cap));
-        TRY(ensure(ctx, ctx->o_grad, sizeof(double) * (size_t) ctx->D * cap));
+        // candidate and result staging: two shard buffers each (run_sweep)
+        TRY(ensure(ctx, ctx->Xq, 2 * sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_mu, 2 * sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_sigma, 2 * sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_val, 2 * sizeof(double) * cap));
+        TRY(ensure(ctx, ctx->o_dmu, 2 * sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_dsigma, 2 * sizeof(double) * (size_t) ctx->D * cap));
+        TRY(ensure(ctx, ctx->o_grad, 2 * sizeof(double) * (size_t) ctx->D * cap));
         TRY(ensure(ctx, ctx->am_part, sizeof(ArgMax) * 1024));
         TRY(ensure(ctx, ctx->am_acc, sizeof(ArgMax)));
         ctx->Mcap = cap;
@@ -479,7 +485,7 @@ namespace
         const size_t brows = 2 * (size_t) ldt + TC_BN;
         TRY(ensure(ctx, ctx->Bmat, sizeof(__half) * brows * ldt));
         TRY(ensure(ctx, ctx->Xt, sizeof(float) * (size_t) ldt * XP));
-        TRY(ensure(ctx, ctx->Xs32, sizeof(float) * (size_t) ldt * ctx->D));
+        TRY(ensure(ctx, ctx->Xs32, sizeof(float) * (size_t) ldt * (ctx->D + 1)));
         TRY(ensure(ctx, ctx->tcs, sizeof(TcScales)));
         if (!ctx->tc_err.p)
         {
@@ -560,36 +566,46 @@ namespace
         return SLSGP_OK;
     }
 
-    slsgp_status sweep_shard_tensor(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
-                                    SweepOut out)
+    // k* operand of one shard into shard buffer `buf`, on `st` (the pipeline's `pre` stream).
+    slsgp_status tensor_kstar(slsgp_ctx* ctx, int buf, const double* d_Xq, long long Mc, cudaStream_t st)
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
-        __half*         Ks_lo = passes > 1 ? ptr<__half>(ctx->Ks) + (size_t) ctx->tc_Mcap * ldt : nullptr;
+        __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) buf * 2 * ctx->tc_Mcap * ldt;
+        __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
+        ProfScope       ps(ctx, "tc_kstar", st);
+        const size_t    smem = sizeof(float) * (size_t) (64 * (((D + 3) & ~3) + 4) + (D + 1) * 128);
+        static bool     kstar_attr = false;
+        if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
+        {
+            CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          (int) (sizeof(float) * (64 * 72 + 68 * 128))));
+            kstar_attr = true;
+        }
+        kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, st>>>(
+            d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    // contraction + fused epilogue + acquisition formulas of one shard whose k* operand sits in shard buffer `buf`
+    slsgp_status tensor_main(slsgp_ctx* ctx, int buf, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out)
+    {
+        const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
+        const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
+        const long long row0 = (long long) buf * 2 * ctx->tc_Mcap;
+        __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) row0 * ldt;
+        __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
         static int      n_sm = 0;
         if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
-        {
-            ProfScope    ps(ctx, "tc_kstar");
-            const size_t smem = sizeof(float) * (size_t) (64 * (D + 1) + D * 128);
-            static bool  kstar_attr = false;
-            if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
-            {
-                CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int) (sizeof(float) * (64 * 68 + 67 * 128))));
-                kstar_attr = true;
-            }
-            kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, ctx->stream>>>(
-                d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs),
-                ptr<__half>(ctx->Ks), Ks_lo);
-            LAUNCH_CHECK();
-        }
         {
             ProfScope    ps(ctx, "tc_gemm");
             TcGemmParams prm;
             prm.ldt = ldt, prm.kb = round_up(ctx->N, TC_BK) / TC_BK, prm.ncb = ldt / TC_BN, prm.D = D, prm.stages = 0;
-            prm.n_cand_blocks = (int) (Mpad / TC_BM), prm.Mc = Mc;
+            prm.stage_bytes = 0;
+            prm.n_cand_blocks = (int) (Mpad / TC_BM), prm.Mc = Mc, prm.a_row0 = (int) row0;
             prm.passes = passes, prm.a_lo_row = (int) ctx->tc_Mcap, prm.b_lo_row = ldt + TC_BN, prm.Ks_lo = Ks_lo;
-            prm.Ks = ptr<__half>(ctx->Ks), prm.Xt = ptr<float>(ctx->Xt), prm.sc = ptr<TcScales>(ctx->tcs);
+            prm.Ks = Ks, prm.Xt = ptr<float>(ctx->Xt), prm.sc = ptr<TcScales>(ctx->tcs);
             prm.se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
             prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2), prm.ldp = ctx->Dp;
             prm.err = ptr<int>(ctx->tc_err);
@@ -609,7 +625,6 @@ namespace
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
                              SweepOut out)
     {
-        if (is_tensor_mode(ctx->sweep_mode)) return sweep_shard_tensor(ctx, acq_type, ucb_beta, d_Xq, Mc, out);
         const int       ld = ctx->ld, D = ctx->D, Dp = ctx->Dp;
         const long long Mp = round_up64(Mc, TILE);
         const bool      want_grad = out.dmu || out.dsigma || out.grad;
@@ -652,6 +667,122 @@ namespace
                         "sweep needs a fitted model: slsgp_set_data, slsgp_gram, slsgp_factor, slsgp_solve_alpha");
         return SLSGP_OK;
     }
+
+    // ---------------------------------------------------------------------------------------------------------
+    // The shard pipeline shared by every K4 entry point. Shard s goes through
+    //   in   (pre stream)   candidates into shard buffer s % 2 (H2D copy / counter-based generator / caller's device
+    //                       pointer) and, in tensor mode, their k* operand
+    //   main (ctx->stream)  contraction, epilogue, acquisition formulas (+ running arg-max)
+    //   out  (post stream)  D2H of the results (host-buffer entry points only)
+    // so the copies and the k* generator of neighbouring shards hide behind the contraction. Everything is ordered
+    // behind ctx->stream: work enqueued there before the call is complete before `in` starts, and ctx->stream
+    // waits for the last `out` before the call returns.
+    // ---------------------------------------------------------------------------------------------------------
+    struct SweepJob
+    {
+        int           acq_type = 0;
+        double        ucb_beta = 0.0;
+        long long     M        = 0;
+        const double* d_Xq     = nullptr; // candidates already on the device (D x M), or
+        const double* h_Xq     = nullptr; // on the host, or
+        bool          generate = false;   // counter-based: candidate i = candidate_coord(seed, first + i, .)
+        uint64_t      seed     = 0;
+        long long     first    = 0;
+        bool          host_out = false;   // outputs below are host pointers (else device pointers); any may be null
+        double *      mu = nullptr, *sigma = nullptr, *dmu = nullptr, *dsigma = nullptr, *val = nullptr, *grad = nullptr;
+        bool          argmax = false;     // fold every shard's values into ctx->am_acc (index = first + i)
+    };
+
+    slsgp_status run_sweep(slsgp_ctx* ctx, const SweepJob& job)
+    {
+        const bool      tensor = is_tensor_mode(ctx->sweep_mode);
+        const int       D = ctx->D;
+        const long long cap = ctx->Mcap, n_shards = (job.M + cap - 1) / cap;
+        if (n_shards == 0) return SLSGP_OK;
+        static const bool overlap = !(std::getenv("SLSGP_PIPELINE") && std::atoi(std::getenv("SLSGP_PIPELINE")) == 0);
+        cudaStream_t main = ctx->stream, pre = overlap ? ctx->pre_stream : main, post = overlap ? ctx->post_stream : main;
+        CUDA_TRY(cudaEventRecord(ctx->ev_start, main));
+        CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_start, 0));
+        CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_start, 0));
+
+        auto xq_of = [&](long long s) -> const double* {
+            return job.d_Xq ? job.d_Xq + (size_t) (s * cap) * D : dp(ctx->Xq) + (size_t) (s & 1) * D * cap;
+        };
+        auto stage_in = [&](long long s) -> slsgp_status {
+            const int       b  = (int) (s & 1);
+            const long long m0 = s * cap, Mc = std::min<long long>(cap, job.M - m0);
+            if (s >= 2) CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_main[b], 0)); // shard s - 2 no longer reads buffer b
+            double* xq = dp(ctx->Xq) + (size_t) b * D * cap;
+            if (job.h_Xq)
+                CUDA_TRY(cudaMemcpyAsync(xq, job.h_Xq + (size_t) m0 * D, sizeof(double) * (size_t) Mc * D, cudaMemcpyHostToDevice, pre));
+            else if (job.generate)
+            {
+                candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, pre>>>(job.seed, job.first + m0, Mc, D, xq);
+                LAUNCH_CHECK();
+            }
+            if (tensor) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre));
+            CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
+            return SLSGP_OK;
+        };
+
+        TRY(stage_in(0));
+        for (long long s = 0; s < n_shards; ++s)
+        {
+            const int       b  = (int) (s & 1);
+            const long long m0 = s * cap, Mc = std::min<long long>(cap, job.M - m0);
+            if (s + 1 < n_shards) TRY(stage_in(s + 1));
+
+            // ---- main
+            CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_in[b], 0));
+            if (job.host_out && s >= 2) CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[b], 0)); // result buffer b drained
+            SweepOut o;
+            if (job.host_out)
+            {
+                const size_t ov = (size_t) b * cap, og = ov * D;
+                o.mu = job.mu ? dp(ctx->o_mu) + ov : nullptr, o.sigma = job.sigma ? dp(ctx->o_sigma) + ov : nullptr;
+                o.val = job.val ? dp(ctx->o_val) + ov : nullptr, o.dmu = job.dmu ? dp(ctx->o_dmu) + og : nullptr;
+                o.dsigma = job.dsigma ? dp(ctx->o_dsigma) + og : nullptr, o.grad = job.grad ? dp(ctx->o_grad) + og : nullptr;
+            }
+            else
+            {
+                o.mu = job.mu ? job.mu + m0 : nullptr, o.sigma = job.sigma ? job.sigma + m0 : nullptr;
+                o.val = job.val ? job.val + m0 : nullptr, o.dmu = job.dmu ? job.dmu + (size_t) m0 * D : nullptr;
+                o.dsigma = job.dsigma ? job.dsigma + (size_t) m0 * D : nullptr, o.grad = job.grad ? job.grad + (size_t) m0 * D : nullptr;
+            }
+            if (job.argmax && !o.val) o.val = dp(ctx->o_val) + (size_t) b * cap;
+            if (tensor)
+                TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
+            else
+                TRY(sweep_shard(ctx, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
+            if (job.argmax)
+            {
+                const int nblk = (int) std::min<long long>(1024, (Mc + 255) / 256);
+                argmax_partial_kernel<<<nblk, 256, 0, main>>>(o.val, Mc, job.first + m0, ptr<ArgMax>(ctx->am_part));
+                LAUNCH_CHECK();
+                argmax_final_kernel<<<1, 256, 0, main>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
+                LAUNCH_CHECK();
+            }
+            CUDA_TRY(cudaEventRecord(ctx->ev_main[b], main));
+
+            // ---- out
+            if (job.host_out)
+            {
+                CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_main[b], 0));
+                const size_t sv = sizeof(double) * (size_t) Mc, sg = sv * D;
+                if (job.mu) CUDA_TRY(cudaMemcpyAsync(job.mu + m0, o.mu, sv, cudaMemcpyDeviceToHost, post));
+                if (job.sigma) CUDA_TRY(cudaMemcpyAsync(job.sigma + m0, o.sigma, sv, cudaMemcpyDeviceToHost, post));
+                if (job.val) CUDA_TRY(cudaMemcpyAsync(job.val + m0, o.val, sv, cudaMemcpyDeviceToHost, post));
+                if (job.dmu) CUDA_TRY(cudaMemcpyAsync(job.dmu + (size_t) m0 * D, o.dmu, sg, cudaMemcpyDeviceToHost, post));
+                if (job.dsigma) CUDA_TRY(cudaMemcpyAsync(job.dsigma + (size_t) m0 * D, o.dsigma, sg, cudaMemcpyDeviceToHost, post));
+                if (job.grad) CUDA_TRY(cudaMemcpyAsync(job.grad + (size_t) m0 * D, o.grad, sg, cudaMemcpyDeviceToHost, post));
+                CUDA_TRY(cudaEventRecord(ctx->ev_out[b], post));
+            }
+        }
+        if (job.host_out)
+            for (long long s = std::max<long long>(0, n_shards - 2); s < n_shards; ++s)
+                CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[s & 1], 0));
+        return SLSGP_OK;
+    }
 } // namespace
 
 // =============================================================================================================
@@ -692,6 +823,18 @@ extern "C"
             return SLSGP_ERR_CUDA;
         }
         ctx->stream       = ctx->own_stream;
+        bool aux_ok = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) == cudaSuccess &&
+                      cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+        for (int b = 0; b < 2 && aux_ok; ++b)
+            aux_ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ctx->ev_main[b], cudaEventDisableTiming) == cudaSuccess &&
+                     cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
+        if (!aux_ok)
+        {
+            delete ctx;
+            return SLSGP_ERR_CUDA;
+        }
         if (const char* e = std::getenv("SLSGP_TC_PAIR")) ctx->tc_ncta = std::atoi(e) ? 2 : 1;
         ctx->pinned_bytes = 1 << 16;
         if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess)
@@ -727,6 +870,15 @@ extern "C"
             for (auto& r : kv.second) ctx->prof_free.push_back(r);
         for (auto& r : ctx->prof_free) cudaEventDestroy(r.start), cudaEventDestroy(r.stop);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        for (int b = 0; b < 2; ++b)
+        {
+            cudaEventDestroy(ctx->ev_in[b]);
+            cudaEventDestroy(ctx->ev_main[b]);
+            cudaEventDestroy(ctx->ev_out[b]);
+        }
+        cudaEventDestroy(ctx->ev_start);
+        cudaStreamDestroy(ctx->pre_stream);
+        cudaStreamDestroy(ctx->post_stream);
         cudaStreamDestroy(ctx->own_stream);
         delete ctx;
         return SLSGP_OK;
@@ -924,19 +1076,10 @@ extern "C"
         CUDA_TRY(cudaSetDevice(ctx->device));
         TRY(ensure_sweep_workspace(ctx, M));
         TRY(phase_begin(ctx, "sweep"));
-        const int D = ctx->D;
-        for (int64_t m0 = 0; m0 < M; m0 += ctx->Mcap)
-        {
-            const long long Mc = std::min<long long>(ctx->Mcap, M - m0);
-            SweepOut        o;
-            o.mu     = d_mu ? d_mu + m0 : nullptr;
-            o.sigma  = d_sigma ? d_sigma + m0 : nullptr;
-            o.val    = d_val ? d_val + m0 : nullptr;
-            o.dmu    = d_dmu ? d_dmu + (size_t) m0 * D : nullptr;
-            o.dsigma = d_dsigma ? d_dsigma + (size_t) m0 * D : nullptr;
-            o.grad   = d_grad ? d_grad + (size_t) m0 * D : nullptr;
-            TRY(sweep_shard(ctx, (int) acq_type, ucb_beta, d_Xq + (size_t) m0 * D, Mc, o));
-        }
+        SweepJob job;
+        job.acq_type = (int) acq_type, job.ucb_beta = ucb_beta, job.M = M, job.d_Xq = d_Xq;
+        job.mu = d_mu, job.sigma = d_sigma, job.dmu = d_dmu, job.dsigma = d_dsigma, job.val = d_val, job.grad = d_grad;
+        TRY(run_sweep(ctx, job));
         TRY(phase_end(ctx, "sweep"));
         return SLSGP_OK;
     }
@@ -954,26 +1097,10 @@ extern "C"
         CUDA_TRY(cudaSetDevice(ctx->device));
         TRY(ensure_sweep_workspace(ctx, M));
         TRY(phase_begin(ctx, "sweep"));
-        const int D = ctx->D;
-        for (int64_t m0 = 0; m0 < M; m0 += ctx->Mcap)
-        {
-            const long long Mc = std::min<long long>(ctx->Mcap, M - m0);
-            CUDA_TRY(cudaMemcpyAsync(ctx->Xq.p, Xq + (size_t) m0 * D, sizeof(double) * (size_t) Mc * D,
-                                     cudaMemcpyHostToDevice, ctx->stream));
-            SweepOut o;
-            o.mu = mu ? dp(ctx->o_mu) : nullptr, o.sigma = sigma ? dp(ctx->o_sigma) : nullptr;
-            o.val = val ? dp(ctx->o_val) : nullptr, o.dmu = dmu ? dp(ctx->o_dmu) : nullptr;
-            o.dsigma = dsigma ? dp(ctx->o_dsigma) : nullptr, o.grad = grad ? dp(ctx->o_grad) : nullptr;
-            TRY(sweep_shard(ctx, acq_type, ucb_beta, dp(ctx->Xq), Mc, o));
-            const size_t sv = sizeof(double) * (size_t) Mc, sg = sv * D;
-            if (mu) CUDA_TRY(cudaMemcpyAsync(mu + m0, o.mu, sv, cudaMemcpyDeviceToHost, ctx->stream));
-            if (sigma) CUDA_TRY(cudaMemcpyAsync(sigma + m0, o.sigma, sv, cudaMemcpyDeviceToHost, ctx->stream));
-            if (val) CUDA_TRY(cudaMemcpyAsync(val + m0, o.val, sv, cudaMemcpyDeviceToHost, ctx->stream));
-            if (dmu) CUDA_TRY(cudaMemcpyAsync(dmu + (size_t) m0 * D, o.dmu, sg, cudaMemcpyDeviceToHost, ctx->stream));
-            if (dsigma)
-                CUDA_TRY(cudaMemcpyAsync(dsigma + (size_t) m0 * D, o.dsigma, sg, cudaMemcpyDeviceToHost, ctx->stream));
-            if (grad) CUDA_TRY(cudaMemcpyAsync(grad + (size_t) m0 * D, o.grad, sg, cudaMemcpyDeviceToHost, ctx->stream));
-        }
+        SweepJob job;
+        job.acq_type = acq_type, job.ucb_beta = ucb_beta, job.M = M, job.h_Xq = Xq, job.host_out = true;
+        job.mu = mu, job.sigma = sigma, job.dmu = dmu, job.dsigma = dsigma, job.val = val, job.grad = grad;
+        TRY(run_sweep(ctx, job));
         TRY(phase_end(ctx, "sweep"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return SLSGP_OK;
@@ -1044,23 +1171,10 @@ extern "C"
         std::memcpy(ctx->pinned, &init, sizeof(init));
         CUDA_TRY(cudaMemcpyAsync(ctx->am_acc.p, ctx->pinned, sizeof(ArgMax), cudaMemcpyHostToDevice, ctx->stream));
         TRY(phase_begin(ctx, "sweep"));
-        for (int64_t m0 = 0; m0 < count; m0 += ctx->Mcap)
-        {
-            const long long Mc = std::min<long long>(ctx->Mcap, count - m0);
-            candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, ctx->stream>>>(seed, first + m0, Mc, D,
-                                                                                         dp(ctx->Xq));
-            LAUNCH_CHECK();
-            SweepOut o;
-            o.mu = o.sigma = o.dmu = o.dsigma = nullptr;
-            o.val  = dp(ctx->o_val);
-            o.grad = nullptr; // the winner's gradient is evaluated once at the end
-            TRY(sweep_shard(ctx, (int) acq_type, ucb_beta, dp(ctx->Xq), Mc, o));
-            const int nblk = (int) std::min<long long>(1024, (Mc + 255) / 256);
-            argmax_partial_kernel<<<nblk, 256, 0, ctx->stream>>>(dp(ctx->o_val), Mc, first + m0, ptr<ArgMax>(ctx->am_part));
-            LAUNCH_CHECK();
-            argmax_final_kernel<<<1, 256, 0, ctx->stream>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
-            LAUNCH_CHECK();
-        }
+        SweepJob job; // values only: the winner's gradient is evaluated once at the end
+        job.acq_type = (int) acq_type, job.ucb_beta = ucb_beta, job.M = count, job.generate = true, job.seed = seed;
+        job.first = first, job.argmax = true;
+        TRY(run_sweep(ctx, job));
         TRY(phase_end(ctx, "sweep"));
         ArgMax best;
         CUDA_TRY(cudaMemcpyAsync(&best, ctx->am_acc.p, sizeof(ArgMax), cudaMemcpyDeviceToHost, ctx->stream));

@@ -256,6 +256,15 @@ namespace slsgp
             asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
         }
 
+        // Packed FP32 FMA (Blackwell FFMA2): d = a * b + c on both halves of a register pair, one issue slot.
+        __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+        {
+            unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                               rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+            asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+            return *reinterpret_cast<float2*>(&rd);
+        }
+
         __device__ __forceinline__ float ex2_approx(float x)
         {
             float y;

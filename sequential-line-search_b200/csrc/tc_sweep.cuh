@@ -114,7 +114,8 @@ namespace slsgp
         Bmat[(size_t) i * ldt + j] = __float2half_rn(v);
     }
 
-    // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = (X_dj - 1/2) / l_d for kstar16.
+    // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = (X_dj - 1/2) / l_d for kstar16 and
+    // Xs32[D][j] = -1/2 log2(e) |Xs32[.][j]|^2 (the observation's share of the exponent).
     __global__ void __launch_bounds__(256)
         tc_pack_x_kernel(const double* __restrict__ X, int N, int D, int XP, int ldt, const double* __restrict__ inv_l,
                          float* __restrict__ Xt, float* __restrict__ Xs32)
@@ -127,71 +128,101 @@ namespace slsgp
             if (i < N) v = c == 0 ? 1.f : (c <= D ? (float) X[(size_t) (c - 1) + (size_t) i * D] : 0.f);
             Xt[(size_t) i * XP + c] = v;
         }
+        float nn = 0.f;
         for (int d = 0; d < D; ++d)
-            Xs32[(size_t) d * ldt + i] = i < N ? (float) ((X[(size_t) d + (size_t) i * D] - 0.5) * inv_l[d]) : 0.f;
+        {
+            const float v = i < N ? (float) ((X[(size_t) d + (size_t) i * D] - 0.5) * inv_l[d]) : 0.f;
+            Xs32[(size_t) d * ldt + i] = v;
+            nn                         = fmaf(v, v, nn);
+        }
+        Xs32[(size_t) D * ldt + i] = -0.72134752044448170368f * nn;
     }
 
-    // Ks[m][j] = fp16(sK * a * exp(-r2/2)), r2 by direct differences of the length-scaled coordinates in fp32.
+    // Ks[m][j] = fp16(sK * a * exp(-r2/2)) and its rounding residual. With q, x the centred, length-scaled coordinates in
+    // fp32, r2 = |q|^2 + |x|^2 - 2 q.x: the dot product runs on packed FFMA2 (two observations per issue slot); in fp32
+    // the cancellation costs ~1e-6 of k, far below the fp16 operand rounding the residual row exists to repair.
     // Tile: 64 candidates x 128 observations per CTA; thread = 4 candidates x 8 consecutive j (one 16-byte store per row).
-    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * (D + 1) + D * 128) floats.
+    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * (DQ + 1) + (D + 1) * 128) floats, DQ = round_up(D, 4).
     __global__ void __launch_bounds__(256)
         kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
                        const float* __restrict__ Xs32, const double* __restrict__ inv_l,
                        const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo)
     {
-        extern __shared__ float ksm[];
-        float*                  sq = ksm;                 // [64][D + 1]
-        float*                  sx = ksm + 64 * (D + 1);  // [D][128]
+        extern __shared__ __align__(16) float ksm[];
+        const int               DQ = (D + 3) & ~3, QS = DQ + 4; // row stride of sq: 16-byte aligned rows, column DQ = exponent share
+        float*                  sq = ksm;                       // [64][QS]
+        float*                  sx = ksm + 64 * QS;             // [D + 1][128], row D = -1/2 log2(e) |x|^2
         const int               tid = threadIdx.x, j_base = blockIdx.x * 128;
         const long long         m_base = (long long) blockIdx.y * 64;
-        for (int e = tid; e < 64 * D; e += 256)
+        const float             c1 = -0.72134752044448170368f; // -0.5 * log2(e)
+        for (int e = tid; e < 64 * DQ; e += 256)
         {
-            const int       p = e / D, d = e - p * D;
+            const int       p = e / DQ, d = e - p * DQ;
             const long long m = m_base + p;
-            sq[p * (D + 1) + d] = m < Mc ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
+            sq[p * QS + d]  = (m < Mc && d < D) ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
         }
-        for (int e = tid; e < D * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
+        for (int e = tid; e < (D + 1) * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
+        __syncthreads();
+        if (tid < 64)
+        {
+            float nn = 0.f;
+            for (int d = 0; d < D; ++d) nn = fmaf(sq[tid * QS + d], sq[tid * QS + d], nn);
+            sq[tid * QS + DQ] = fmaf(c1, nn, sc->c0); // candidate's share of the exponent, log2(a sK) folded in
+        }
         __syncthreads();
 
         const int tj = tid & 15, tm = tid >> 4;
-        float     r2[4][8];
+        float2    dot[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 8; ++jj) r2[i][jj] = 0.f;
-        for (int d = 0; d < D; ++d)
+            for (int jj = 0; jj < 4; ++jj) dot[i][jj] = make_float2(0.f, 0.f);
+        for (int d0 = 0; d0 < DQ; d0 += 4)
         {
-            const float4 xa = *reinterpret_cast<const float4*>(&sx[d * 128 + tj * 8]);
-            const float4 xb = *reinterpret_cast<const float4*>(&sx[d * 128 + tj * 8 + 4]);
-            const float  x[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+            float4 qv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
+            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(&sq[(tm * 4 + i) * QS + d0]);
+#pragma unroll
+            for (int dd = 0; dd < 4; ++dd)
             {
-                const float qv = sq[(tm * 4 + i) * (D + 1) + d];
-#pragma unroll
-                for (int jj = 0; jj < 8; ++jj)
+                if (d0 + dd < D)
                 {
-                    const float df = qv - x[jj];
-                    r2[i][jj]      = fmaf(df, df, r2[i][jj]);
+                    const float4 xa = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + tj * 8]);
+                    const float4 xb = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + tj * 8 + 4]);
+                    const float2 x2[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        const float  q  = dd == 0 ? qv[i].x : (dd == 1 ? qv[i].y : (dd == 2 ? qv[i].z : qv[i].w));
+                        const float2 q2 = make_float2(q, q);
+#pragma unroll
+                        for (int jj = 0; jj < 4; ++jj) dot[i][jj] = tc::ffma2(q2, x2[jj], dot[i][jj]);
+                    }
                 }
             }
         }
-        const float c1 = -0.72134752044448170368f; // -0.5 * log2(e)
-        const float c0 = sc->c0;
+        const float4 na = *reinterpret_cast<const float4*>(&sx[D * 128 + tj * 8]);
+        const float4 nb = *reinterpret_cast<const float4*>(&sx[D * 128 + tj * 8 + 4]);
+        const float  xn[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
+        const float  m2c1 = -2.f * c1;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            const long long m = m_base + tm * 4 + i;
+            const long long m  = m_base + tm * 4 + i;
+            const float     qa = sq[(tm * 4 + i) * QS + DQ];
             __half2         h[4], hl[4];
 #pragma unroll
-            for (int jj = 0; jj < 8; jj += 2)
+            for (int jj = 0; jj < 4; ++jj)
             {
-                const int   j  = j_base + tj * 8 + jj;
-                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(fmaf(r2[i][jj], c1, c0)) : 0.f;
-                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(fmaf(r2[i][jj + 1], c1, c0)) : 0.f;
-                h[jj >> 1]     = __floats2half2_rn(v0, v1);
-                const float2 b = __half22float2(h[jj >> 1]);
-                hl[jj >> 1]    = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)
+                const int   j  = j_base + tj * 8 + 2 * jj;
+                // exponent = c0 + c1 (|q|^2 + |x|^2 - 2 q.x), clamped at 0 distance against rounding
+                const float e0 = fminf(fmaf(dot[i][jj].x, m2c1, qa + xn[2 * jj]), sc->c0);
+                const float e1 = fminf(fmaf(dot[i][jj].y, m2c1, qa + xn[2 * jj + 1]), sc->c0);
+                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(e0) : 0.f;
+                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(e1) : 0.f;
+                h[jj]          = __floats2half2_rn(v0, v1);
+                const float2 b = __half22float2(h[jj]);
+                hl[jj]         = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)
             }
             const size_t off = (size_t) m * ldt + j_base + tj * 8;
             *reinterpret_cast<uint4*>(Ks + off) = *reinterpret_cast<const uint4*>(h);
@@ -210,7 +241,8 @@ namespace slsgp
         int              n_cand_blocks; // ceil(Mc / 128), rounded up to the CTAs per cluster
         long long        Mc;
         int              passes;    // 1: k16 x A16 | 2: + k16 x A_lo | 3: + k_lo x A16 (split-fp16, fp32-class result)
-        int              a_lo_row;  // row offset of the k residuals inside the Ks tensor map
+        int              a_row0;    // first row of this shard buffer inside the Ks tensor map
+        int              a_lo_row;  // row offset of the k residuals (relative to a_row0)
         int              b_lo_row;  // row offset of the Kinv residuals inside the Bmat tensor map
         const __half*    Ks_lo;     // k residuals (null when passes == 1)
         const __half*    Ks;
@@ -305,7 +337,7 @@ namespace slsgp
             uint32_t   it = 0;
             for (int g = cid; g < n_groups; g += ncl)
             {
-                const int cbk = g * NCTA + (int) rank;
+                const int cbk = g * NCTA + (int) rank, a_row = p.a_row0 + cbk * TC_BM;
                 for (int cb = 0; cb <= p.ncb; ++cb)
                 {
                     const bool     extras = cb == p.ncb;
@@ -323,8 +355,8 @@ namespace slsgp
                             {
                                 const uint32_t fb = tc::smem_u32(&full_bar[s]);
                                 tc::mbar_arrive_expect_tx(fb, tx);
-                                tc::tma_load_2d(sa, &tmA, fb, k * TC_BK, cbk * TC_BM);
-                                if (P == 3) tc::tma_load_2d(sa + off_a1, &tmA, fb, k * TC_BK, cbk * TC_BM + p.a_lo_row);
+                                tc::tma_load_2d(sa, &tmA, fb, k * TC_BK, a_row);
+                                if (P == 3) tc::tma_load_2d(sa + off_a1, &tmA, fb, k * TC_BK, a_row + p.a_lo_row);
                                 tc::tma_load_2d(sa + off_b0, &tmB, fb, k * TC_BK, b_row);
                                 if (two_b) tc::tma_load_2d(sa + off_b1, &tmB, fb, k * TC_BK, b_row + p.b_lo_row);
                             }
@@ -332,8 +364,8 @@ namespace slsgp
                             {
                                 const uint32_t fb = tc::map_to_cta(tc::smem_u32(&full_bar[s]), 0);
                                 if (rank == 0) tc::mbar_arrive_expect_tx(tc::smem_u32(&full_bar[s]), tx);
-                                tc::tma_load_2d_pair(sa, &tmA, fb, k * TC_BK, cbk * TC_BM);
-                                if (P == 3) tc::tma_load_2d_pair(sa + off_a1, &tmA, fb, k * TC_BK, cbk * TC_BM + p.a_lo_row);
+                                tc::tma_load_2d_pair(sa, &tmA, fb, k * TC_BK, a_row);
+                                if (P == 3) tc::tma_load_2d_pair(sa + off_a1, &tmA, fb, k * TC_BK, a_row + p.a_lo_row);
                                 tc::tma_load_2d_pair(sa + off_b0, &tmB, fb, k * TC_BK, b_row);
                                 if (two_b) tc::tma_load_2d_pair(sa + off_b1, &tmB, fb, k * TC_BK, b_row + p.b_lo_row);
                             }
@@ -414,16 +446,20 @@ namespace slsgp
                 const __half*   lrow = p.Ks_lo ? p.Ks_lo + (size_t) m * p.ldt : nullptr;
                 // passes == 2: u lacks A * dk, so q takes the first-order term 2 dk.u (q = k.A.k is symmetric in k)
                 const float     qw = p.passes == 2 ? 2.f : 1.f;
-                float           acc[XP];
+                float2          acc[XP / 2]; // packed pairs: the reduction against Xt runs on FFMA2
 #pragma unroll
-                for (int c = 0; c < XP; ++c) acc[c] = 0.f;
+                for (int c = 0; c < XP / 2; ++c) acc[c] = make_float2(0.f, 0.f);
+
+                const uint4* kbase = reinterpret_cast<const uint4*>(krow);
+                const uint4* lbase = reinterpret_cast<const uint4*>(lrow);
+                uint4        kn[4], ln[4]; // software-pipelined: the k (and residual) values of the NEXT 32-column chunk
+#pragma unroll
+                for (int v = 0; v < 4; ++v) kn[v] = __ldg(kbase + v), ln[v] = lrow ? __ldg(lbase + v) : make_uint4(0, 0, 0, 0);
 
                 for (int cb = 0; cb < p.ncb; ++cb, ++t)
                 {
                     const uint32_t slot = t & 1, use = t >> 1;
                     const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + slot * TC_BN;
-                    const uint4*   kptr  = reinterpret_cast<const uint4*>(krow + (size_t) cb * TC_BN);
-                    const uint4*   lptr  = lrow ? reinterpret_cast<const uint4*>(lrow + (size_t) cb * TC_BN) : nullptr;
 #pragma unroll 1
                     for (int xs = 0; xs < TC_BN / XS_COLS; ++xs)
                     {
@@ -446,11 +482,17 @@ namespace slsgp
                             const int ch = xs * (XS_COLS / 32) + chl;
                             uint32_t  r[32];
                             tc::tmem_ld_x32(taddr + ch * 32, r);
+                            // this chunk's k values were fetched one chunk ago; fetch the next chunk's now
                             uint4 kv[4], lv[4];
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) kv[v] = __ldg(kptr + ch * 4 + v);
+                            for (int v = 0; v < 4; ++v) kv[v] = kn[v], lv[v] = ln[v];
+                            {
+                                const int gn = min(cb * (TC_BN / 32) + ch + 1, p.ncb * (TC_BN / 32) - 1);
 #pragma unroll
-                            for (int v = 0; v < 4; ++v) lv[v] = lrow ? __ldg(lptr + ch * 4 + v) : make_uint4(0, 0, 0, 0);
+                                for (int v = 0; v < 4; ++v) kn[v] = __ldg(kbase + gn * 4 + v);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) ln[v] = lrow ? __ldg(lbase + gn * 4 + v) : make_uint4(0, 0, 0, 0);
+                            }
                             tc::tmem_ld_wait();
                             const __half2* kh = reinterpret_cast<const __half2*>(kv);
                             const __half2* lh = reinterpret_cast<const __half2*>(lv);
@@ -467,14 +509,13 @@ namespace slsgp
                                     const float   tv = (k1 + dk) * u;            // gradient sums
                                     const float   tq = fmaf(qw * dk, u, k1 * u); // quadratic form
                                     const float4* xr = reinterpret_cast<const float4*>(Xs + (chl * 32 + c) * XP);
+                                    const float2  t2 = make_float2(tv, tv), tq2 = make_float2(tq, tv);
 #pragma unroll
                                     for (int q4 = 0; q4 < XP / 4; ++q4)
                                     {
                                         const float4 xv = xr[q4];
-                                        acc[q4 * 4 + 0] = fmaf(xv.x, q4 == 0 ? tq : tv, acc[q4 * 4 + 0]);
-                                        acc[q4 * 4 + 1] = fmaf(xv.y, tv, acc[q4 * 4 + 1]);
-                                        acc[q4 * 4 + 2] = fmaf(xv.z, tv, acc[q4 * 4 + 2]);
-                                        acc[q4 * 4 + 3] = fmaf(xv.w, tv, acc[q4 * 4 + 3]);
+                                        acc[q4 * 2 + 0] = tc::ffma2(make_float2(xv.x, xv.y), q4 == 0 ? tq2 : t2, acc[q4 * 2 + 0]);
+                                        acc[q4 * 2 + 1] = tc::ffma2(make_float2(xv.z, xv.w), t2, acc[q4 * 2 + 1]);
                                     }
                                 }
                             }
@@ -489,12 +530,12 @@ namespace slsgp
 
                 const bool   live = m < p.Mc;
                 const double c    = p.se_factor;
-                const double q    = (double) acc[0] * (double) inv_u;
+                const double q    = (double) acc[0].x * (double) inv_u;
                 if (live)
                 {
 #pragma unroll
                     for (int d = 0; d < XP - 1; ++d)
-                        if (d < p.D) p.P2[(size_t) d + (size_t) m * p.ldp] = -c * (double) acc[1 + d] * (double) inv_u;
+                        if (d < p.D) p.P2[(size_t) d + (size_t) m * p.ldp] = -c * (double) (((1 + d) & 1) ? acc[(1 + d) >> 1].y : acc[(1 + d) >> 1].x) * (double) inv_u;
                 }
 
                 // extras block: column 2c = hi, 2c + 1 = lo of sum_j k_mj alpha_j (1, X_0j, ..)[c]
