@@ -138,6 +138,16 @@ extern "C"
     slsgp_status slsgp_acq_batch(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, const double* Xq,
                                  int64_t M, double* val_out, double* grad_out);
 
+    /* The acquisition formulas alone, for callers that combine the posterior mean of one model with the deviation of
+     * another: Schonlau's batch criterion, objective_for_multiple_points (src/acquisition-function.cpp:63-110), where mu
+     * comes from the original regressor and sigma from a regressor that already holds the pending points. All arrays are
+     * host memory, laid out as slsgp_posterior_batch writes them (dmu / dsigma / grad: D x M); f_best is
+     * mu(PredictMaximumPointFromData()) of the original model (slsgp_get_f_best). grad_out (and then dmu / dsigma) may be
+     * NULL. Evaluated on `ctx`'s device; the context needs no model. */
+    slsgp_status slsgp_acq_from_posterior(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, double f_best, int D,
+                                          int64_t M, const double* mu, const double* sigma, const double* dmu,
+                                          const double* dsigma, double* val_out, double* grad_out);
+
     /* Same sweep with every buffer already resident on the context's device (device pointers): no copies.
      * Any output may be NULL. Asynchronous on the context's stream. */
     slsgp_status slsgp_acq_batch_device(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta,

@@ -39,6 +39,7 @@ _API = [
     ("slsgp_get_f_best", C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int)]),
     ("slsgp_posterior_batch", C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
     ("slsgp_acq_batch", C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp, C.c_int64, c_dp, c_dp]),
+    ("slsgp_acq_from_posterior", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int64, c_dp, c_dp, c_dp, c_dp, c_dp, c_dp]),
     ("slsgp_acq_batch_device", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
     ("slsgp_acq_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, c_dp, c_dp,
                                    C.POINTER(C.c_int64), c_dp]),
@@ -187,6 +188,19 @@ class Context:
         val = np.empty(M)
         grad = np.empty((D, M), order="F") if grads else None
         self._check(self.lib.slsgp_acq_batch(self.h, acq_type, ucb_beta, _p(Xq), M, _p(val), _p(grad)))
+        return val, grad
+
+    def acq_from_posterior(self, acq_type, ucb_beta, f_best, mu, sigma, dmu=None, dsigma=None):
+        """Acquisition value (and gradient when dmu / dsigma are given) from an externally supplied posterior."""
+        mu, sigma = _f64(mu), _f64(sigma)
+        M = mu.shape[0]
+        grads = dmu is not None
+        D = _f64(dmu).shape[0] if grads else 1
+        val = np.empty(M)
+        grad = np.empty((D, M), order="F") if grads else None
+        self._check(self.lib.slsgp_acq_from_posterior(self.h, acq_type, ucb_beta, f_best, D, M, _p(mu), _p(sigma),
+                                                      _p(_f64(dmu)) if grads else None, _p(_f64(dsigma)) if grads else None,
+                                                      _p(val), _p(grad) if grads else None))
         return val, grad
 
     def acq_batch_device(self, acq_type, ucb_beta, d_Xq, M, d_mu=0, d_sigma=0, d_dmu=0, d_dsigma=0, d_val=0, d_grad=0):

@@ -49,5 +49,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+HOST_DIR = os.path.join(PKG_DIR, "host")
+HOST_LIB_PATH = os.path.join(LIB_DIR, "libsls_b200_host.so")
+
+
+def build_host(force: bool = False) -> str:
+    """Build libsls_b200_host.so: the C++ mirror of the reference's Regressor / acquisition_func interface above the
+    C ABI (g++, links libslsgp.so with an $ORIGIN rpath). Uses the system Eigen when EIGEN_INC names it, else the
+    repository's eigen-lite subset."""
+    build()
+    cmd = ["make", "-s", "-C", HOST_DIR] + (["-B"] if force else [])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("host layer build failed:\n" + res.stdout + res.stderr)
+    return HOST_LIB_PATH
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build_host(force=True))

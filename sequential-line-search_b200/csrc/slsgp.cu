@@ -72,7 +72,7 @@ struct slsgp_ctx
     long long Mcap = 0;
 
     // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
-    DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err;
+    DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err, comb;
     CUtensorMap tmA, tmB;
     int         ldt = 0, XP = 0;
     bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
@@ -858,7 +858,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err};
+                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)
@@ -970,6 +970,7 @@ extern "C"
         for (size_t i = 0; i < (size_t) N * D; ++i)
             if (!std::isfinite(X[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_set_data: non-finite coordinate in X");
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (N != ctx->N) ctx->P = 0, ctx->pref_total = 0; // tuples index the columns of X: a new N voids them
         ctx->N = N, ctx->D = D, ctx->ld = round_up(N, TILE), ctx->Dp = round_up(D, TILE), ctx->ldx = round_up(D + 1, TILE);
         ctx->has_data = ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
         ctx->Mcap = 0; // sweep workspace depends on ld
@@ -1117,6 +1118,39 @@ extern "C"
                                  int64_t M, double* val_out, double* grad_out)
     {
         return host_sweep(ctx, (int) acq_type, ucb_beta, Xq, M, nullptr, nullptr, nullptr, nullptr, val_out, grad_out);
+    }
+
+    slsgp_status slsgp_acq_from_posterior(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, double f_best, int D,
+                                          int64_t M, const double* mu, const double* sigma, const double* dmu,
+                                          const double* dsigma, double* val_out, double* grad_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (M < 0 || D <= 0 || (M > 0 && (!mu || !sigma)) || (grad_out && (!dmu || !dsigma)))
+            return fail(ctx, SLSGP_ERR_INVALID, "slsgp_acq_from_posterior: bad arguments");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB)
+            return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        if (M == 0) return SLSGP_OK;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        // scratch: [mu | sigma | val] (M each) and, with gradients, [dmu | dsigma | grad] (D x M each)
+        const size_t sv = sizeof(double) * (size_t) M, sg = sv * D;
+        TRY(ensure(ctx, ctx->comb, 3 * sv + (grad_out ? 3 * sg : 0)));
+        double *d_mu = dp(ctx->comb), *d_sigma = d_mu + M, *d_val = d_sigma + M;
+        double *d_dmu = d_val + M, *d_dsigma = d_dmu + (size_t) M * D, *d_grad = d_dsigma + (size_t) M * D;
+        CUDA_TRY(cudaMemcpyAsync(d_mu, mu, sv, cudaMemcpyHostToDevice, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(d_sigma, sigma, sv, cudaMemcpyHostToDevice, ctx->stream));
+        if (grad_out)
+        {
+            CUDA_TRY(cudaMemcpyAsync(d_dmu, dmu, sg, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(d_dsigma, dsigma, sg, cudaMemcpyHostToDevice, ctx->stream));
+        }
+        acq_combine_kernel<<<(unsigned) ((M + 255) / 256), 256, 0, ctx->stream>>>(
+            d_mu, d_sigma, d_dmu, d_dsigma, D, M, f_best, (int) acq_type, ucb_beta, val_out ? d_val : nullptr,
+            grad_out ? d_grad : nullptr);
+        LAUNCH_CHECK();
+        if (val_out) CUDA_TRY(cudaMemcpyAsync(val_out, d_val, sv, cudaMemcpyDeviceToHost, ctx->stream));
+        if (grad_out) CUDA_TRY(cudaMemcpyAsync(grad_out, d_grad, sg, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
     }
 
     slsgp_status slsgp_argmax_device(slsgp_ctx* ctx, const double* d_val, int64_t count, int64_t index0,

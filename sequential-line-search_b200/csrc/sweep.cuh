@@ -155,6 +155,45 @@ namespace slsgp
             for (int d = 0; d < D; ++d) o.grad[(size_t) d + (size_t) m * D] = 0.0;
     }
 
+    // The acquisition formulas alone, for a posterior whose mean and deviation come from two different models
+    // (Schonlau's batch criterion: objective_for_multiple_points, src/acquisition-function.cpp:63-110, takes mu from
+    // the original regressor and sigma from one that already contains the pending points). Same arithmetic as the
+    // tail of sweep_finish_kernel. One thread per candidate; dmu / dsigma / grad are D x M.
+    __global__ void __launch_bounds__(256)
+        acq_combine_kernel(const double* __restrict__ mu_in, const double* __restrict__ sigma_in,
+                           const double* __restrict__ dmu_in, const double* __restrict__ dsigma_in, int D, long long M,
+                           double f_best, int acq_type, double ucb_beta, double* __restrict__ val, double* __restrict__ grad)
+    {
+        const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
+        if (m >= M) return;
+        const double mu = mu_in[m], sigma = sigma_in[m];
+        const double diff = mu - f_best, Z = diff / sigma;
+        const double Phi = std_normal_cdf(Z), phi = std_normal_pdf(Z), dphi = -Z * phi;
+        if (val)
+        {
+            const double EI = diff * Phi + sigma * phi;
+            val[m]          = acq_type == 1 ? mu + ucb_beta * sigma : ((sigma < 1e-16 || isnan(EI)) ? 0.0 : EI);
+        }
+        if (!grad) return;
+        bool has_nan = false;
+        for (int d = 0; d < D; ++d)
+        {
+            const double dmu = dmu_in[(size_t) d + (size_t) m * D], dsg = dsigma_in[(size_t) d + (size_t) m * D];
+            double       gr;
+            if (acq_type == 1)
+                gr = dmu + ucb_beta * dsg;
+            else
+            {
+                const double dZ = (dmu - Z * dsg) / sigma;
+                gr              = dmu * Phi + diff * dZ * phi + dsg * phi + sigma * dZ * dphi;
+                has_nan |= isnan(gr);
+            }
+            grad[(size_t) d + (size_t) m * D] = gr;
+        }
+        if (acq_type == 0 && (sigma < 1e-16 || has_nan))
+            for (int d = 0; d < D; ++d) grad[(size_t) d + (size_t) m * D] = 0.0;
+    }
+
     // Counter-based candidates: Xq[d + i*D] = candidate_coord(seed, first + i, d)
     __global__ void candidates_kernel(uint64_t seed, long long first, long long count, int D, double* __restrict__ Xq)
     {

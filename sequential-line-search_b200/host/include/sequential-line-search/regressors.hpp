@@ -1,0 +1,218 @@
+// Host-side C++ mirror of the reference's regressor interface for the GP hot path, served by libslsgp (sm_100a).
+//
+// Same namespace, class names, constructor arguments, public members and method semantics as
+//   include/sequential-line-search/kernel-type.hpp:8-22, preference.hpp:9-19, regressor.hpp:10-72,
+//   gaussian-process-regressor.hpp:9-52, preference-regressor.hpp:13-88
+// of yuki-koyama/sequential-line-search, so code written against those headers compiles against this one. What is
+// different is where the numbers come from: every regressor owns a libslsgp context (include/slsgp.h) holding X, the
+// Gram matrix, its Cholesky factor, K^-1 and alpha on the GPU; Predict* are one-candidate calls of the batched sweep,
+// and PredictBatch / acquisition_func::CalcAcquisitionValues expose the batched form directly. There is no CPU
+// fallback: constructing a regressor without a usable CUDA device throws std::runtime_error.
+//
+// Deviations from the reference surface:
+//   * PreferenceRegressor::m_K_llt (an Eigen::LLT computed on the host) is replaced by m_L, the lower Cholesky factor
+//     read back from the device; define SLS_B200_HOST_LLT to also get the Eigen::LLT member (host O(N^3)).
+//   * CalcSmallK / CalcSmallKSmallXDerivative / CalcLargeKYThetaDerivative are never materialised by the device path
+//     (they are fused into the sweep and MAP kernels) and are not offered as free functions.
+#ifndef SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP
+#define SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP
+
+#include <Eigen/Core>
+#ifdef SLS_B200_HOST_LLT
+#include <Eigen/Cholesky>
+#endif
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+struct slsgp_ctx;
+
+namespace sequential_line_search
+{
+    enum class KernelType
+    {
+        ArdSquaredExponentialKernel,
+        ArdMatern52Kernel,
+    };
+
+    // k(x_a, x_b; theta), d k / d theta and d k / d x_a as plain function pointers, as the reference hands them out
+    using Kernel                   = double (*)(const Eigen::VectorXd&, const Eigen::VectorXd&, const Eigen::VectorXd&);
+    using KernelThetaDerivative    = Eigen::VectorXd (*)(const Eigen::VectorXd&, const Eigen::VectorXd&, const Eigen::VectorXd&);
+    using KernelFirstArgDerivative = Eigen::VectorXd (*)(const Eigen::VectorXd&, const Eigen::VectorXd&, const Eigen::VectorXd&);
+
+    // One preference tuple: indices into the columns of X, the first one is the chosen (preferred) point.
+    struct Preference : public std::vector<unsigned>
+    {
+        Preference(unsigned i, unsigned j) : std::vector<unsigned>{i, j} {}
+        Preference(unsigned i, unsigned j, unsigned k) : std::vector<unsigned>{i, j, k} {}
+        Preference(const std::vector<unsigned>& indices) : std::vector<unsigned>(indices) {}
+    };
+
+    class Regressor
+    {
+    public:
+        explicit Regressor(const KernelType kernel_type);
+        virtual ~Regressor() {}
+
+        unsigned GetNumDims() const { return GetLargeX().rows(); }
+
+        virtual double          PredictMu(const Eigen::VectorXd& x) const              = 0;
+        virtual double          PredictSigma(const Eigen::VectorXd& x) const           = 0;
+        virtual Eigen::VectorXd PredictMuDerivative(const Eigen::VectorXd& x) const    = 0;
+        virtual Eigen::VectorXd PredictSigmaDerivative(const Eigen::VectorXd& x) const = 0;
+
+        virtual const Eigen::VectorXd& GetKernelHyperparams() const = 0;
+        virtual double                 GetNoiseHyperparam() const   = 0;
+        virtual const Eigen::MatrixXd& GetLargeX() const            = 0;
+        virtual const Eigen::VectorXd& GetSmallY() const            = 0;
+
+        // The data point with the largest posterior mean (one GEMV on the device for the regressors below; N calls of
+        // PredictMu for a foreign subclass, as in the reference).
+        Eigen::VectorXd PredictMaximumPointFromData() const;
+
+        Kernel                   GetKernel() const { return m_kernel; }
+        KernelThetaDerivative    GetKernelThetaDerivative() const { return m_kernel_theta_derivative; }
+        KernelFirstArgDerivative GetKernelFirstArgDerivative() const { return m_kernel_first_arg_derivative; }
+        KernelType               GetKernelType() const { return m_kernel_type; } // addition: the reference drops the enum
+
+    protected:
+        Kernel                   m_kernel;
+        KernelThetaDerivative    m_kernel_theta_derivative;
+        KernelFirstArgDerivative m_kernel_first_arg_derivative;
+        KernelType               m_kernel_type;
+    };
+
+    // Common part of the two device-backed regressors: the libslsgp context and the batched entry points.
+    class DeviceRegressor : public Regressor
+    {
+    public:
+        explicit DeviceRegressor(const KernelType kernel_type);
+
+        double          PredictMu(const Eigen::VectorXd& x) const override;
+        double          PredictSigma(const Eigen::VectorXd& x) const override;
+        Eigen::VectorXd PredictMuDerivative(const Eigen::VectorXd& x) const override;
+        Eigen::VectorXd PredictSigmaDerivative(const Eigen::VectorXd& x) const override;
+
+        // Posterior of every column of Xq (D x M) in one sweep; any output pointer may be null.
+        void PredictBatch(const Eigen::MatrixXd& Xq,
+                          Eigen::VectorXd*       mu,
+                          Eigen::VectorXd*       sigma,
+                          Eigen::MatrixXd*       mu_derivative    = nullptr,
+                          Eigen::MatrixXd*       sigma_derivative = nullptr) const;
+
+        bool       HasModel() const { return m_fitted; }
+        slsgp_ctx* Device() const { return m_device.get(); }
+        std::mutex& DeviceMutex() const { return *m_mutex; } // calls on one context are serialised
+
+    protected:
+        // set_data + gram + factor + inverse + alpha for (X, y, theta, noise); fills K / Kinv / L when asked
+        void FitOnDevice(const Eigen::MatrixXd& X,
+                         const Eigen::VectorXd& y,
+                         const Eigen::VectorXd& kernel_hyperparams,
+                         double                 noise,
+                         Eigen::MatrixXd*       K_out,
+                         Eigen::MatrixXd*       Kinv_out,
+                         Eigen::MatrixXd*       L_out);
+        void EnsureDevice();
+
+        std::shared_ptr<slsgp_ctx>  m_device;
+        std::shared_ptr<std::mutex> m_mutex;
+        bool                        m_fitted = false, m_data_on_device = false;
+    };
+
+    class GaussianProcessRegressor : public DeviceRegressor
+    {
+    public:
+        // hyper-parameters by MAP estimation (log marginal likelihood + log-normal priors)
+        GaussianProcessRegressor(const Eigen::MatrixXd& X,
+                                 const Eigen::VectorXd& y,
+                                 const KernelType       kernel_type = KernelType::ArdMatern52Kernel);
+        // hyper-parameters given
+        GaussianProcessRegressor(const Eigen::MatrixXd& X,
+                                 const Eigen::VectorXd& y,
+                                 const Eigen::VectorXd& kernel_hyperparams,
+                                 double                 noise_hyperparam,
+                                 const KernelType       kernel_type = KernelType::ArdMatern52Kernel);
+
+        Eigen::MatrixXd m_K_y;
+        Eigen::MatrixXd m_K_y_inv;
+
+        const Eigen::MatrixXd& GetLargeX() const override { return m_X; }
+        const Eigen::VectorXd& GetSmallY() const override { return m_y; }
+        const Eigen::VectorXd& GetKernelHyperparams() const override { return m_kernel_hyperparams; }
+        double                 GetNoiseHyperparam() const override { return m_noise_hyperparam; }
+
+    private:
+        void PerformMapEstimation();
+
+        Eigen::MatrixXd m_X;
+        Eigen::VectorXd m_y;
+        Eigen::VectorXd m_kernel_hyperparams;
+        double          m_noise_hyperparam = 0.0;
+    };
+
+    class PreferenceRegressor : public DeviceRegressor
+    {
+    public:
+        PreferenceRegressor(const Eigen::MatrixXd&         X,
+                            const std::vector<Preference>& D,
+                            const bool                     use_map_hyperparams          = false,
+                            const double                   default_kernel_signal_var    = 0.500,
+                            const double                   default_kernel_length_scale  = 0.500,
+                            const double                   default_noise_level          = 0.005,
+                            const double                   kernel_hyperparams_prior_var = 0.250,
+                            const double                   btl_scale                    = 0.010,
+                            const unsigned                 num_map_estimation_iters     = 100,
+                            const KernelType               kernel_type = KernelType::ArdMatern52Kernel);
+
+        const bool m_use_map_hyperparams;
+
+        Eigen::VectorXd FindArgMax() const; // the data point with the largest goodness value y_i
+
+        Eigen::MatrixXd         m_X;
+        std::vector<Preference> m_D;
+        double                  m_noise_hyperparam = 0.0;
+        Eigen::VectorXd         m_kernel_hyperparams;
+        Eigen::MatrixXd         m_K;
+        Eigen::MatrixXd         m_L; // lower Cholesky factor of m_K (from the device)
+#ifdef SLS_B200_HOST_LLT
+        Eigen::LLT<Eigen::MatrixXd> m_K_llt;
+#endif
+
+        void DampData(const std::string& dir_path, const std::string& prefix = "") const; // X.csv and D.csv
+
+        const Eigen::MatrixXd& GetLargeX() const override { return m_X; }
+        const Eigen::VectorXd& GetSmallY() const override { return m_y; }
+        const Eigen::VectorXd& GetKernelHyperparams() const override { return m_kernel_hyperparams; }
+        double                 GetNoiseHyperparam() const override { return m_noise_hyperparam; }
+
+        const double m_default_kernel_signal_var;
+        const double m_default_kernel_length_scale;
+        const double m_default_noise_level;
+        const double m_kernel_hyperparams_prior_var;
+        const double m_btl_scale;
+
+        // MAP objective F(y[, a, b, r]) and its gradient at an arbitrary point (what NLopt's callback evaluates in the
+        // reference, src/preference-regressor.cpp:129-259); exposed for hosts that drive their own optimiser.
+        double EvaluateMapObjective(const Eigen::VectorXd& x, Eigen::VectorXd* gradient) const;
+        // Diagnostics of the last MAP run
+        unsigned GetNumMapEvaluations() const { return m_num_map_evaluations; }
+
+    private:
+        Eigen::VectorXd m_y;
+        unsigned        m_num_map_evaluations = 0;
+
+        void PerformMapEstimation(const unsigned num_iters);
+    };
+
+    // K_y = K_f + noise I and K_f for one of the two library kernels, built by the device Gram kernel
+    // (regressor.hpp:51-59 of the reference). `kernel` must be a pointer obtained from Regressor::GetKernel().
+    Eigen::MatrixXd CalcLargeKY(const Eigen::MatrixXd& X,
+                                const Eigen::VectorXd& kernel_hyperparameters,
+                                const double           noise_level,
+                                const Kernel           kernel);
+    Eigen::MatrixXd CalcLargeKF(const Eigen::MatrixXd& X, const Eigen::VectorXd& kernel_hyperparameters, const Kernel kernel);
+} // namespace sequential_line_search
+
+#endif // SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP

@@ -1,0 +1,247 @@
+// acquisition_func::* (src/acquisition-function.cpp:170-298 of the reference) on libslsgp.
+//   CalcAcquisitionValue{,Derivative}   one-candidate calls of the device sweep (slsgp_acq_batch)
+//   CalcAcquisitionValues               the batched form the GPU path exists for
+//   FindNextPoint                       FindGlobalSolution (:112-167): dense candidate sweep on the device instead of
+//                                       NLopt DIRECT, then a bound-constrained quasi-Newton polish instead of LD_LBFGS
+//   FindNextPoints                      Schonlau's batch criterion (:246-298): mu from the regressor, sigma from a
+//                                       temporary GaussianProcessRegressor that also holds the points chosen so far
+#include "device.hpp"
+#include "optimizer.hpp"
+
+#include <cmath>
+#include <limits>
+
+using Eigen::MatrixXd;
+using Eigen::VectorXd;
+
+namespace sequential_line_search
+{
+    using internal::check;
+
+    namespace
+    {
+        // Scalar Expected Improvement / GP-UCB for a regressor that is NOT device-backed (a foreign subclass of
+        // Regressor): mathtoolbox acquisition-functions.cpp:8-78 through the Predict* virtuals.
+        double pdf(double z) { return (1.0 / std::sqrt(2.0 * 3.14159265358979323846)) * std::exp(-0.5 * z * z); }
+        double cdf(double z) { return 0.5 * (1.0 + std::erf(z / std::sqrt(2.0))); }
+
+        double generic_value(const Regressor& r, const VectorXd& x, AcquisitionFuncType type, double beta)
+        {
+            const double mu = r.PredictMu(x), sigma = r.PredictSigma(x);
+            if (type == AcquisitionFuncType::GaussianProcessUpperConfidenceBound) return mu + beta * sigma;
+            const double diff = mu - r.PredictMu(r.PredictMaximumPointFromData()), z = diff / sigma;
+            const double ei   = diff * cdf(z) + sigma * pdf(z);
+            return (sigma < 1e-16 || std::isnan(ei)) ? 0.0 : ei;
+        }
+        VectorXd generic_derivative(const Regressor& r, const VectorXd& x, AcquisitionFuncType type, double beta)
+        {
+            const double   mu = r.PredictMu(x), sigma = r.PredictSigma(x);
+            const VectorXd dmu = r.PredictMuDerivative(x), dsg = r.PredictSigmaDerivative(x);
+            VectorXd       g = VectorXd::Zero(x.size());
+            if (type == AcquisitionFuncType::GaussianProcessUpperConfidenceBound)
+            {
+                for (int i = 0; i < (int) x.size(); ++i) g(i) = dmu(i) + beta * dsg(i);
+                return g;
+            }
+            const double diff = mu - r.PredictMu(r.PredictMaximumPointFromData()), z = diff / sigma;
+            bool         bad  = sigma < 1e-16;
+            for (int i = 0; i < (int) x.size(); ++i)
+            {
+                const double dz = (dmu(i) - z * dsg(i)) / sigma;
+                g(i)            = dmu(i) * cdf(z) + diff * dz * pdf(z) + dsg(i) * pdf(z) + sigma * dz * (-z * pdf(z));
+                bad |= std::isnan(g(i));
+            }
+            return bad ? VectorXd::Zero(x.size()) : g;
+        }
+
+        const DeviceRegressor* device_of(const Regressor& r)
+        {
+            const auto* d = dynamic_cast<const DeviceRegressor*>(&r);
+            return (d && d->HasModel()) ? d : nullptr;
+        }
+
+        void device_acq(const DeviceRegressor& r, const double* Xq, long M, AcquisitionFuncType type, double beta, double* val, double* grad)
+        {
+            std::lock_guard<std::mutex> lock(r.DeviceMutex());
+            check(r.Device(), slsgp_acq_batch(r.Device(), internal::to_abi(type), beta, Xq, M, val, grad), "slsgp_acq_batch");
+        }
+
+        // maximise `value_and_gradient` over [0, 1]^D from x0 within `max_evals` evaluations
+        VectorXd polish(const std::function<double(const VectorXd&, VectorXd&)>& value_and_gradient, const VectorXd& x0, unsigned max_evals)
+        {
+            const size_t              n = (size_t) x0.size();
+            const std::vector<double> lo(n, 0.0), hi(n, 1.0);
+            std::vector<double>       start(x0.data(), x0.data() + n);
+            const internal::Objective neg = [&](const std::vector<double>& x, std::vector<double>& g) {
+                VectorXd xe = VectorXd::Zero((long) n), ge = VectorXd::Zero((long) n);
+                for (size_t i = 0; i < n; ++i) xe((long) i) = x[i];
+                const double v = value_and_gradient(xe, ge);
+                if (!std::isfinite(v)) return std::numeric_limits<double>::infinity();
+                for (size_t i = 0; i < n; ++i) g[i] = std::isfinite(ge((long) i)) ? -ge((long) i) : 0.0;
+                return -v;
+            };
+            const internal::MinimizeResult r = internal::minimize_bounded(neg, start, lo, hi, std::max(2u, max_evals), 1e-10, 1e-14);
+            VectorXd                       out = VectorXd::Zero((long) n);
+            for (size_t i = 0; i < n; ++i) out((long) i) = r.x[i];
+            return out;
+        }
+
+        uint64_t search_seed(const Regressor& r) { return 0x9E3779B97F4A7C15ull ^ ((uint64_t) r.GetLargeX().cols() << 20) ^ (uint64_t) r.GetNumDims(); }
+    } // namespace
+
+    namespace acquisition_func
+    {
+        double CalcAcquisitionValue(const Regressor& regressor, const VectorXd& x, const AcquisitionFuncType func_type, const double hyperparam)
+        {
+            if (regressor.GetSmallY().rows() == 0) return 0.0; // :176-179
+            if (const DeviceRegressor* d = device_of(regressor))
+            {
+                double v = 0.0;
+                device_acq(*d, x.data(), 1, func_type, hyperparam, &v, nullptr);
+                return v;
+            }
+            return generic_value(regressor, x, func_type, hyperparam);
+        }
+
+        VectorXd CalcAcquisitionValueDerivative(const Regressor& regressor, const VectorXd& x, const AcquisitionFuncType func_type,
+                                                const double hyperparam)
+        {
+            if (regressor.GetSmallY().rows() == 0) return VectorXd::Zero(x.size()); // :206-209
+            if (const DeviceRegressor* d = device_of(regressor))
+            {
+                VectorXd g = VectorXd::Zero(x.size());
+                device_acq(*d, x.data(), 1, func_type, hyperparam, nullptr, g.data());
+                return g;
+            }
+            return generic_derivative(regressor, x, func_type, hyperparam);
+        }
+
+        VectorXd CalcAcquisitionValues(const DeviceRegressor& regressor, const MatrixXd& Xq, const AcquisitionFuncType func_type,
+                                       const double hyperparam, MatrixXd* derivatives)
+        {
+            const long M = Xq.cols();
+            VectorXd   val = VectorXd::Zero(M);
+            if (derivatives) *derivatives = MatrixXd::Zero(Xq.rows(), M);
+            if (regressor.GetSmallY().rows() == 0 || M == 0) return val;
+            if (!regressor.HasModel()) throw std::logic_error("the regressor holds no model");
+            device_acq(regressor, Xq.data(), M, func_type, hyperparam, val.data(), derivatives ? derivatives->data() : nullptr);
+            return val;
+        }
+
+        VectorXd FindNextPoint(const Regressor& regressor, const unsigned num_global_search_iters, const unsigned num_local_search_iters,
+                               const AcquisitionFuncType func_type, const double hyperparam)
+        {
+            const unsigned D = regressor.GetNumDims();
+            if (regressor.GetSmallY().rows() == 0 || D == 0) return VectorXd::Constant(D, 0.5); // flat objective: the box centre
+            const long     count = (long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter;
+            VectorXd       x0    = VectorXd::Zero(D);
+            if (const DeviceRegressor* d = device_of(regressor))
+            {
+                std::lock_guard<std::mutex> lock(d->DeviceMutex());
+                slsgp_ctx*                  c = d->Device();
+                // the tensor-core sweep pays off for large candidate counts (ARD-SE kernel only); the polish is FP64
+                const bool tensor = regressor.GetKernelType() == KernelType::ArdSquaredExponentialKernel && count >= 32768 && D <= 67;
+                check(c, slsgp_set_sweep_mode(c, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), "slsgp_set_sweep_mode");
+                double       v0 = 0.0;
+                int64_t      i0 = 0;
+                slsgp_status s  = slsgp_acq_argmax(c, internal::to_abi(func_type), hyperparam, search_seed(regressor), 0, count, x0.data(), &v0, &i0, nullptr);
+                slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
+                check(c, s, "slsgp_acq_argmax");
+            }
+            else
+            {
+                // foreign regressor: the same candidate sequence, evaluated through the virtual interface
+                double best = -std::numeric_limits<double>::infinity();
+                for (long i = 0; i < std::min<long>(count, 4096); ++i)
+                {
+                    VectorXd x = VectorXd::Zero(D);
+                    for (unsigned k = 0; k < D; ++k) x(k) = std::fmod(0.5 + (i + 1) * 0.6180339887498949 * (k + 1), 1.0);
+                    const double v = generic_value(regressor, x, func_type, hyperparam);
+                    if (v > best) best = v, x0 = x;
+                }
+            }
+            return polish(
+                [&](const VectorXd& x, VectorXd& g) {
+                    g = CalcAcquisitionValueDerivative(regressor, x, func_type, hyperparam);
+                    return CalcAcquisitionValue(regressor, x, func_type, hyperparam);
+                },
+                x0, num_local_search_iters);
+        }
+
+        std::vector<VectorXd> FindNextPoints(const Regressor& regressor, const unsigned num_points, const unsigned num_global_search_iters,
+                                             const unsigned num_local_search_iters, const AcquisitionFuncType func_type, const double hyperparam)
+        {
+            const unsigned        D = regressor.GetNumDims();
+            std::vector<VectorXd> points;
+            if (num_points == 0) return points;
+            const DeviceRegressor* orig = device_of(regressor);
+            if (!orig) throw std::invalid_argument("FindNextPoints needs a device-backed regressor with data");
+
+            const VectorXd theta = regressor.GetKernelHyperparams();
+            const double   noise = regressor.GetNoiseHyperparam();
+            // As in the reference (:259-260) the temporary regressor is built with GaussianProcessRegressor's DEFAULT
+            // kernel type (Matern 5/2) whatever kernel `regressor` uses; kept for parity.
+            std::unique_ptr<GaussianProcessRegressor> temp(new GaussianProcessRegressor(regressor.GetLargeX(), regressor.GetSmallY(), theta, noise));
+
+            double f_best = 0.0;
+            {
+                std::lock_guard<std::mutex> lock(orig->DeviceMutex());
+                check(orig->Device(), slsgp_get_f_best(orig->Device(), &f_best, nullptr), "slsgp_get_f_best");
+            }
+            // mu / dmu from the original model, sigma / dsigma from the temporary one, formulas on the device
+            const auto pair_acq = [&](const MatrixXd& Xq, VectorXd& val, MatrixXd* grad) {
+                const long M = Xq.cols();
+                VectorXd   mu, sigma;
+                MatrixXd   dmu, dsigma;
+                orig->PredictBatch(Xq, &mu, nullptr, grad ? &dmu : nullptr, nullptr);
+                temp->PredictBatch(Xq, nullptr, &sigma, nullptr, grad ? &dsigma : nullptr);
+                val = VectorXd::Zero(M);
+                if (grad) *grad = MatrixXd::Zero(D, M);
+                std::lock_guard<std::mutex> lock(orig->DeviceMutex());
+                check(orig->Device(),
+                      slsgp_acq_from_posterior(orig->Device(), internal::to_abi(func_type), hyperparam, f_best, (int) D, M, mu.data(), sigma.data(),
+                                               grad ? dmu.data() : nullptr, grad ? dsigma.data() : nullptr, val.data(), grad ? grad->data() : nullptr),
+                      "slsgp_acq_from_posterior");
+            };
+
+            const long count = (long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter;
+            MatrixXd   cand  = MatrixXd::Zero(D, count);
+            for (unsigned i = 0; i < num_points; ++i)
+            {
+                {
+                    std::lock_guard<std::mutex> lock(orig->DeviceMutex());
+                    check(orig->Device(), slsgp_candidates(orig->Device(), search_seed(regressor) + 0x51ED27ull * (i + 1), 0, count, cand.data()), "slsgp_candidates");
+                }
+                VectorXd val;
+                pair_acq(cand, val, nullptr);
+                long best = 0;
+                for (long m = 1; m < count; ++m)
+                    if (val(m) > val(best)) best = m; // NaN never wins, lowest index wins ties
+                const VectorXd x_star = polish(
+                    [&](const VectorXd& x, VectorXd& g) {
+                        MatrixXd X1 = MatrixXd::Zero(D, 1), G;
+                        X1.col(0)   = x;
+                        VectorXd v;
+                        pair_acq(X1, v, &G);
+                        g = G.col(0);
+                        return v(0);
+                    },
+                    cand.col(best), num_local_search_iters);
+                points.push_back(x_star);
+
+                if (points.size() != num_points)
+                {
+                    // the pending point joins the temporary model with its predicted value (which never influences sigma)
+                    const long N = temp->GetLargeX().cols();
+                    MatrixXd   new_X = MatrixXd::Zero(D, N + 1);
+                    VectorXd   new_y = VectorXd::Zero(N + 1);
+                    for (long j = 0; j < N; ++j) new_X.col(j) = temp->GetLargeX().col(j), new_y(j) = temp->GetSmallY()(j);
+                    new_X.col(N) = x_star;
+                    new_y(N)     = temp->PredictMu(x_star);
+                    temp.reset(new GaussianProcessRegressor(new_X, new_y, theta, noise));
+                }
+            }
+            return points;
+        }
+    } // namespace acquisition_func
+} // namespace sequential_line_search

@@ -1,0 +1,215 @@
+// extern "C" handles onto the C++ host layer, one per handle oracle/ref_capi.cpp offers onto the reference, so the
+// parity tests drive both class hierarchies through ctypes with the same arguments (prefix b200_ here, ref_ there).
+// C++ exceptions never cross this boundary: a failing call stores the message (b200_last_error) and returns null / NaN.
+#include "device.hpp"
+
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <string>
+
+using Eigen::MatrixXd;
+using Eigen::VectorXd;
+using namespace sequential_line_search;
+
+namespace
+{
+    thread_local std::string g_error;
+
+    KernelType          kernel_type(int kt) { return kt == 0 ? KernelType::ArdSquaredExponentialKernel : KernelType::ArdMatern52Kernel; }
+    AcquisitionFuncType acq_type(int t) { return t == 0 ? AcquisitionFuncType::ExpectedImprovement : AcquisitionFuncType::GaussianProcessUpperConfidenceBound; }
+    MatrixXd            matrix(const double* p, int rows, int cols)
+    {
+        MatrixXd m = MatrixXd::Zero(rows, cols);
+        if (rows && cols) std::memcpy(m.data(), p, sizeof(double) * (size_t) rows * (size_t) cols);
+        return m;
+    }
+    VectorXd vector(const double* p, int n)
+    {
+        VectorXd v = VectorXd::Zero(n);
+        if (n) std::memcpy(v.data(), p, sizeof(double) * (size_t) n);
+        return v;
+    }
+    void store(const VectorXd& v, double* out) { std::memcpy(out, v.data(), sizeof(double) * (size_t) v.size()); }
+    void store(const MatrixXd& m, double* out) { std::memcpy(out, m.data(), sizeof(double) * (size_t) m.rows() * (size_t) m.cols()); }
+
+    template <typename F> auto guarded(F&& f, decltype(f()) on_error) -> decltype(f())
+    {
+        try
+        {
+            g_error.clear();
+            return f();
+        }
+        catch (const std::exception& e)
+        {
+            g_error = e.what();
+            return on_error;
+        }
+    }
+    const double kNaN = std::numeric_limits<double>::quiet_NaN();
+} // namespace
+
+extern "C"
+{
+    const char* b200_last_error() { return g_error.c_str(); }
+
+    // ---- kernels handed out by Regressor::GetKernel() & co ------------------------------------------------------
+    void b200_kernel(int kt, int D, const double* xa, const double* xb, const double* theta, double* k, double* dtheta, double* dxa)
+    {
+        GaussianProcessRegressor probe(MatrixXd(), VectorXd(), VectorXd(), 0.0, kernel_type(kt)); // no data: no device needed
+        const VectorXd           a = vector(xa, D), b = vector(xb, D), th = vector(theta, D + 1);
+        if (k) *k = probe.GetKernel()(a, b, th);
+        if (dtheta) store(probe.GetKernelThetaDerivative()(a, b, th), dtheta);
+        if (dxa) store(probe.GetKernelFirstArgDerivative()(a, b, th), dxa);
+    }
+    int b200_calc_large_ky(int kt, int D, int N, const double* X, const double* theta, double b, double* K_out)
+    {
+        return guarded(
+            [&]() {
+                GaussianProcessRegressor probe(MatrixXd(), VectorXd(), VectorXd(), 0.0, kernel_type(kt));
+                store(CalcLargeKY(matrix(X, D, N), vector(theta, D + 1), b, probe.GetKernel()), K_out);
+                return 0;
+            },
+            1);
+    }
+
+    // ---- GaussianProcessRegressor ---------------------------------------------------------------------------------
+    void* b200_gpr_create(int kt, int D, int N, const double* X, const double* y, const double* theta, double b)
+    {
+        return guarded([&]() -> void* { return new GaussianProcessRegressor(matrix(X, D, N), vector(y, N), vector(theta, D + 1), b, kernel_type(kt)); },
+                       nullptr);
+    }
+    void* b200_gpr_create_map(int kt, int D, int N, const double* X, const double* y) // hyper-parameters by MAP estimation
+    {
+        return guarded([&]() -> void* { return new GaussianProcessRegressor(matrix(X, D, N), vector(y, N), kernel_type(kt)); }, nullptr);
+    }
+    void        b200_gpr_destroy(void* h) { delete static_cast<GaussianProcessRegressor*>(h); }
+    const void* b200_gpr_regressor(void* h) { return static_cast<const Regressor*>(static_cast<GaussianProcessRegressor*>(h)); }
+    void        b200_gpr_get_state(void* hv, double* K_y, double* K_y_inv, double* theta, double* b)
+    {
+        const auto& r = *static_cast<GaussianProcessRegressor*>(hv);
+        if (K_y) store(r.m_K_y, K_y);
+        if (K_y_inv) store(r.m_K_y_inv, K_y_inv);
+        if (theta) store(r.GetKernelHyperparams(), theta);
+        if (b) *b = r.GetNoiseHyperparam();
+    }
+
+    // ---- PreferenceRegressor (tuples in CSR form, first member preferred) ---------------------------------------------
+    void* b200_pref_create(int kt, int D, int N, const double* X, int P, const unsigned* offsets, const unsigned* idx, int use_map,
+                           double a, double r, double b, double prior_var, double btl_scale, unsigned num_iters)
+    {
+        return guarded(
+            [&]() -> void* {
+                std::vector<Preference> prefs;
+                for (int t = 0; t < P; ++t) prefs.push_back(Preference(std::vector<unsigned>(idx + offsets[t], idx + offsets[t + 1])));
+                return new PreferenceRegressor(matrix(X, D, N), prefs, use_map != 0, a, r, b, prior_var, btl_scale, num_iters, kernel_type(kt));
+            },
+            nullptr);
+    }
+    void        b200_pref_destroy(void* h) { delete static_cast<PreferenceRegressor*>(h); }
+    const void* b200_pref_regressor(void* h) { return static_cast<const Regressor*>(static_cast<PreferenceRegressor*>(h)); }
+    double      b200_pref_objective(void* hv, const double* x, int n, double* grad /* may be null */)
+    {
+        return guarded(
+            [&]() {
+                VectorXd     g;
+                const double f = static_cast<PreferenceRegressor*>(hv)->EvaluateMapObjective(vector(x, n), grad ? &g : nullptr);
+                if (grad) store(g, grad);
+                return f;
+            },
+            kNaN);
+    }
+    unsigned b200_pref_num_map_evaluations(void* hv) { return static_cast<PreferenceRegressor*>(hv)->GetNumMapEvaluations(); }
+    void     b200_pref_get_state(void* hv, double* y, double* theta, double* b, double* K, double* L)
+    {
+        const PreferenceRegressor& r = *static_cast<PreferenceRegressor*>(hv);
+        if (y) store(r.GetSmallY(), y);
+        if (theta) store(r.m_kernel_hyperparams, theta);
+        if (b) *b = r.m_noise_hyperparam;
+        if (K) store(r.m_K, K);
+        if (L) store(r.m_L, L);
+    }
+    void b200_pref_find_arg_max(void* hv, double* x_out) { store(static_cast<PreferenceRegressor*>(hv)->FindArgMax(), x_out); }
+    int  b200_pref_damp_data(void* hv, const char* dir, const char* prefix)
+    {
+        return guarded([&]() { return static_cast<PreferenceRegressor*>(hv)->DampData(dir, prefix), 0; }, 1);
+    }
+
+    // ---- Regressor virtual interface ------------------------------------------------------------------------------------
+    double b200_predict_mu(const void* r, int D, const double* x)
+    {
+        return guarded([&]() { return static_cast<const Regressor*>(r)->PredictMu(vector(x, D)); }, kNaN);
+    }
+    double b200_predict_sigma(const void* r, int D, const double* x)
+    {
+        return guarded([&]() { return static_cast<const Regressor*>(r)->PredictSigma(vector(x, D)); }, kNaN);
+    }
+    int b200_predict_mu_derivative(const void* r, int D, const double* x, double* out)
+    {
+        return guarded([&]() { return store(static_cast<const Regressor*>(r)->PredictMuDerivative(vector(x, D)), out), 0; }, 1);
+    }
+    int b200_predict_sigma_derivative(const void* r, int D, const double* x, double* out)
+    {
+        return guarded([&]() { return store(static_cast<const Regressor*>(r)->PredictSigmaDerivative(vector(x, D)), out), 0; }, 1);
+    }
+    int b200_predict_maximum_point_from_data(const void* r, int D, double* out)
+    {
+        return guarded([&]() { return store(static_cast<const Regressor*>(r)->PredictMaximumPointFromData(), out), 0; }, 1);
+    }
+    int b200_predict_batch(const void* r, int D, int M, const double* Xq, double* mu, double* sigma, double* dmu, double* dsigma)
+    {
+        return guarded(
+            [&]() {
+                const auto* d = dynamic_cast<const DeviceRegressor*>(static_cast<const Regressor*>(r));
+                if (!d) throw std::invalid_argument("not a device-backed regressor");
+                VectorXd m, s;
+                MatrixXd dm, ds;
+                d->PredictBatch(matrix(Xq, D, M), mu ? &m : nullptr, sigma ? &s : nullptr, dmu ? &dm : nullptr, dsigma ? &ds : nullptr);
+                if (mu) store(m, mu);
+                if (sigma) store(s, sigma);
+                if (dmu) store(dm, dmu);
+                if (dsigma) store(ds, dsigma);
+                return 0;
+            },
+            1);
+    }
+
+    // ---- acquisition_func --------------------------------------------------------------------------------------------------
+    double b200_acq_value(const void* r, int D, int acq, double ucb_beta, const double* x)
+    {
+        return guarded([&]() { return acquisition_func::CalcAcquisitionValue(*static_cast<const Regressor*>(r), vector(x, D), acq_type(acq), ucb_beta); }, kNaN);
+    }
+    int b200_acq_derivative(const void* r, int D, int acq, double ucb_beta, const double* x, double* out)
+    {
+        return guarded(
+            [&]() { return store(acquisition_func::CalcAcquisitionValueDerivative(*static_cast<const Regressor*>(r), vector(x, D), acq_type(acq), ucb_beta), out), 0; }, 1);
+    }
+    int b200_acq_values(const void* r, int D, int M, int acq, double ucb_beta, const double* Xq, double* val, double* grad)
+    {
+        return guarded(
+            [&]() {
+                const auto* d = dynamic_cast<const DeviceRegressor*>(static_cast<const Regressor*>(r));
+                if (!d) throw std::invalid_argument("not a device-backed regressor");
+                MatrixXd g;
+                store(acquisition_func::CalcAcquisitionValues(*d, matrix(Xq, D, M), acq_type(acq), ucb_beta, grad ? &g : nullptr), val);
+                if (grad) store(g, grad);
+                return 0;
+            },
+            1);
+    }
+    int b200_find_next_point(const void* r, int D, unsigned n_global, unsigned n_local, int acq, double ucb_beta, double* x_out)
+    {
+        return guarded(
+            [&]() { return store(acquisition_func::FindNextPoint(*static_cast<const Regressor*>(r), n_global, n_local, acq_type(acq), ucb_beta), x_out), 0; }, 1);
+    }
+    int b200_find_next_points(const void* r, int D, unsigned n_points, unsigned n_global, unsigned n_local, int acq, double ucb_beta, double* X_out)
+    {
+        return guarded(
+            [&]() {
+                const auto pts = acquisition_func::FindNextPoints(*static_cast<const Regressor*>(r), n_points, n_global, n_local, acq_type(acq), ucb_beta);
+                for (size_t i = 0; i < pts.size(); ++i) store(pts[i], X_out + i * (size_t) D);
+                return 0;
+            },
+            1);
+    }
+}

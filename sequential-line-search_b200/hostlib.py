@@ -1,0 +1,203 @@
+"""ctypes view of libsls_b200_host.so, the C++ host layer (host/): the reference's Regressor / acquisition_func
+interface served by libslsgp. The extern "C" facade (host/src/capi.cpp) offers the same handles oracle/ref_capi.cpp
+offers onto the reference, so tests drive both with identical arguments. Used by tests and smoke only; C++ users link
+the library and include host/include/sequential-line-search/*.hpp directly."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import HOST_LIB_PATH, build_host
+
+c_dp = C.POINTER(C.c_double)
+c_up = C.POINTER(C.c_uint)
+_lib = None
+
+_DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value")
+_POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_regressor")
+HOST_SYMBOLS = [
+    "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy",
+    "b200_gpr_regressor", "b200_gpr_get_state", "b200_pref_create", "b200_pref_destroy", "b200_pref_regressor",
+    "b200_pref_objective", "b200_pref_num_map_evaluations", "b200_pref_get_state", "b200_pref_find_arg_max",
+    "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
+    "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
+    "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points",
+]
+
+
+def load_host_library(build_if_missing: bool = True) -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(HOST_LIB_PATH):
+        if not build_if_missing:
+            raise RuntimeError(f"{HOST_LIB_PATH} is missing; run `python __graft_entry__.py build`")
+        build_host()
+    lib = C.CDLL(HOST_LIB_PATH)
+    for name in HOST_SYMBOLS:
+        getattr(lib, name)  # AttributeError == facade / library mismatch
+    for name in _DOUBLE:
+        getattr(lib, name).restype = C.c_double
+    for name in _POINTER:
+        getattr(lib, name).restype = C.c_void_p
+    lib.b200_last_error.restype = C.c_char_p
+    lib.b200_pref_num_map_evaluations.restype = C.c_uint
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.require(np.asarray(a, dtype=np.float64), requirements=["F", "A"])
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+class HostError(RuntimeError):
+    pass
+
+
+class Host:
+    """Thin wrapper: numpy in / numpy out, raises HostError with the C++ exception text."""
+
+    def __init__(self):
+        self.lib = load_host_library()
+
+    def _ok(self, cond):
+        if not cond:
+            raise HostError(self.lib.b200_last_error().decode())
+
+    def kernel(self, kt, xa, xb, theta):
+        xa, xb, theta = _f64(xa), _f64(xb), _f64(theta)
+        D = len(xa)
+        k, dth, dx = C.c_double(), np.empty(D + 1), np.empty(D)
+        self.lib.b200_kernel(kt, D, _p(xa), _p(xb), _p(theta), C.byref(k), _p(dth), _p(dx))
+        return k.value, dth, dx
+
+    def large_ky(self, kt, X, theta, b):
+        X, theta = _f64(X), _f64(theta)
+        D, N = X.shape
+        K = np.empty((N, N), order="F")
+        self._ok(self.lib.b200_calc_large_ky(kt, D, N, _p(X), _p(theta), C.c_double(b), _p(K)) == 0)
+        return K
+
+    # GaussianProcessRegressor
+    def gpr_create(self, kt, X, y, theta=None, b=None):
+        X, y = _f64(X), _f64(y)
+        D, N = X.shape
+        if theta is None:
+            h = self.lib.b200_gpr_create_map(kt, D, N, _p(X), _p(y))
+        else:
+            h = self.lib.b200_gpr_create(kt, D, N, _p(X), _p(y), _p(_f64(theta)), C.c_double(b))
+        self._ok(h)
+        return C.c_void_p(h)
+
+    def gpr_destroy(self, h):
+        self.lib.b200_gpr_destroy(h)
+
+    def gpr_regressor(self, h):
+        return C.c_void_p(self.lib.b200_gpr_regressor(h))
+
+    def gpr_state(self, h, N, D):
+        K, Kinv = np.empty((N, N), order="F"), np.empty((N, N), order="F")
+        theta, b = np.empty(D + 1), C.c_double()
+        self.lib.b200_gpr_get_state(h, _p(K), _p(Kinv), _p(theta), C.byref(b))
+        return dict(K=K, Kinv=Kinv, theta=theta, b=b.value)
+
+    # PreferenceRegressor
+    def pref_create(self, kt, X, offsets, idx, use_map, a, r, b, prior_var, btl_scale, num_iters=100):
+        X = _f64(X)
+        D, N = X.shape
+        offsets, idx = np.ascontiguousarray(offsets, dtype=np.uint32), np.ascontiguousarray(idx, dtype=np.uint32)
+        h = self.lib.b200_pref_create(kt, D, N, _p(X), len(offsets) - 1, offsets.ctypes.data_as(c_up), idx.ctypes.data_as(c_up),
+                                      int(use_map), C.c_double(a), C.c_double(r), C.c_double(b), C.c_double(prior_var),
+                                      C.c_double(btl_scale), C.c_uint(num_iters))
+        self._ok(h)
+        return C.c_void_p(h)
+
+    def pref_destroy(self, h):
+        self.lib.b200_pref_destroy(h)
+
+    def pref_regressor(self, h):
+        return C.c_void_p(self.lib.b200_pref_regressor(h))
+
+    def pref_objective(self, h, x, want_grad=True):
+        x = _f64(x)
+        g = np.empty(len(x)) if want_grad else None
+        f = self.lib.b200_pref_objective(h, _p(x), len(x), _p(g))
+        self._ok(f == f)
+        return f, g
+
+    def pref_num_map_evaluations(self, h):
+        return int(self.lib.b200_pref_num_map_evaluations(h))
+
+    def pref_state(self, h, N, D):
+        y, theta, b = np.empty(N), np.empty(D + 1), C.c_double()
+        K, L = np.empty((N, N), order="F"), np.empty((N, N), order="F")
+        self.lib.b200_pref_get_state(h, _p(y), _p(theta), C.byref(b), _p(K), _p(L))
+        return dict(y=y, theta=theta, b=b.value, K=K, L=L)
+
+    def pref_find_arg_max(self, h, D):
+        out = np.empty(D)
+        self.lib.b200_pref_find_arg_max(h, _p(out))
+        return out
+
+    def pref_damp_data(self, h, directory, prefix=""):
+        self._ok(self.lib.b200_pref_damp_data(h, directory.encode(), prefix.encode()) == 0)
+
+    # Regressor virtuals + acquisition
+    def predict(self, reg, x):
+        x = _f64(x)
+        D = len(x)
+        dmu, dsg = np.empty(D), np.empty(D)
+        mu = self.lib.b200_predict_mu(reg, D, _p(x))
+        sg = self.lib.b200_predict_sigma(reg, D, _p(x))
+        self._ok(mu == mu)
+        self._ok(self.lib.b200_predict_mu_derivative(reg, D, _p(x), _p(dmu)) == 0)
+        self._ok(self.lib.b200_predict_sigma_derivative(reg, D, _p(x), _p(dsg)) == 0)
+        return mu, sg, dmu, dsg
+
+    def predict_batch(self, reg, Xq):
+        Xq = _f64(Xq)
+        D, M = Xq.shape
+        mu, sg = np.empty(M), np.empty(M)
+        dmu, dsg = np.empty((D, M), order="F"), np.empty((D, M), order="F")
+        self._ok(self.lib.b200_predict_batch(reg, D, M, _p(Xq), _p(mu), _p(sg), _p(dmu), _p(dsg)) == 0)
+        return mu, sg, dmu, dsg
+
+    def x_best(self, reg, D):
+        out = np.empty(D)
+        self._ok(self.lib.b200_predict_maximum_point_from_data(reg, D, _p(out)) == 0)
+        return out
+
+    def acq(self, reg, acq_type, beta, x, want_grad=True):
+        x = _f64(x)
+        D = len(x)
+        v = self.lib.b200_acq_value(reg, D, acq_type, C.c_double(beta), _p(x))
+        self._ok(v == v)
+        g = None
+        if want_grad:
+            g = np.empty(D)
+            self._ok(self.lib.b200_acq_derivative(reg, D, acq_type, C.c_double(beta), _p(x), _p(g)) == 0)
+        return v, g
+
+    def acq_values(self, reg, acq_type, beta, Xq, want_grad=True):
+        Xq = _f64(Xq)
+        D, M = Xq.shape
+        val = np.empty(M)
+        grad = np.empty((D, M), order="F") if want_grad else None
+        self._ok(self.lib.b200_acq_values(reg, D, M, acq_type, C.c_double(beta), _p(Xq), _p(val), _p(grad)) == 0)
+        return val, grad
+
+    def find_next_point(self, reg, D, n_global=100, n_local=50, acq_type=0, beta=1.0):
+        out = np.empty(D)
+        self._ok(self.lib.b200_find_next_point(reg, D, n_global, n_local, acq_type, C.c_double(beta), _p(out)) == 0)
+        return out
+
+    def find_next_points(self, reg, D, n_points, n_global=100, n_local=50, acq_type=0, beta=1.0):
+        out = np.empty((D, n_points), order="F")
+        self._ok(self.lib.b200_find_next_points(reg, D, n_points, n_global, n_local, acq_type, C.c_double(beta), _p(out)) == 0)
+        return out
