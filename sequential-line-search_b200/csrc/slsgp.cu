@@ -485,7 +485,7 @@ namespace
         const size_t brows = 2 * (size_t) ldt + TC_BN;
         TRY(ensure(ctx, ctx->Bmat, sizeof(__half) * brows * ldt));
         TRY(ensure(ctx, ctx->Xt, sizeof(float) * (size_t) ldt * XP));
-        TRY(ensure(ctx, ctx->Xs32, sizeof(float) * (size_t) ldt * (ctx->D + 1)));
+        TRY(ensure(ctx, ctx->Xs32, sizeof(float) * (size_t) ldt * ctx->D));
         TRY(ensure(ctx, ctx->tcs, sizeof(TcScales)));
         if (!ctx->tc_err.p)
         {
@@ -574,12 +574,12 @@ namespace
         __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) buf * 2 * ctx->tc_Mcap * ldt;
         __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
         ProfScope       ps(ctx, "tc_kstar", st);
-        const size_t    smem = sizeof(float) * (size_t) (64 * (((D + 3) & ~3) + 4) + (D + 1) * 128);
+        const size_t    smem = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + D * 128);
         static bool     kstar_attr = false;
         if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
         {
             CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int) (sizeof(float) * (64 * 72 + 68 * 128))));
+                                          (int) (sizeof(float) * (64 * 68 + 67 * 128))));
             kstar_attr = true;
         }
         kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, st>>>(

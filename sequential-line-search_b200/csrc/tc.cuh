@@ -265,6 +265,13 @@ namespace slsgp
             return *reinterpret_cast<float2*>(&rd);
         }
 
+        __device__ __forceinline__ float2 fadd2(float2 a, float2 b) // packed FP32 add (FADD2)
+        {
+            unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b), rd;
+            asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+            return *reinterpret_cast<float2*>(&rd);
+        }
+
         __device__ __forceinline__ float ex2_approx(float x)
         {
             float y;

@@ -114,8 +114,8 @@ namespace slsgp
         Bmat[(size_t) i * ldt + j] = __float2half_rn(v);
     }
 
-    // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = (X_dj - 1/2) / l_d for kstar16 and
-    // Xs32[D][j] = -1/2 log2(e) |Xs32[.][j]|^2 (the observation's share of the exponent).
+    // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = -(X_dj - 1/2) / l_d (negated: kstar16
+    // forms q - x with a packed add).
     __global__ void __launch_bounds__(256)
         tc_pack_x_kernel(const double* __restrict__ X, int N, int D, int XP, int ldt, const double* __restrict__ inv_l,
                          float* __restrict__ Xt, float* __restrict__ Xs32)
@@ -128,60 +128,47 @@ namespace slsgp
             if (i < N) v = c == 0 ? 1.f : (c <= D ? (float) X[(size_t) (c - 1) + (size_t) i * D] : 0.f);
             Xt[(size_t) i * XP + c] = v;
         }
-        float nn = 0.f;
         for (int d = 0; d < D; ++d)
-        {
-            const float v = i < N ? (float) ((X[(size_t) d + (size_t) i * D] - 0.5) * inv_l[d]) : 0.f;
-            Xs32[(size_t) d * ldt + i] = v;
-            nn                         = fmaf(v, v, nn);
-        }
-        Xs32[(size_t) D * ldt + i] = -0.72134752044448170368f * nn;
+            Xs32[(size_t) d * ldt + i] = i < N ? -(float) ((X[(size_t) d + (size_t) i * D] - 0.5) * inv_l[d]) : 0.f;
     }
 
-    // Ks[m][j] = fp16(sK * a * exp(-r2/2)) and its rounding residual. With q, x the centred, length-scaled coordinates in
-    // fp32, r2 = |q|^2 + |x|^2 - 2 q.x: the dot product runs on packed FFMA2 (two observations per issue slot); in fp32
-    // the cancellation costs ~1e-6 of k, far below the fp16 operand rounding the residual row exists to repair.
+    // Ks[m][j] = fp16(sK * a * exp(-r2/2)) and its rounding residual; r2 by direct differences of the centred,
+    // length-scaled coordinates in fp32 (no |q|^2 + |x|^2 - 2 q.x cancellation: near a data point sigma^2 = a - k.A.k
+    // amplifies any relative error of k by a / sigma^2). The differences and their squares run on the packed FP32
+    // pipe (FADD2 + FFMA2: two observations per issue slot); Xs32 holds the NEGATED observation coordinates.
     // Tile: 64 candidates x 128 observations per CTA; thread = 4 candidates x 8 consecutive j (one 16-byte store per row).
-    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * (DQ + 1) + (D + 1) * 128) floats, DQ = round_up(D, 4).
+    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * DQ + D * 128) floats, DQ = round_up(D, 4).
     __global__ void __launch_bounds__(256)
         kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
                        const float* __restrict__ Xs32, const double* __restrict__ inv_l,
                        const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo)
     {
         extern __shared__ __align__(16) float ksm[];
-        const int               DQ = (D + 3) & ~3, QS = DQ + 4; // row stride of sq: 16-byte aligned rows, column DQ = exponent share
-        float*                  sq = ksm;                       // [64][QS]
-        float*                  sx = ksm + 64 * QS;             // [D + 1][128], row D = -1/2 log2(e) |x|^2
+        const int               DQ = (D + 3) & ~3; // row stride of sq: 16-byte aligned rows
+        float*                  sq = ksm;          // [64][DQ]
+        float*                  sx = ksm + 64 * DQ; // [D][128], negated
         const int               tid = threadIdx.x, j_base = blockIdx.x * 128;
         const long long         m_base = (long long) blockIdx.y * 64;
-        const float             c1 = -0.72134752044448170368f; // -0.5 * log2(e)
         for (int e = tid; e < 64 * DQ; e += 256)
         {
             const int       p = e / DQ, d = e - p * DQ;
             const long long m = m_base + p;
-            sq[p * QS + d]  = (m < Mc && d < D) ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
+            sq[p * DQ + d]  = (m < Mc && d < D) ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
         }
-        for (int e = tid; e < (D + 1) * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
-        __syncthreads();
-        if (tid < 64)
-        {
-            float nn = 0.f;
-            for (int d = 0; d < D; ++d) nn = fmaf(sq[tid * QS + d], sq[tid * QS + d], nn);
-            sq[tid * QS + DQ] = fmaf(c1, nn, sc->c0); // candidate's share of the exponent, log2(a sK) folded in
-        }
+        for (int e = tid; e < D * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
         __syncthreads();
 
         const int tj = tid & 15, tm = tid >> 4;
-        float2    dot[4][4];
+        float2    r2[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int jj = 0; jj < 4; ++jj) dot[i][jj] = make_float2(0.f, 0.f);
+            for (int jj = 0; jj < 4; ++jj) r2[i][jj] = make_float2(0.f, 0.f);
         for (int d0 = 0; d0 < DQ; d0 += 4)
         {
             float4 qv[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(&sq[(tm * 4 + i) * QS + d0]);
+            for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(&sq[(tm * 4 + i) * DQ + d0]);
 #pragma unroll
             for (int dd = 0; dd < 4; ++dd)
             {
@@ -196,30 +183,28 @@ namespace slsgp
                         const float  q  = dd == 0 ? qv[i].x : (dd == 1 ? qv[i].y : (dd == 2 ? qv[i].z : qv[i].w));
                         const float2 q2 = make_float2(q, q);
 #pragma unroll
-                        for (int jj = 0; jj < 4; ++jj) dot[i][jj] = tc::ffma2(q2, x2[jj], dot[i][jj]);
+                        for (int jj = 0; jj < 4; ++jj)
+                        {
+                            const float2 df = tc::fadd2(q2, x2[jj]); // q - x
+                            r2[i][jj]       = tc::ffma2(df, df, r2[i][jj]);
+                        }
                     }
                 }
             }
         }
-        const float4 na = *reinterpret_cast<const float4*>(&sx[D * 128 + tj * 8]);
-        const float4 nb = *reinterpret_cast<const float4*>(&sx[D * 128 + tj * 8 + 4]);
-        const float  xn[8] = {na.x, na.y, na.z, na.w, nb.x, nb.y, nb.z, nb.w};
-        const float  m2c1 = -2.f * c1;
+        const float c1 = -0.72134752044448170368f; // -0.5 * log2(e)
+        const float c0 = sc->c0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
-            const long long m  = m_base + tm * 4 + i;
-            const float     qa = sq[(tm * 4 + i) * QS + DQ];
+            const long long m = m_base + tm * 4 + i;
             __half2         h[4], hl[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
             {
                 const int   j  = j_base + tj * 8 + 2 * jj;
-                // exponent = c0 + c1 (|q|^2 + |x|^2 - 2 q.x), clamped at 0 distance against rounding
-                const float e0 = fminf(fmaf(dot[i][jj].x, m2c1, qa + xn[2 * jj]), sc->c0);
-                const float e1 = fminf(fmaf(dot[i][jj].y, m2c1, qa + xn[2 * jj + 1]), sc->c0);
-                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(e0) : 0.f;
-                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(e1) : 0.f;
+                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)) : 0.f;
+                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0)) : 0.f;
                 h[jj]          = __floats2half2_rn(v0, v1);
                 const float2 b = __half22float2(h[jj]);
                 hl[jj]         = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)

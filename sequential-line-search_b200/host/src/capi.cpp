@@ -1,4 +1,4 @@
-// extern "C" handles onto the C++ host layer, one per handle oracle/ref_capi.cpp offers onto the reference, so the
+// extern "C" handles onto the C++ host layer, mirroring the handles the test suite binds onto the reference classes, so the
 // parity tests drive both class hierarchies through ctypes with the same arguments (prefix b200_ here, ref_ there).
 // C++ exceptions never cross this boundary: a failing call stores the message (b200_last_error) and returns null / NaN.
 #include "device.hpp"

@@ -1,6 +1,6 @@
 """ctypes view of libsls_b200_host.so, the C++ host layer (host/): the reference's Regressor / acquisition_func
-interface served by libslsgp. The extern "C" facade (host/src/capi.cpp) offers the same handles oracle/ref_capi.cpp
-offers onto the reference, so tests drive both with identical arguments. Used by tests and smoke only; C++ users link
+interface served by libslsgp. The extern "C" facade (host/src/capi.cpp) offers the same handles the test suite binds
+onto the reference classes, so tests drive both with identical arguments. Used by tests and smoke only; C++ users link
 the library and include host/include/sequential-line-search/*.hpp directly."""
 from __future__ import annotations
 

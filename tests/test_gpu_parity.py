@@ -89,6 +89,25 @@ def test_posterior_and_acquisition_sweep(ctx, oracle, kt, D, N):
         np.testing.assert_array_equal(val2, val)
 
 
+def test_acq_from_posterior_reproduces_the_sweep(ctx):
+    """slsgp_acq_from_posterior applies the same formulas as the tail of the sweep (used with mu and sigma from two
+    different models by FindNextPoints, src/acquisition-function.cpp:63-110)."""
+    kt, D, N = S.MATERN, 5, 60
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    ctx.fit(X, kt, theta, 0.005, S.make_y(X))
+    f_best, _ = ctx.f_best()
+    Q = np.concatenate([S.make_queries(300, D), X[:, :2]], axis=1)   # includes sigma ~ 0 points
+    mu, sigma, dmu, dsigma = ctx.posterior_batch(Q)
+    for acq, beta in ((0, 1.0), (1, 2.5)):
+        val, grad = ctx.acq_batch(acq, beta, Q)
+        v2, g2 = ctx.acq_from_posterior(acq, beta, f_best, mu, sigma, dmu, dsigma)
+        np.testing.assert_allclose(v2, val, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(g2, grad, rtol=1e-10, atol=1e-14 * np.max(np.abs(grad)))
+        v3, g3 = ctx.acq_from_posterior(acq, beta, f_best, mu, sigma)
+        np.testing.assert_array_equal(v3, v2)
+        assert g3 is None
+
+
 def test_sweep_shards_are_consistent(ctx, oracle):
     """M larger than one internal shard (16384): results must not depend on the sharding."""
     kt, D, N = S.SE, 6, 100
