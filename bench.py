@@ -364,9 +364,17 @@ def main_graft(args):
             kname = "gemm64_kernel<NN> (beta = K^-1 k*, FP64 DFMA)"
             note = "the kernel runs on the FP64 pipe; the tensor peak is quoted for scale only"
         else:
-            kname = f"tc_sweep_gemm_kernel<20> (tcgen05.mma kind::f16, {PASSES[args.mode]} split-fp16 pass(es), fused epilogue)"
+            kname = (f"tc_sweep_gemm_kernel<20, 2> (tcgen05.mma cta_group::2 kind::f16, 256x256x16, {PASSES[args.mode]} split-fp16 "
+                     "pass(es) per pipeline stage, fused epilogue)")
             note = (f"achieved counts ALGORITHMIC flops; the tensor pipe executes {PASSES[args.mode]}x the 2N^2 term "
                     f"(executed ~{PASSES[args.mode] * achieved:.0f} TFLOP/s)") if achieved else ""
+        traffic = None
+        try:  # dram bytes per launch of the dominant kernel, from the committed ncu --set full capture
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_roofline_traffic.json")))["tc_sweep_gemm_kernel"]
+            if args.mode == "tensor" and cands_per_launch:
+                traffic = tr["dram_bytes_per_launch"] * cands_per_launch / tr["candidates_per_launch"]
+        except Exception:
+            traffic = None
         line = {
             "metric": METRIC, "value": world * M * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -385,7 +393,9 @@ def main_graft(args):
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": kname,
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic,
+                         "executed_tflops": (PASSES[args.mode] * achieved) if achieved else None,
+                         "executed_frac": (PASSES[args.mode] * achieved / peak) if achieved else None,
                          "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)", "note": note,
                          "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                          "share_of_sweep": gemm_ms / sweep_total if sweep_total else None,

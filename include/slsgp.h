@@ -162,6 +162,19 @@ extern "C"
     slsgp_status slsgp_acq_argmax(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
                                   int64_t first, int64_t count, double* x_best_out, double* val_best_out,
                                   int64_t* index_best_out, double* grad_best_out);
+    /* FindGlobalSolution (src/acquisition-function.cpp:112-167) as one device-resident procedure; the multi-start form of
+     * the reference (random starts + NLopt L-BFGS on threads, :125-144) without a host round trip per objective evaluation:
+     *   1. the dense sweep of slsgp_acq_argmax over candidates [first, first + count) in the context's sweep mode;
+     *   2. the best candidate of each of `n_starts` equal slices of that range becomes a starting point (<= 16384);
+     *   3. `n_iters` iterations of projected, normalised-gradient ascent with a per-start trust radius inside [0,1]^D,
+     *      every start advanced by ONE batched IEEE-double sweep per iteration;
+     *   4. the arg-max over the refined starts.
+     * x_best_out: D. grad_best_out (D) and val_sweep_best_out (best value of step 1 alone) may be NULL.
+     * Shards across GPUs like slsgp_acq_argmax: each rank maximises its own range, the winners are compared by value. */
+    slsgp_status slsgp_acq_maximize(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed, int64_t first,
+                                    int64_t count, int n_starts, int n_iters, double* x_best_out, double* val_best_out,
+                                    double* grad_best_out, double* val_sweep_best_out);
+
     /* Arg-max (lowest index wins ties, NaN never wins) of `count` values already on the device, e.g. the d_val of
      * slsgp_acq_batch_device; index_best_out = index0 + position. Synchronises the context's stream. */
     slsgp_status slsgp_argmax_device(slsgp_ctx* ctx, const double* d_val, int64_t count, int64_t index0,
@@ -194,7 +207,7 @@ extern "C"
     /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
     uint64_t     slsgp_launch_count(const slsgp_ctx* ctx);
     /* Milliseconds (CUDA events on the context's stream) spent in the most recent call of the named phase:
-     * "gram", "factor", "inverse", "alpha", "sweep", "map". Returns < 0 for an unknown name. */
+     * "gram", "factor", "inverse", "alpha", "sweep", "map", "maximize". Returns < 0 for an unknown name. */
     double       slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase);
     /* Per-kernel device timing: while enabled, every launch of the named hot kernels is bracketed by CUDA events on
      * the context's stream. slsgp_profile_read synchronises, returns the summed duration and launch count of

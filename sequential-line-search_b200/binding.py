@@ -43,6 +43,8 @@ _API = [
     ("slsgp_acq_batch_device", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p, C.c_int64] + [C.c_void_p] * 6),
     ("slsgp_acq_argmax", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, c_dp, c_dp,
                                    C.POINTER(C.c_int64), c_dp]),
+    ("slsgp_acq_maximize", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, c_dp, c_dp,
+                                     c_dp, c_dp]),
     ("slsgp_argmax_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_dp, C.POINTER(C.c_int64)]),
     ("slsgp_candidates", C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, c_dp]),
     ("slsgp_set_preferences", C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int]),
@@ -216,6 +218,14 @@ class Context:
         self._check(self.lib.slsgp_acq_argmax(self.h, acq_type, ucb_beta, seed, first, count, _p(x), C.byref(val),
                                               C.byref(idx), _p(grad)))
         return x, val.value, idx.value, grad
+
+    def acq_maximize(self, acq_type, ucb_beta, seed, first, count, n_starts=1024, n_iters=40):
+        """Sweep + batched multi-start ascent on the device. Returns (x_best, value, gradient at x_best, best sweep value)."""
+        x, g = np.empty(self.D), np.empty(self.D)
+        v, vs = C.c_double(), C.c_double()
+        self._check(self.lib.slsgp_acq_maximize(self.h, acq_type, ucb_beta, seed, first, count, n_starts, n_iters, _p(x), C.byref(v),
+                                                _p(g), C.byref(vs)))
+        return x, v.value, g, vs.value
 
     def argmax_device(self, d_val, count, index0=0):
         val, idx = C.c_double(), C.c_int64()

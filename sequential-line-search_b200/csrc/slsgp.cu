@@ -15,6 +15,7 @@
 #include "gram.cuh"
 #include "map.cuh"
 #include "sweep.cuh"
+#include "maximize.cuh"
 #include "tc_sweep.cuh"
 
 #include <algorithm>
@@ -73,6 +74,7 @@ struct slsgp_ctx
 
     // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
     DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err, comb;
+    DevBuf      mx_best, mx_X, mx_Xbest, mx_Gbest, mx_state, mx_val, mx_grad; // slsgp_acq_maximize
     CUtensorMap tmA, tmB;
     int         ldt = 0, XP = 0;
     bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
@@ -691,6 +693,8 @@ namespace
         bool          host_out = false;   // outputs below are host pointers (else device pointers); any may be null
         double *      mu = nullptr, *sigma = nullptr, *dmu = nullptr, *dsigma = nullptr, *val = nullptr, *grad = nullptr;
         bool          argmax = false;     // fold every shard's values into ctx->am_acc (index = first + i)
+        long long     slice_len = 0;      // > 0: also keep the best candidate of every `slice_len` consecutive indices
+        ArgMax*       slice_best = nullptr;
     };
 
     slsgp_status run_sweep(slsgp_ctx* ctx, const SweepJob& job)
@@ -749,7 +753,7 @@ namespace
                 o.val = job.val ? job.val + m0 : nullptr, o.dmu = job.dmu ? job.dmu + (size_t) m0 * D : nullptr;
                 o.dsigma = job.dsigma ? job.dsigma + (size_t) m0 * D : nullptr, o.grad = job.grad ? job.grad + (size_t) m0 * D : nullptr;
             }
-            if (job.argmax && !o.val) o.val = dp(ctx->o_val) + (size_t) b * cap;
+            if ((job.argmax || job.slice_len > 0) && !o.val) o.val = dp(ctx->o_val) + (size_t) b * cap;
             if (tensor)
                 TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
             else
@@ -760,6 +764,13 @@ namespace
                 argmax_partial_kernel<<<nblk, 256, 0, main>>>(o.val, Mc, job.first + m0, ptr<ArgMax>(ctx->am_part));
                 LAUNCH_CHECK();
                 argmax_final_kernel<<<1, 256, 0, main>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
+                LAUNCH_CHECK();
+            }
+            if (job.slice_len > 0)
+            {
+                const long long s_lo = m0 / job.slice_len, s_hi = (m0 + Mc - 1) / job.slice_len;
+                slice_argmax_kernel<<<(unsigned) (s_hi - s_lo + 1), 256, 0, main>>>(o.val, Mc, job.first + m0, job.first, job.slice_len,
+                                                                                   s_lo, job.slice_best);
                 LAUNCH_CHECK();
             }
             CUDA_TRY(cudaEventRecord(ctx->ev_main[b], main));
@@ -858,7 +869,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb};
+                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb, &ctx->mx_best, &ctx->mx_X, &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)
@@ -1220,6 +1231,96 @@ extern "C"
         if (val_best_out) *val_best_out = best.v;
         if (index_best_out) *index_best_out = best.i;
         if (grad_best_out) TRY(slsgp_acq_batch(ctx, acq_type, ucb_beta, xb.data(), 1, nullptr, grad_best_out));
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_acq_maximize(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed, int64_t first,
+                                    int64_t count, int n_starts, int n_iters, double* x_best_out, double* val_best_out,
+                                    double* grad_best_out, double* val_sweep_best_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (count <= 0 || first < 0 || n_starts <= 0 || n_iters < 0)
+            return fail(ctx, SLSGP_ERR_INVALID, "slsgp_acq_maximize: empty candidate range or bad n_starts / n_iters");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB)
+            return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        TRY(require_model(ctx));
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const int       D         = ctx->D;
+        const long long slice_len = (count + std::min<long long>(std::min<long long>(n_starts, 16384), count) - 1) /
+                                    std::min<long long>(std::min<long long>(n_starts, 16384), count);
+        const int       K         = (int) ((count + slice_len - 1) / slice_len);
+        TRY(ensure(ctx, ctx->mx_best, sizeof(ArgMax) * (size_t) K));
+        TRY(ensure(ctx, ctx->mx_X, sizeof(double) * (size_t) K * D));
+        TRY(ensure(ctx, ctx->mx_Xbest, sizeof(double) * (size_t) K * D));
+        TRY(ensure(ctx, ctx->mx_Gbest, sizeof(double) * (size_t) K * D));
+        TRY(ensure(ctx, ctx->mx_grad, sizeof(double) * (size_t) K * D));
+        TRY(ensure(ctx, ctx->mx_val, sizeof(double) * (size_t) K));
+        TRY(ensure(ctx, ctx->mx_state, sizeof(AscentState) * (size_t) K));
+        TRY(ensure(ctx, ctx->am_acc, sizeof(ArgMax)));
+        {
+            std::vector<ArgMax> init((size_t) K);
+            for (auto& a : init) a.v = 0.0, a.i = -1;
+            CUDA_TRY(cudaMemcpyAsync(ctx->mx_best.p, init.data(), sizeof(ArgMax) * (size_t) K, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream)); // `init` is pageable and dies with this scope
+        }
+        TRY(phase_begin(ctx, "maximize"));
+        // (1) global stage: dense sweep in the caller's sweep mode, best candidate per slice
+        TRY(ensure_sweep_workspace(ctx, count));
+        {
+            SweepJob job;
+            job.acq_type = (int) acq_type, job.ucb_beta = ucb_beta, job.M = count, job.generate = true, job.seed = seed, job.first = first;
+            job.slice_len = slice_len, job.slice_best = ptr<ArgMax>(ctx->mx_best);
+            TRY(run_sweep(ctx, job));
+        }
+        starts_from_slices_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(ptr<ArgMax>(ctx->mx_best), K, D, seed, 0.05, dp(ctx->mx_X),
+                                                                           dp(ctx->mx_Xbest), ptr<AscentState>(ctx->mx_state));
+        LAUNCH_CHECK();
+        // (2) local stage in IEEE double whatever the sweep mode: n_iters + 1 evaluations, n_iters moves
+        const int    user_mode = ctx->sweep_mode;
+        slsgp_status st        = SLSGP_OK;
+        ctx->sweep_mode        = SLSGP_SWEEP_FP64;
+        if (is_tensor_mode(user_mode)) ctx->Mcap = 0;
+        st = ensure_sweep_workspace(ctx, K);
+        for (int it = 0; it <= n_iters && st == SLSGP_OK; ++it)
+        {
+            SweepJob job;
+            job.acq_type = (int) acq_type, job.ucb_beta = ucb_beta, job.M = K, job.d_Xq = dp(ctx->mx_X);
+            job.val = dp(ctx->mx_val), job.grad = dp(ctx->mx_grad);
+            st = run_sweep(ctx, job);
+            if (st != SLSGP_OK) break;
+            ascent_update_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, D, dp(ctx->mx_val), dp(ctx->mx_grad), dp(ctx->mx_X),
+                                                                          dp(ctx->mx_Xbest), dp(ctx->mx_Gbest),
+                                                                          ptr<AscentState>(ctx->mx_state), 1.6, 0.35, 0.25);
+            ++ctx->launches;
+            if (cudaGetLastError() != cudaSuccess) st = fail(ctx, SLSGP_ERR_CUDA, "ascent_update_kernel launch failed");
+        }
+        ctx->sweep_mode = user_mode;
+        if (is_tensor_mode(user_mode)) ctx->Mcap = 0;
+        TRY(st);
+        ascent_winner_kernel<<<1, 256, 0, ctx->stream>>>(ptr<AscentState>(ctx->mx_state), K, ptr<ArgMax>(ctx->am_acc));
+        LAUNCH_CHECK();
+        TRY(phase_end(ctx, "maximize"));
+        ArgMax win;
+        CUDA_TRY(cudaMemcpyAsync(&win, ctx->am_acc.p, sizeof(ArgMax), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (win.i < 0) return fail(ctx, SLSGP_ERR_NAN, "slsgp_acq_maximize: every start evaluated to NaN");
+        if (x_best_out)
+            CUDA_TRY(cudaMemcpyAsync(x_best_out, dp(ctx->mx_Xbest) + (size_t) win.i * D, sizeof(double) * D, cudaMemcpyDeviceToHost, ctx->stream));
+        if (grad_best_out)
+            CUDA_TRY(cudaMemcpyAsync(grad_best_out, dp(ctx->mx_Gbest) + (size_t) win.i * D, sizeof(double) * D, cudaMemcpyDeviceToHost, ctx->stream));
+        if (val_sweep_best_out)
+        {
+            // the best value the global stage alone found (diagnostic: what the local stage added)
+            std::vector<ArgMax> slices((size_t) K);
+            CUDA_TRY(cudaMemcpyAsync(slices.data(), ctx->mx_best.p, sizeof(ArgMax) * (size_t) K, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            double b = -INFINITY;
+            for (const auto& a : slices)
+                if (a.i >= 0 && a.v > b) b = a.v;
+            *val_sweep_best_out = b;
+        }
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (val_best_out) *val_best_out = win.v;
         return SLSGP_OK;
     }
 

@@ -142,11 +142,13 @@ namespace sequential_line_search
                 // the tensor-core sweep pays off for large candidate counts (ARD-SE kernel only); the polish is FP64
                 const bool tensor = regressor.GetKernelType() == KernelType::ArdSquaredExponentialKernel && count >= 32768 && D <= 67;
                 check(c, slsgp_set_sweep_mode(c, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), "slsgp_set_sweep_mode");
-                double       v0 = 0.0;
-                int64_t      i0 = 0;
-                slsgp_status s  = slsgp_acq_argmax(c, internal::to_abi(func_type), hyperparam, search_seed(regressor), 0, count, x0.data(), &v0, &i0, nullptr);
+                // global sweep + batched multi-start ascent, all on the device; the winner is polished below
+                double             v0 = 0.0;
+                const int          n_starts = (int) std::min<long>(1024, std::max<long>(1, count / 64));
+                const slsgp_status s = slsgp_acq_maximize(c, internal::to_abi(func_type), hyperparam, search_seed(regressor), 0, count, n_starts,
+                                                          (int) std::min(num_local_search_iters, 200u), x0.data(), &v0, nullptr, nullptr);
                 slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
-                check(c, s, "slsgp_acq_argmax");
+                check(c, s, "slsgp_acq_maximize");
             }
             else
             {

@@ -258,3 +258,30 @@ def test_numpy_candidate_generator_matches_the_library(ctx, slsb):
     ctx.set_data(X)
     for seed, first, count in ((0, 0, 100), (1234, 10**9, 257), (2**63 + 5, 3, 64)):
         np.testing.assert_array_equal(ctx.candidates(seed, first, count), slsb.sharding.candidate_coords(seed, first, count, 7))
+
+
+@pytest.mark.parametrize("kt,acq", [(S.SE, 0), (S.MATERN, 0), (S.SE, 1)])
+def test_device_maximiser_improves_on_the_sweep_and_reaches_a_stationary_point(ctx, oracle, kt, acq):
+    """slsgp_acq_maximize: sweep, best candidate per slice, batched projected ascent (FindGlobalSolution,
+    src/acquisition-function.cpp:112-167). Checked against the oracle's value / gradient at the returned point."""
+    D, N = 5, 60
+    X, theta = S.make_X(N, D), S.make_theta(D, "perturbed")
+    y = S.make_y(X)
+    ctx.fit(X, kt, theta, 0.005, y)
+    seed, first, count = 99, 0, 40000
+    _, v_sweep, _, _ = ctx.acq_argmax(acq, 1.0, seed, first, count)
+    x, v, g, v_slices = ctx.acq_maximize(acq, 1.0, seed, first, count, n_starts=256, n_iters=60)
+    assert v_slices == v_sweep                       # the slice winners contain the overall sweep winner
+    assert v >= v_sweep and np.all(x >= 0) and np.all(x <= 1)
+    m = oracle.model(kt, X, theta, 0.005, y)
+    _, f_best = oracle.f_best(m)
+    v_o, g_o = oracle.acq(m, acq, 1.0, f_best, x)
+    assert abs(v - v_o) <= 1e-9 * max(abs(v_o), 1e-30) + 1e-15
+    g0 = np.max(np.abs(ctx.acq_batch(acq, 1.0, ctx.candidates(seed, first, 256))[1]))   # gradient scale away from optima
+    np.testing.assert_allclose(g, g_o, rtol=1e-6, atol=1e-9 * g0)   # at a stationary point the gradient is all cancellation
+    # first-order optimality on the box: interior coordinates have (nearly) vanished gradients
+    pg = np.where(((x <= 0) & (g_o < 0)) | ((x >= 1) & (g_o > 0)), 0.0, g_o)
+    assert np.max(np.abs(pg)) < 0.05 * g0, (pg, g0)
+    # no iterations == the sweep winner; a split range (two GPUs) gives the same slice winners' maximum
+    x0, v0, _, _ = ctx.acq_maximize(acq, 1.0, seed, first, count, n_starts=256, n_iters=0)
+    assert v0 == v_sweep
