@@ -10,6 +10,7 @@
 #include <nlopt.hpp>
 #include <sequential-line-search/acquisition-function.hpp>
 #include <sequential-line-search/gaussian-process-regressor.hpp>
+#include <sequential-line-search/preference-data-manager.hpp>
 #include <sequential-line-search/preference-regressor.hpp>
 #include <sequential-line-search/regressor.hpp>
 #include <sequential-line-search/utils.hpp>
@@ -279,5 +280,30 @@ extern "C"
             std::memcpy(derivative, d.data(), sizeof(double) * size_t(n));
         }
         return utils::CalcBtl(fv, scale);
+    }
+    // ---- PreferenceDataManager (src/preference-data-manager.cpp:88-141, with MergeClosePoints :14-86) -------------------
+    // Same calling convention as the host facade's b200_data_manager_run.
+    int ref_data_manager_run(int D, int n_batches, const int* sizes, const double* points, double eps, double* X_out,
+                             unsigned* offsets_out, unsigned* idx_out)
+    {
+        PreferenceDataManager dm;
+        const double*         p = points;
+        for (int b = 0; b < n_batches; ++b)
+        {
+            const VectorXd        first = to_vector(p, D);
+            std::vector<VectorXd> others;
+            for (int k = 1; k < sizes[b]; ++k) others.push_back(to_vector(p + size_t(k) * D, D));
+            p += size_t(sizes[b]) * D;
+            dm.AddNewPoints(first, others, true, eps);
+        }
+        std::memcpy(X_out, dm.GetX().data(), sizeof(double) * size_t(D) * size_t(dm.GetNumDataPoints()));
+        unsigned n     = 0;
+        offsets_out[0] = 0;
+        for (size_t t = 0; t < dm.GetD().size(); ++t)
+        {
+            for (unsigned i : dm.GetD()[t]) idx_out[n++] = i;
+            offsets_out[t + 1] = n;
+        }
+        return dm.GetNumDataPoints();
     }
 }

@@ -6,7 +6,7 @@ reference's Regressor / acquisition_func interface above the C ABI) and hostlib.
 The directory name is not a Python identifier; import it with
     importlib.import_module("sequential-line-search_b200")
 """
-from .build import build, build_host, LIB_PATH, HOST_LIB_PATH  # noqa: F401
+from .build import build, build_host, build_python_module, python_module_path, LIB_PATH, LIB_DIR, HOST_LIB_PATH  # noqa: F401
 from .binding import *  # noqa: F401,F403
 from .binding import Context, SlsgpError, load_library, API_SYMBOLS  # noqa: F401
 from . import sharding  # noqa: F401

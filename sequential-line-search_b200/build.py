@@ -65,6 +65,36 @@ def build_host(force: bool = False) -> str:
     return HOST_LIB_PATH
 
 
+PY_SRC = os.path.join(PKG_DIR, "python", "pySequentialLineSearch.cpp")
+
+
+def python_module_path() -> str:
+    import sysconfig
+    return os.path.join(LIB_DIR, "pySequentialLineSearch" + sysconfig.get_config_var("EXT_SUFFIX"))
+
+
+def build_python_module(force: bool = False) -> str:
+    """Build pySequentialLineSearch (pybind11): the reference's Python module over the host layer. Import it with
+    sequential-line-search_b200/lib on sys.path."""
+    build_host()
+    out = python_module_path()
+    deps = [PY_SRC, HOST_LIB_PATH] + [os.path.join(HOST_DIR, "include", "sequential-line-search", f)
+                                      for f in os.listdir(os.path.join(HOST_DIR, "include", "sequential-line-search"))]
+    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+        return out
+    import pybind11
+    import sysconfig
+    eigen = os.environ.get("EIGEN_INC", os.path.join(os.path.dirname(PKG_DIR), "include", "eigen-lite"))
+    cmd = ["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + pybind11.get_include(), "-I" + sysconfig.get_paths()["include"],
+           "-I" + os.path.join(HOST_DIR, "include"), "-I" + eigen, "-o", out, PY_SRC, "-L" + LIB_DIR, "-lsls_b200_host", "-lslsgp",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("pySequentialLineSearch build failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
     print(build_host(force=True))
+    print(build_python_module(force=True))

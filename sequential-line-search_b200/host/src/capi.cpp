@@ -3,6 +3,8 @@
 // C++ exceptions never cross this boundary: a failing call stores the message (b200_last_error) and returns null / NaN.
 #include "device.hpp"
 
+#include <sequential-line-search/optimizers.hpp>
+
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -133,6 +135,39 @@ extern "C"
     int  b200_pref_damp_data(void* hv, const char* dir, const char* prefix)
     {
         return guarded([&]() { return static_cast<PreferenceRegressor*>(hv)->DampData(dir, prefix), 0; }, 1);
+    }
+
+    // ---- PreferenceDataManager / Slider (host bookkeeping) -------------------------------------------------------------------
+    // Feeds `n_batches` batches to AddNewPoints; batch b holds sizes[b] points (first = the preferred one), stored back to
+    // back in `points` (D doubles each). Returns the final number of points; X_out (D x N) and the tuples in CSR form.
+    int b200_data_manager_run(int D, int n_batches, const int* sizes, const double* points, double eps, double* X_out, unsigned* offsets_out,
+                              unsigned* idx_out)
+    {
+        PreferenceDataManager dm;
+        const double*         p = points;
+        for (int b = 0; b < n_batches; ++b)
+        {
+            const VectorXd        first = vector(p, D);
+            std::vector<VectorXd> others;
+            for (int k = 1; k < sizes[b]; ++k) others.push_back(vector(p + (size_t) k * D, D));
+            p += (size_t) sizes[b] * D;
+            dm.AddNewPoints(first, others, true, eps);
+        }
+        store(dm.GetX(), X_out);
+        unsigned n = 0;
+        offsets_out[0] = 0;
+        for (size_t t = 0; t < dm.GetD().size(); ++t)
+        {
+            for (unsigned i : dm.GetD()[t]) idx_out[n++] = i;
+            offsets_out[t + 1] = n;
+        }
+        return dm.GetNumDataPoints();
+    }
+    void b200_slider(int D, const double* end_0, const double* end_1, int enlarge, double scale, double minimum_length, double* out_0, double* out_1)
+    {
+        const Slider s(vector(end_0, D), vector(end_1, D), enlarge != 0, scale, minimum_length);
+        store(s.end_0, out_0);
+        store(s.end_1, out_1);
     }
 
     // ---- Regressor virtual interface ------------------------------------------------------------------------------------

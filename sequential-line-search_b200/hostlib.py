@@ -23,7 +23,7 @@ HOST_SYMBOLS = [
     "b200_pref_objective", "b200_pref_num_map_evaluations", "b200_pref_get_state", "b200_pref_find_arg_max",
     "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
-    "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points",
+    "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider",
 ]
 
 
@@ -147,6 +147,25 @@ class Host:
 
     def pref_damp_data(self, h, directory, prefix=""):
         self._ok(self.lib.b200_pref_damp_data(h, directory.encode(), prefix.encode()) == 0)
+
+    # host bookkeeping
+    def data_manager_run(self, batches, eps=1e-4):
+        """batches: list of (D x k) arrays, first column preferred. Returns (X, offsets, idx) after AddNewPoints of each."""
+        D = batches[0].shape[0]
+        sizes = np.asarray([b.shape[1] for b in batches], dtype=np.int32)
+        pts = _f64(np.concatenate([np.asarray(b, dtype=np.float64).T.reshape(-1) for b in batches]))
+        total = int(sizes.sum())
+        X = np.empty(D * total)
+        offsets, idx = np.zeros(len(batches) + 1, dtype=np.uint32), np.zeros(total, dtype=np.uint32)
+        n = self.lib.b200_data_manager_run(D, len(batches), sizes.ctypes.data_as(C.POINTER(C.c_int)), _p(pts), C.c_double(eps), _p(X),
+                                           offsets.ctypes.data_as(c_up), idx.ctypes.data_as(c_up))
+        return X[:D * n].reshape((D, n), order="F"), offsets, idx
+
+    def slider(self, end_0, end_1, enlarge=True, scale=1.25, minimum_length=0.25):
+        end_0, end_1 = _f64(end_0), _f64(end_1)
+        a, b = np.empty(len(end_0)), np.empty(len(end_0))
+        self.lib.b200_slider(len(end_0), _p(end_0), _p(end_1), int(enlarge), C.c_double(scale), C.c_double(minimum_length), _p(a), _p(b))
+        return a, b
 
     # Regressor virtuals + acquisition
     def predict(self, reg, x):

@@ -330,6 +330,18 @@ class Ref:
         d = np.empty(len(f))
         return self.lib.ref_btl(len(f), _p(f), C.c_double(scale), _p(d)), d
 
+    def data_manager_run(self, batches, eps=1e-4):
+        """PreferenceDataManager::AddNewPoints over a list of (D x k) batches (first column preferred)."""
+        D = batches[0].shape[0]
+        sizes = np.asarray([b.shape[1] for b in batches], dtype=np.int32)
+        pts = f64(np.concatenate([np.asarray(b, dtype=np.float64).T.reshape(-1) for b in batches]))
+        total = int(sizes.sum())
+        X = np.empty(D * total)
+        offsets, idx = np.zeros(len(batches) + 1, dtype=np.uint32), np.zeros(total, dtype=np.uint32)
+        n = self.lib.ref_data_manager_run(D, len(batches), sizes.ctypes.data_as(C.POINTER(C.c_int)), _p(pts), C.c_double(eps),
+                                          _p(X), _u(offsets), _u(idx))
+        return X[:D * n].reshape((D, n), order="F"), offsets, idx
+
 
 def rel_err(a, b, floor=1e-300):
     a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
