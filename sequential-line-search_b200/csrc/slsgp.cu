@@ -73,7 +73,7 @@ struct slsgp_ctx
     long long Mcap = 0;
 
     // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
-    DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err, comb;
+    DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err, comb, tc_qx, tc_P2x;
     DevBuf      mx_best, mx_X, mx_Xbest, mx_Gbest, mx_state, mx_val, mx_grad; // slsgp_acq_maximize
     CUtensorMap tmA, tmB;
     int         ldt = 0, XP = 0;
@@ -418,6 +418,11 @@ namespace
         TRY(ensure(ctx, ctx->P1, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->P2, sizeof(double) * (size_t) ctx->Dp * cap));
         TRY(ensure(ctx, ctx->stats, sizeof(double4) * (size_t) cap));
+        if (tensor)
+        {
+            TRY(ensure(ctx, ctx->tc_qx, 3 * sizeof(double2) * (size_t) cap)); // partial sums of up to 3 extra column-block groups
+            TRY(ensure(ctx, ctx->tc_P2x, 3 * sizeof(double) * (size_t) ctx->Dp * cap));
+        }
         // candidate and result staging: two shard buffers each (run_sweep)
         TRY(ensure(ctx, ctx->Xq, 2 * sizeof(double) * (size_t) ctx->D * cap));
         TRY(ensure(ctx, ctx->o_mu, 2 * sizeof(double) * cap));
@@ -535,7 +540,7 @@ namespace
             CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             attr_smem = smem;
         }
-        const int groups = prm.n_cand_blocks / NCTA;
+        const int groups = prm.n_cand_blocks / NCTA * prm.split; // work items: candidate groups x column-block halves
         const int grid   = std::min(groups, n_sm / NCTA) * NCTA;
         if (NCTA == 1)
             tc_sweep_gemm_kernel<XP, NCTA><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
@@ -558,12 +563,13 @@ namespace
         return ctx->tc_ncta == 2 ? launch_tc_gemm_n<XP, 2>(ctx, prm, n_sm) : launch_tc_gemm_n<XP, 1>(ctx, prm, n_sm);
     }
 
-    slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out)
+    slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
+                              int n_parts = 0)
     {
         ProfScope ps(ctx, "sweep_finish");
         sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
             d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
-            acq_type, ucb_beta, out);
+            acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x));
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -600,6 +606,7 @@ namespace
         __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
         static int      n_sm = 0;
         if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+        int split = 1;
         {
             ProfScope    ps(ctx, "tc_gemm");
             TcGemmParams prm;
@@ -611,6 +618,10 @@ namespace
             prm.se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
             prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2), prm.ldp = ctx->Dp;
             prm.err = ptr<int>(ctx->tc_err);
+            static const int split_env = std::getenv("SLSGP_TC_SPLIT") ? std::atoi(std::getenv("SLSGP_TC_SPLIT")) : 2;
+            prm.split = std::max(1, std::min(std::min(split_env, 4), prm.ncb));
+            prm.qx = ptr<double2>(ctx->tc_qx), prm.P2x = dp(ctx->tc_P2x), prm.part_stride = ctx->Mcap;
+            split = prm.split;
             switch (ctx->XP)
             {
                 case 8: TRY(launch_tc_gemm<8>(ctx, prm, n_sm)); break;
@@ -621,7 +632,7 @@ namespace
                 default: return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: unsupported D");
             }
         }
-        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out);
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1);
     }
 
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
@@ -869,7 +880,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb, &ctx->mx_best, &ctx->mx_X, &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
+                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb, &ctx->tc_qx, &ctx->tc_P2x, &ctx->mx_best, &ctx->mx_X, &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)

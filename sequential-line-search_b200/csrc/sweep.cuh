@@ -96,11 +96,17 @@ namespace slsgp
         sweep_finish_kernel(const double* __restrict__ Xq, int D, long long Mc, const double4* __restrict__ stats,
                             const double* __restrict__ P1, const double* __restrict__ P2, int ldp,
                             const double* __restrict__ theta, const double* __restrict__ f_best_ptr, int acq_type,
-                            double ucb_beta, SweepOut o)
+                            double ucb_beta, SweepOut o, int n_parts = 0, long long part_stride = 0,
+                            const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr)
     {
         const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (m >= Mc) return;
-        const double4 s      = stats[m];
+        double4 s = stats[m];
+        for (int h = 0; h < n_parts; ++h) // the tensor sweep split the column blocks over several CTA groups: add their partial sums
+        {
+            const double2 e = qx[(size_t) h * part_stride + m];
+            s.y += e.x, s.w += e.y;
+        }
         const double  a      = theta[0];
         const double  mu     = s.x;
         const double  sig2   = a - s.y;
@@ -134,7 +140,9 @@ namespace slsgp
             const double il2 = 1.0 / (l * l);
             const double x   = Xq[(size_t) d + (size_t) m * D];
             const double dmu = (x * s.z - P1[(size_t) d + (size_t) m * ldp]) * il2;
-            const double dsg = -(1.0 / sigma) * ((x * s.w - P2[(size_t) d + (size_t) m * ldp]) * il2);
+            double p2 = P2[(size_t) d + (size_t) m * ldp];
+            for (int h = 0; h < n_parts; ++h) p2 += P2x[(size_t) h * ldp * part_stride + (size_t) d + (size_t) m * ldp];
+            const double dsg = -(1.0 / sigma) * ((x * s.w - p2) * il2);
             if (o.dmu) o.dmu[(size_t) d + (size_t) m * D] = dmu;
             if (o.dsigma) o.dsigma[(size_t) d + (size_t) m * D] = dsg;
             if (o.grad)

@@ -238,6 +238,10 @@ namespace slsgp
         double*          P1;        // ldp x Mc
         double*          P2;
         int              ldp;
+        int              split;     // S >= 1: S CTA groups share each candidate block and take 1/S of the column blocks each
+        double2*         qx;        // S > 1: (q, gb) partials of the S - 1 groups that do not own the extras block, [S-1][part_stride]
+        double*          P2x;       // S > 1: their P2 partials, [S-1][ldp x part_stride]
+        long long        part_stride;
         int*             err;
     };
 
@@ -281,6 +285,10 @@ namespace slsgp
         const uint32_t off_a1  = TC_A_BYTES;                       // k_lo tile (passes == 3)
         const uint32_t off_b0  = TC_A_BYTES * (P == 3 ? 2 : 1);    // Kinv hi (or the extras)
         const uint32_t off_b1  = off_b0 + BH_BYTES;                // Kinv lo (passes >= 2)
+        // Work item w = candidate group (NCTA x 128 candidates) x column-block range. With split == S, S consecutive work
+        // items share the candidate rows and take 1/split of the Kinv column blocks each (the last one also the extras
+        // block): the k* rows in flight at any time shrink by that factor, so they stay L2-resident across their re-reads.
+        const int half_cb = (p.ncb + p.split - 1) / p.split;
 
         if (warp == 0 && lane == 0)
         {
@@ -320,10 +328,12 @@ namespace slsgp
             // registers); one elected lane issues. Both CTAs of a pair post their bytes on the leader's barrier. =====
             const bool elected = tc::elect_one();
             uint32_t   it = 0;
-            for (int g = cid; g < n_groups; g += ncl)
+            for (int w = cid; w < n_groups * p.split; w += ncl)
             {
+                const int g = w / p.split, h = w - g * p.split;
+                const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb : cb_end - 1;
                 const int cbk = g * NCTA + (int) rank, a_row = p.a_row0 + cbk * TC_BM;
-                for (int cb = 0; cb <= p.ncb; ++cb)
+                for (int cb = cb_begin; cb <= last; ++cb)
                 {
                     const bool     extras = cb == p.ncb;
                     const bool     two_b  = P >= 2 && !extras;
@@ -368,8 +378,11 @@ namespace slsgp
                 const bool     elected    = tc::elect_one();
                 const uint32_t idesc_full = tc::instr_desc_f16(TC_BM * NCTA, TC_BN), idesc_extra = tc::instr_desc_f16(TC_BM * NCTA, EC);
                 uint32_t       it = 0, t = 0;
-                for (int g = cid; g < n_groups; g += ncl)
-                    for (int cb = 0; cb <= p.ncb; ++cb, ++t)
+                for (int w = cid; w < n_groups * p.split; w += ncl)
+                {
+                    const int h = w % p.split;
+                    const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb : cb_end - 1;
+                    for (int cb = cb_begin; cb <= last; ++cb, ++t)
                     {
                         const bool     extras = cb == p.ncb;
                         const bool     two_b = P >= 2 && !extras, two_a = P == 3;
@@ -412,6 +425,7 @@ namespace slsgp
                             __syncwarp();
                         }
                     }
+                }
             }
         }
         else if (warp >= 4)
@@ -423,8 +437,11 @@ namespace slsgp
             // the accumulator-free barriers live in the leader CTA
             const uint32_t tempty0 = NCTA == 2 ? tc::map_to_cta(tc::smem_u32(&tempty_bar[0]), 0) : tc::smem_u32(&tempty_bar[0]);
             const uint32_t tempty1 = NCTA == 2 ? tc::map_to_cta(tc::smem_u32(&tempty_bar[1]), 0) : tc::smem_u32(&tempty_bar[1]);
-            for (int g = cid; g < n_groups; g += ncl)
+            for (int w = cid; w < n_groups * p.split; w += ncl)
             {
+                const int       g = w / p.split, h = w - g * p.split;
+                const int       cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb);
+                const bool      owns_extras = h == p.split - 1;
                 const int       cbk  = g * NCTA + (int) rank;
                 const long long m    = (long long) cbk * TC_BM + row;
                 const __half*   krow = p.Ks + (size_t) m * p.ldt;
@@ -439,9 +456,10 @@ namespace slsgp
                 const uint4* lbase = reinterpret_cast<const uint4*>(lrow);
                 uint4        kn[4], ln[4]; // software-pipelined: the k (and residual) values of the NEXT 32-column chunk
 #pragma unroll
-                for (int v = 0; v < 4; ++v) kn[v] = __ldg(kbase + v), ln[v] = lrow ? __ldg(lbase + v) : make_uint4(0, 0, 0, 0);
+                for (int v = 0; v < 4; ++v)
+                    kn[v] = __ldg(kbase + cb_begin * (TC_BN / 8) + v), ln[v] = lrow ? __ldg(lbase + cb_begin * (TC_BN / 8) + v) : make_uint4(0, 0, 0, 0);
 
-                for (int cb = 0; cb < p.ncb; ++cb, ++t)
+                for (int cb = cb_begin; cb < cb_end; ++cb, ++t)
                 {
                     const uint32_t slot = t & 1, use = t >> 1;
                     const uint32_t taddr = tmem_base + ((uint32_t) (quad * 32) << 16) + slot * TC_BN;
@@ -516,12 +534,15 @@ namespace slsgp
                 const bool   live = m < p.Mc;
                 const double c    = p.se_factor;
                 const double q    = (double) acc[0].x * (double) inv_u;
+                double*      P2o  = owns_extras ? p.P2 : p.P2x + (size_t) h * p.ldp * p.part_stride;
                 if (live)
                 {
 #pragma unroll
                     for (int d = 0; d < XP - 1; ++d)
-                        if (d < p.D) p.P2[(size_t) d + (size_t) m * p.ldp] = -c * (double) (((1 + d) & 1) ? acc[(1 + d) >> 1].y : acc[(1 + d) >> 1].x) * (double) inv_u;
+                        if (d < p.D) P2o[(size_t) d + (size_t) m * p.ldp] = -c * (double) (((1 + d) & 1) ? acc[(1 + d) >> 1].y : acc[(1 + d) >> 1].x) * (double) inv_u;
+                    if (!owns_extras) p.qx[(size_t) h * p.part_stride + m] = make_double2(q, -c * q);
                 }
+                if (!owns_extras) continue;
 
                 // extras block: column 2c = hi, 2c + 1 = lo of sum_j k_mj alpha_j (1, X_0j, ..)[c]
                 {
