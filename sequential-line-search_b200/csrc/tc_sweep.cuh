@@ -136,8 +136,8 @@ namespace slsgp
     // length-scaled coordinates in fp32 (no |q|^2 + |x|^2 - 2 q.x cancellation: near a data point sigma^2 = a - k.A.k
     // amplifies any relative error of k by a / sigma^2). The differences and their squares run on the packed FP32
     // pipe (FADD2 + FFMA2: two observations per issue slot); Xs32 holds the NEGATED observation coordinates.
-    // Tile: 64 candidates x 128 observations per CTA; thread = 4 candidates x 8 consecutive j (one 16-byte store per row).
-    // grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * DQ + D * 128) floats, DQ = round_up(D, 4).
+    // Tile: 64 candidates x 128 observations per CTA. grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * DQ + D * 128) floats,
+    // DQ = round_up(D, 4).
     __global__ void __launch_bounds__(256)
         kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
                        const float* __restrict__ Xs32, const double* __restrict__ inv_l,
@@ -158,6 +158,9 @@ namespace slsgp
         for (int e = tid; e < D * 128; e += 256) sx[e] = Xs32[(size_t) (e >> 7) * ldt + j_base + (e & 127)];
         __syncthreads();
 
+        // thread = 4 candidates (tm) x 8 observations: j = 4 tj + {0..3} and 64 + 4 tj + {0..3}, so the 16-byte operand reads
+        // of consecutive threads are consecutive in shared memory (conflict-free) and each row is written as two 8-byte
+        // pieces that coalesce into full 128-byte lines across the half-warp
         const int tj = tid & 15, tm = tid >> 4;
         float2    r2[4][4];
 #pragma unroll
@@ -174,8 +177,8 @@ namespace slsgp
             {
                 if (d0 + dd < D)
                 {
-                    const float4 xa = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + tj * 8]);
-                    const float4 xb = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + tj * 8 + 4]);
+                    const float4 xa = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + tj * 4]);
+                    const float4 xb = *reinterpret_cast<const float4*>(&sx[(d0 + dd) * 128 + 64 + tj * 4]);
                     const float2 x2[4] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w), make_float2(xb.x, xb.y), make_float2(xb.z, xb.w)};
 #pragma unroll
                     for (int i = 0; i < 4; ++i)
@@ -194,6 +197,7 @@ namespace slsgp
         }
         const float c1 = -0.72134752044448170368f; // -0.5 * log2(e)
         const float c0 = sc->c0;
+        const bool  interior = m_base + 64 <= Mc && j_base + 128 <= N; // whole tile in range: no per-value predicates
 #pragma unroll
         for (int i = 0; i < 4; ++i)
         {
@@ -202,16 +206,25 @@ namespace slsgp
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
             {
-                const int   j  = j_base + tj * 8 + 2 * jj;
-                const float v0 = (m < Mc && j < N) ? tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)) : 0.f;
-                const float v1 = (m < Mc && j + 1 < N) ? tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0)) : 0.f;
+                const int j  = j_base + (jj >> 1) * 64 + tj * 4 + (jj & 1) * 2;
+                float     v0 = tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)), v1 = tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0));
+                if (!interior)
+                {
+                    if (!(m < Mc && j < N)) v0 = 0.f;
+                    if (!(m < Mc && j + 1 < N)) v1 = 0.f;
+                }
                 h[jj]          = __floats2half2_rn(v0, v1);
                 const float2 b = __half22float2(h[jj]);
                 hl[jj]         = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)
             }
-            const size_t off = (size_t) m * ldt + j_base + tj * 8;
-            *reinterpret_cast<uint4*>(Ks + off) = *reinterpret_cast<const uint4*>(h);
-            if (Ks_lo) *reinterpret_cast<uint4*>(Ks_lo + off) = *reinterpret_cast<const uint4*>(hl);
+            const size_t off = (size_t) m * ldt + j_base + tj * 4;
+            *reinterpret_cast<uint2*>(Ks + off)      = *reinterpret_cast<const uint2*>(&h[0]);
+            *reinterpret_cast<uint2*>(Ks + off + 64) = *reinterpret_cast<const uint2*>(&h[2]);
+            if (Ks_lo)
+            {
+                *reinterpret_cast<uint2*>(Ks_lo + off)      = *reinterpret_cast<const uint2*>(&hl[0]);
+                *reinterpret_cast<uint2*>(Ks_lo + off + 64) = *reinterpret_cast<const uint2*>(&hl[2]);
+            }
         }
     }
 
