@@ -715,6 +715,7 @@ namespace
         const long long cap = ctx->Mcap, n_shards = (job.M + cap - 1) / cap;
         if (n_shards == 0) return SLSGP_OK;
         static const bool overlap = !(std::getenv("SLSGP_PIPELINE") && std::atoi(std::getenv("SLSGP_PIPELINE")) == 0);
+        static const bool kstar_overlap = std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) != 0;
         cudaStream_t main = ctx->stream, pre = overlap ? ctx->pre_stream : main, post = overlap ? ctx->post_stream : main;
         CUDA_TRY(cudaEventRecord(ctx->ev_start, main));
         CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_start, 0));
@@ -735,7 +736,9 @@ namespace
                 candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, pre>>>(job.seed, job.first + m0, Mc, D, xq);
                 LAUNCH_CHECK();
             }
-            if (tensor) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre));
+            // The k* generator can ride on `pre` too (SLSGP_KSTAR_OVERLAP=1). Default off: under the tensor load the chip is
+            // power-capped, the two kernels share one budget, and the measured step is shorter when they run back to back.
+            if (tensor && kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre));
             CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
             return SLSGP_OK;
         };
@@ -766,7 +769,10 @@ namespace
             }
             if ((job.argmax || job.slice_len > 0) && !o.val) o.val = dp(ctx->o_val) + (size_t) b * cap;
             if (tensor)
+            {
+                if (!kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, main));
                 TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
+            }
             else
                 TRY(sweep_shard(ctx, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
             if (job.argmax)
