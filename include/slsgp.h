@@ -198,6 +198,16 @@ extern "C"
                                           double default_b, double prior_var, double btl_scale, double* f_out,
                                           double* grad_out);
 
+    /* The same objective for FIXED hyper-parameters in whitened coordinates: y = L z with K_y = L L^T the factor last built
+     * by slsgp_gram + slsgp_factor, so that log N(y; 0, K_y) = -1/2 |z|^2 - 1/2 logdet - N/2 log(2 pi) and
+     *   F(z) = sum_tuples log BTL(L z) - 1/2 |z|^2 + const,     grad_z F = L^T grad_y(log BTL) - z.
+     * F(z) equals slsgp_map_objective_pref(y = L z, use_map_hyperparams = 0). The prior Hessian is the identity in z, which is
+     * what makes a quasi-Newton driver converge in tens instead of hundreds of evaluations; no K^-1 is needed.
+     * z: N; grad_z_out and y_out (= L z) may be NULL. slsgp_whiten gives z = L^-1 y for a starting point. */
+    slsgp_status slsgp_map_objective_pref_whitened(slsgp_ctx* ctx, const double* z, double btl_scale, double* f_out,
+                                                   double* grad_z_out, double* y_out);
+    slsgp_status slsgp_whiten(slsgp_ctx* ctx, const double* y, double* z_out);
+
     /* `objective` of GaussianProcessRegressor (src/gaussian-process-regressor.cpp:141-193, calc_grad :108-127, priors
      * :18-64): log marginal likelihood + fixed log-normal priors; x = (a, b, r_1..r_D); grad_out D+2 or NULL. */
     slsgp_status slsgp_map_objective_gpr(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* y,

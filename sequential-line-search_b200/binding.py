@@ -50,6 +50,8 @@ _API = [
     ("slsgp_set_preferences", C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int]),
     ("slsgp_map_objective_pref", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_int, C.c_int, C.c_double, C.c_double,
                                            C.c_double, C.c_double, C.c_double, c_dp, c_dp]),
+    ("slsgp_map_objective_pref_whitened", C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, c_dp, c_dp]),
+    ("slsgp_whiten", C.c_int, [C.c_void_p, c_dp, c_dp]),
     ("slsgp_map_objective_gpr", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
     ("slsgp_launch_count", C.c_uint64, [C.c_void_p]),
     ("slsgp_last_phase_ms", C.c_double, [C.c_void_p, C.c_char_p]),
@@ -251,6 +253,21 @@ class Context:
         self._check(self.lib.slsgp_map_objective_pref(self.h, kernel_type, _p(x), len(x), int(use_map), a, r, b,
                                                       prior_var, btl_scale, C.byref(f), _p(g)))
         return f.value, g
+
+    def map_objective_pref_whitened(self, z, btl_scale, want_grad=True):
+        """F(z), grad_z F and y = L z for the current factor (fixed hyper-parameters)."""
+        z = _f64(z)
+        f = C.c_double()
+        g = np.empty(len(z)) if want_grad else None
+        y = np.empty(len(z))
+        self._check(self.lib.slsgp_map_objective_pref_whitened(self.h, _p(z), btl_scale, C.byref(f), _p(g), _p(y)))
+        return f.value, g, y
+
+    def whiten(self, y):
+        y = _f64(y)
+        z = np.empty(len(y))
+        self._check(self.lib.slsgp_whiten(self.h, _p(y), _p(z)))
+        return z
 
     def map_objective_gpr(self, kernel_type, y, x, want_grad=True):
         y, x = _f64(y), _f64(x)

@@ -39,7 +39,7 @@ namespace slsgp
         if (i >= N) return;
         double s = 0.0;
         for (uint32_t p = slot_off[i]; p < slot_off[i + 1]; ++p) s += contrib[slot_list[p]];
-        grad_y[i] = s + -alpha[i];
+        grad_y[i] = alpha ? s + -alpha[i] : s; // alpha == null: the likelihood part alone (whitened objective)
     }
 
     // Deterministic sum of n doubles into out[0] (single block).

@@ -1504,6 +1504,76 @@ extern "C"
         return SLSGP_OK;
     }
 
+    slsgp_status slsgp_map_objective_pref_whitened(slsgp_ctx* ctx, const double* z, double btl_scale, double* f_out,
+                                                   double* grad_z_out, double* y_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "slsgp_map_objective_pref_whitened needs slsgp_gram + slsgp_factor first");
+        if (!z || !f_out) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_map_objective_pref_whitened: z / f_out null");
+        const int N = ctx->N, ld = ctx->ld;
+        double    zz = 0.0;
+        for (int i = 0; i < N; ++i)
+        {
+            if (!std::isfinite(z[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_map_objective_pref_whitened: non-finite z");
+            zz += z[i] * z[i];
+        }
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(phase_begin(ctx, "map"));
+        const int blocks = (ld * 32 + 255) / 256;
+        CUDA_TRY(cudaMemsetAsync(ctx->vec.p, 0, sizeof(double) * ld, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->vec.p, z, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        gemv_kernel<false><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->L), ld, ld, dp(ctx->vec), dp(ctx->y), 1); // y = L z
+        LAUNCH_CHECK();
+        ctx->has_alpha = false; // y changed under the cached alpha
+        double loglik = 0.0;
+        if (ctx->P > 0)
+        {
+            btl_tuple_kernel<<<(ctx->P + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->y), ptr<uint32_t>(ctx->pref_off), ptr<uint32_t>(ctx->pref_idx),
+                                                                          ctx->P, btl_scale, dp(ctx->loglik), dp(ctx->contrib), grad_z_out ? 1 : 0);
+            LAUNCH_CHECK();
+            sum_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->loglik), ctx->P, dp(ctx->scalars) + 4);
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(&loglik, dp(ctx->scalars) + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (grad_z_out)
+        {
+            CUDA_TRY(cudaMemsetAsync(ctx->grad_y.p, 0, sizeof(double) * ld, ctx->stream));
+            if (ctx->P > 0)
+            {
+                btl_gather_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->contrib), ptr<uint32_t>(ctx->slot_off),
+                                                                           ptr<uint32_t>(ctx->slot_list), nullptr, N, dp(ctx->grad_y));
+                LAUNCH_CHECK();
+            }
+            gemv_kernel<true><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->L), ld, ld, dp(ctx->grad_y), dp(ctx->Kalpha), 1); // L^T g
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(grad_z_out, ctx->Kalpha.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        if (y_out) CUDA_TRY(cudaMemcpyAsync(y_out, ctx->y.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        TRY(phase_end(ctx, "map"));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (grad_z_out)
+            for (int i = 0; i < N; ++i) grad_z_out[i] -= z[i];
+        *f_out = loglik + -0.5 * zz + -0.5 * ctx->logdet_host + -0.5 * N * std::log(2.0 * kPi);
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_whiten(slsgp_ctx* ctx, const double* y, double* z_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "slsgp_whiten needs slsgp_gram + slsgp_factor first");
+        if (!y || !z_out) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_whiten: null argument");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        TRY(do_trtri(ctx)); // W = L^-1
+        const int N = ctx->N, ld = ctx->ld, blocks = (ld * 32 + 255) / 256;
+        CUDA_TRY(cudaMemsetAsync(ctx->vec.p, 0, sizeof(double) * ld, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->vec.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+        gemv_kernel<false><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->W), ld, ld, dp(ctx->vec), dp(ctx->Kalpha), 1);
+        LAUNCH_CHECK();
+        CUDA_TRY(cudaMemcpyAsync(z_out, ctx->Kalpha.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return SLSGP_OK;
+    }
+
     slsgp_status slsgp_map_objective_gpr(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* y,
                                          const double* x, double* f_out, double* grad_out)
     {

@@ -152,6 +152,17 @@ namespace sequential_line_search
         double          m_noise_hyperparam = 0.0;
     };
 
+    // Optional starting point of a PreferenceRegressor's MAP fit (addition): the state of the regressor of the previous
+    // iteration. Goodness values are carried over to the data points that are still present (matched by coordinates);
+    // the optimum searched for is the same, it is just reached in fewer objective evaluations.
+    struct MapWarmStart
+    {
+        Eigen::MatrixXd X;                    // D x N_prev
+        Eigen::VectorXd y;                    // N_prev
+        Eigen::VectorXd kernel_hyperparams;   // D + 1 (used when hyper-parameters are estimated)
+        double          noise_hyperparam = 0.0;
+    };
+
     class PreferenceRegressor : public DeviceRegressor
     {
     public:
@@ -164,7 +175,8 @@ namespace sequential_line_search
                             const double                   kernel_hyperparams_prior_var = 0.250,
                             const double                   btl_scale                    = 0.010,
                             const unsigned                 num_map_estimation_iters     = 100,
-                            const KernelType               kernel_type = KernelType::ArdMatern52Kernel);
+                            const KernelType               kernel_type = KernelType::ArdMatern52Kernel,
+                            const MapWarmStart*            warm_start  = nullptr);
 
         const bool m_use_map_hyperparams;
 
@@ -203,7 +215,7 @@ namespace sequential_line_search
         Eigen::VectorXd m_y;
         unsigned        m_num_map_evaluations = 0;
 
-        void PerformMapEstimation(const unsigned num_iters);
+        void PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start);
     };
 
     // K_y = K_f + noise I and K_f for one of the two library kernels, built by the device Gram kernel

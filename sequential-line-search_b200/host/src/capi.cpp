@@ -108,6 +108,21 @@ extern "C"
             },
             nullptr);
     }
+    // same, warm-started from the state of a previous regressor `prev` (SequentialLineSearchOptimizer does this between iterations)
+    void* b200_pref_create_warm(const void* prev, int kt, int D, int N, const double* X, int P, const unsigned* offsets, const unsigned* idx,
+                                int use_map, double a, double r, double b, double prior_var, double btl_scale, unsigned num_iters)
+    {
+        return guarded(
+            [&]() -> void* {
+                const auto&  pr = *static_cast<const PreferenceRegressor*>(prev);
+                MapWarmStart w;
+                w.X = pr.GetLargeX(), w.y = pr.GetSmallY(), w.kernel_hyperparams = pr.GetKernelHyperparams(), w.noise_hyperparam = pr.GetNoiseHyperparam();
+                std::vector<Preference> prefs;
+                for (int t = 0; t < P; ++t) prefs.push_back(Preference(std::vector<unsigned>(idx + offsets[t], idx + offsets[t + 1])));
+                return new PreferenceRegressor(matrix(X, D, N), prefs, use_map != 0, a, r, b, prior_var, btl_scale, num_iters, kernel_type(kt), &w);
+            },
+            nullptr);
+    }
     void        b200_pref_destroy(void* h) { delete static_cast<PreferenceRegressor*>(h); }
     const void* b200_pref_regressor(void* h) { return static_cast<const Regressor*>(static_cast<PreferenceRegressor*>(h)); }
     double      b200_pref_objective(void* hv, const double* x, int n, double* grad /* may be null */)

@@ -29,7 +29,7 @@ namespace sequential_line_search
 
         inline MinimizeResult minimize_bounded(const Objective& fun, std::vector<double> x, const std::vector<double>& lo,
                                                const std::vector<double>& hi, unsigned max_evals, double gtol = 1e-8,
-                                               double ftol = 1e-13, size_t history = 12)
+                                               double ftol = 1e-15, size_t history = 12)
         {
             const size_t n = x.size();
             for (size_t i = 0; i < n; ++i) x[i] = std::min(std::max(x[i], lo[i]), hi[i]);
@@ -134,7 +134,7 @@ namespace sequential_line_search
                 }
                 flat = (f - fn <= ftol * std::max(1.0, std::fabs(f))) ? flat + 1 : 0;
                 x.swap(xn), g.swap(gn), f = fn;
-                if (flat >= 3)
+                if (flat >= 5) // the objective no longer changes in its last digits: stationary to working precision
                 {
                     res.converged = true;
                     break;

@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 using Eigen::MatrixXd;
 using Eigen::VectorXd;
@@ -87,6 +88,16 @@ namespace sequential_line_search
                     return true;
                 }
             return false;
+        }
+
+        // state of the previous regressor as the starting point of the next MAP fit
+        std::unique_ptr<MapWarmStart> warm_start_of(const std::shared_ptr<PreferenceRegressor>& r)
+        {
+            static const bool disabled = std::getenv("SLS_B200_NO_WARM_START") != nullptr; // A/B switch for timing studies
+            if (disabled || !r || r->GetSmallY().size() == 0) return nullptr;
+            std::unique_ptr<MapWarmStart> w(new MapWarmStart);
+            w->X = r->GetLargeX(), w->y = r->GetSmallY(), w->kernel_hyperparams = r->GetKernelHyperparams(), w->noise_hyperparam = r->GetNoiseHyperparam();
+            return w;
         }
     } // namespace
 
@@ -175,9 +186,10 @@ namespace sequential_line_search
         const VectorXd x_chosen = CalcPointFromSliderPosition(slider_position);
         m_data->AddNewPoints(x_chosen, {m_slider->original_end_0, m_slider->original_end_1}, true);
 
+        const std::unique_ptr<MapWarmStart> warm = warm_start_of(m_regressor);
         m_regressor = std::make_shared<PreferenceRegressor>(m_data->GetX(), m_data->GetD(), m_use_map_hyperparams, m_kernel_signal_var,
                                                             m_kernel_length_scale, m_noise_level, m_kernel_hyperparams_prior_var, m_btl_scale,
-                                                            (unsigned) num_map_estimation_iters, m_kernel_type);
+                                                            (unsigned) num_map_estimation_iters, m_kernel_type, warm.get());
 
         const VectorXd x_plus = m_current_best_selection_strategy == CurrentBestSelectionStrategy::LargestExpectValue ? m_regressor->FindArgMax() : x_chosen;
         const VectorXd x_acquisition =
@@ -284,7 +296,8 @@ namespace sequential_line_search
     {
         // default budget of the reference (:187-195): 10 (D + N)
         const int iters = num_map_estimation_iters_in > 0 ? num_map_estimation_iters_in : 10 * ((int) GetMaximizer().size() + m_data->GetNumDataPoints());
+        const std::unique_ptr<MapWarmStart> warm = warm_start_of(m_regressor);
         m_regressor     = std::make_shared<PreferenceRegressor>(m_data->GetX(), m_data->GetD(), m_use_map_hyperparams, m_kernel_signal_var, m_kernel_length_scale,
-                                                                m_noise_level, m_kernel_hyperparams_prior_var, m_btl_scale, (unsigned) iters, m_kernel_type);
+                                                                m_noise_level, m_kernel_hyperparams_prior_var, m_btl_scale, (unsigned) iters, m_kernel_type, warm.get());
     }
 } // namespace sequential_line_search

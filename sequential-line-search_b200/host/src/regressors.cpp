@@ -221,7 +221,7 @@ namespace sequential_line_search
         for (size_t s = 0; s < std::min<size_t>(3, starts.size()); ++s)
         {
             if (!std::isfinite(starts[s].first)) continue;
-            internal::MinimizeResult r = internal::minimize_bounded(neg, starts[s].second, lo, hi, 500, 1e-8);
+            internal::MinimizeResult r = internal::minimize_bounded(neg, starts[s].second, lo, hi, 500, 1e-8, 1e-13);
             if (r.f < best.f) best = r;
         }
         if (!std::isfinite(best.f)) throw std::runtime_error("GaussianProcessRegressor: MAP estimation found no admissible hyper-parameters");
@@ -239,7 +239,7 @@ namespace sequential_line_search
                                              const double default_kernel_signal_var, const double default_kernel_length_scale,
                                              const double default_noise_level, const double kernel_hyperparams_prior_var,
                                              const double btl_scale, const unsigned num_map_estimation_iters,
-                                             const KernelType kernel_type)
+                                             const KernelType kernel_type, const MapWarmStart* warm_start)
         : DeviceRegressor(kernel_type),
           m_use_map_hyperparams(use_map_hyperparams),
           m_X(X),
@@ -251,7 +251,7 @@ namespace sequential_line_search
           m_btl_scale(btl_scale)
     {
         if (X.cols() == 0 || D.size() == 0) return;
-        PerformMapEstimation(num_map_estimation_iters);
+        PerformMapEstimation(num_map_estimation_iters, warm_start);
         FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, &m_K, nullptr, &m_L);
 #ifdef SLS_B200_HOST_LLT
         m_K_llt = Eigen::LLT<MatrixXd>(m_K);
@@ -265,24 +265,41 @@ namespace sequential_line_search
         if ((int) x.size() != n) throw std::invalid_argument("MAP objective: x has the wrong length");
         if (gradient) *gradient = VectorXd::Zero(n);
         std::lock_guard<std::mutex> lock(*m_mutex);
+        slsgp_ctx*                  c = m_device.get();
         double                      f = 0.0;
-        check(m_device.get(),
-              slsgp_map_objective_pref(m_device.get(), internal::to_abi(m_kernel_type), x.data(), n, m_use_map_hyperparams ? 1 : 0,
-                                       m_default_kernel_signal_var, m_default_kernel_length_scale, m_default_noise_level,
-                                       m_kernel_hyperparams_prior_var, m_btl_scale, &f, gradient ? gradient->data() : nullptr),
-              "slsgp_map_objective_pref");
+        const slsgp_status          s = slsgp_map_objective_pref(c, internal::to_abi(m_kernel_type), x.data(), n, m_use_map_hyperparams ? 1 : 0,
+                                                                 m_default_kernel_signal_var, m_default_kernel_length_scale, m_default_noise_level,
+                                                                 m_kernel_hyperparams_prior_var, m_btl_scale, &f, gradient ? gradient->data() : nullptr);
+        // The evaluation left (y, and with use_map_hyperparams K_y and its factor) of the probe point on the device: put the
+        // fitted model back so that Predict* keep answering for (m_y, m_kernel_hyperparams, m_noise_hyperparam).
+        if (m_fitted)
+        {
+            if (m_use_map_hyperparams)
+            {
+                check(c, slsgp_gram(c, internal::to_abi(m_kernel_type), m_kernel_hyperparams.data(), m_noise_hyperparam, nullptr), "slsgp_gram");
+                check(c, slsgp_factor(c, nullptr, nullptr), "slsgp_factor");
+                check(c, slsgp_inverse(c, nullptr), "slsgp_inverse");
+            }
+            check(c, slsgp_solve_alpha(c, m_y.data(), nullptr), "slsgp_solve_alpha");
+        }
+        check(c, s, "slsgp_map_objective_pref");
         return f;
     }
 
-    // Variables, bounds and initial point as the reference (:332-403): y in [-10, 10]^N from 0; with use_map_hyperparams
-    // also (a, b, r) in [1e-8, 10] from the defaults. `num_iters` is the reference's NLopt evaluation budget for
-    // LD_TNEWTON; the driver here stops on the projected-gradient / flat-objective tests and treats 20 x num_iters
-    // as the hard cap, so a default-constructed regressor is converged rather than truncated.
-    void PreferenceRegressor::PerformMapEstimation(const unsigned num_iters)
+    // The MAP problem of the reference (:332-403): maximise F(y[, a, b, r]) = sum log BTL + log N(y; 0, K_y) [+ log-normal
+    // hyper-priors] over y in [-10, 10]^N from y = 0 and, with use_map_hyperparams, (a, b, r) in [1e-8, 10] from the defaults.
+    // The reference hands the joint vector to NLopt's LD_TNEWTON with `num_iters` evaluations. Here:
+    //   * for fixed hyper-parameters y is found in WHITENED coordinates, y = L z (slsgp_map_objective_pref_whitened): the
+    //     prior Hessian becomes the identity, the problem is strictly concave and the quasi-Newton driver converges to
+    //     |grad| <= 1e-9 in tens of evaluations, none of which rebuilds K_y;
+    //   * the hyper-parameters are an outer problem over w = log(a, b, r) on  G(w) = max_y F(y, w)  whose gradient is
+    //     dF/dw at the inner maximiser (envelope theorem), read from slsgp_map_objective_pref; each outer evaluation
+    //     rebuilds K_y once and warm-starts the inner solve from the previous y.
+    // `num_iters` bounds the OUTER evaluations (>= 60 are always allowed); the inner solves run to convergence.
+    void PreferenceRegressor::PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start)
     {
         EnsureDevice();
         const int  N = (int) m_X.cols(), D = (int) m_X.rows();
-        const int  n = m_use_map_hyperparams ? N + 2 + D : N;
         slsgp_ctx* c = m_device.get();
         const slsgp_kernel_type kt = internal::to_abi(m_kernel_type);
 
@@ -296,60 +313,122 @@ namespace sequential_line_search
             }
             offsets.push_back((uint32_t) indices.size());
         }
+        std::lock_guard<std::mutex> lock(*m_mutex);
+        check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
+        m_data_on_device = true;
+        check(c, slsgp_set_preferences(c, offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
+
+        // starting point: zeros / defaults, or the previous iteration's state for the points that are still there
+        std::vector<double> y_start((size_t) N, 0.0);
+        std::vector<double> w0 = {std::log(m_default_kernel_signal_var), std::log(m_default_noise_level)};
+        for (int i = 0; i < D; ++i) w0.push_back(std::log(m_default_kernel_length_scale));
+        bool have_start = false;
+        if (warm_start && warm_start->X.rows() == D && warm_start->y.size() == warm_start->X.cols())
         {
-            std::lock_guard<std::mutex> lock(*m_mutex);
-            check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
-            m_data_on_device = true;
-            check(c, slsgp_set_preferences(c, offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
-            if (!m_use_map_hyperparams)
+            for (int i = 0; i < N; ++i)
+                for (int j = 0; j < (int) warm_start->X.cols(); ++j)
+                {
+                    bool same = true;
+                    for (int d = 0; d < D && same; ++d) same = m_X(d, i) == warm_start->X(d, j);
+                    if (same)
+                    {
+                        y_start[(size_t) i] = warm_start->y(j), have_start = true;
+                        break;
+                    }
+                }
+            if (m_use_map_hyperparams && (int) warm_start->kernel_hyperparams.size() == D + 1 && warm_start->noise_hyperparam > 0.0)
             {
-                m_kernel_hyperparams = VectorXd::Constant(D + 1, m_default_kernel_length_scale);
-                m_kernel_hyperparams(0) = m_default_kernel_signal_var;
-                m_noise_hyperparam      = m_default_noise_level;
-                check(c, slsgp_gram(c, kt, m_kernel_hyperparams.data(), m_noise_hyperparam, nullptr), "slsgp_gram");
-                check(c, slsgp_factor(c, nullptr, nullptr), "slsgp_factor");
+                w0[0] = std::log(warm_start->kernel_hyperparams(0)), w0[1] = std::log(warm_start->noise_hyperparam);
+                for (int i = 0; i < D; ++i) w0[(size_t) 2 + i] = std::log(warm_start->kernel_hyperparams(i + 1));
             }
         }
 
-        // The goodness values y are optimised as they are; the hyper-parameters (a, b, r) through z = log(.), which
-        // keeps the joint problem well scaled (b ~ 5e-3 against y ~ 1) and maps the box [1e-8, 10] to a box.
-        std::vector<double> lo((size_t) n, -1e+01), hi((size_t) n, +1e+01), x0((size_t) n, 0.0);
-        if (m_use_map_hyperparams)
-        {
-            for (int i = N; i < n; ++i) lo[(size_t) i] = std::log(1e-08), hi[(size_t) i] = std::log(1e+01);
-            x0[(size_t) N + 0] = std::log(m_default_kernel_signal_var);
-            x0[(size_t) N + 1] = std::log(m_default_noise_level);
-            for (int i = 0; i < D; ++i) x0[(size_t) N + 2 + i] = std::log(m_default_kernel_length_scale);
-        }
-        unsigned                  evals = 0;
-        std::vector<double>       xs((size_t) n);
-        const internal::Objective neg   = [&](const std::vector<double>& z, std::vector<double>& g) {
-            std::lock_guard<std::mutex> lock(*m_mutex);
-            ++evals;
-            for (int i = 0; i < n; ++i) xs[(size_t) i] = i < N ? z[(size_t) i] : std::exp(z[(size_t) i]);
-            double             f = 0.0;
-            const slsgp_status s = slsgp_map_objective_pref(c, kt, xs.data(), n, m_use_map_hyperparams ? 1 : 0, m_default_kernel_signal_var,
-                                                            m_default_kernel_length_scale, m_default_noise_level,
-                                                            m_kernel_hyperparams_prior_var, m_btl_scale, &f, g.data());
-            if (s == SLSGP_ERR_NOT_SPD || s == SLSGP_ERR_NAN) return std::numeric_limits<double>::infinity();
-            check(c, s, "slsgp_map_objective_pref");
-            if (!std::isfinite(f)) return std::numeric_limits<double>::infinity();
-            for (int i = 0; i < n; ++i) g[(size_t) i] = i < N ? -g[(size_t) i] : -g[(size_t) i] * xs[(size_t) i];
-            return -f;
+        unsigned evals = 0;
+        // ---- inner problem: y for the hyper-parameters whose factor is current on the device. Returns F at the maximiser.
+        std::vector<double> y_cur = y_start, z((size_t) N), gz((size_t) N);
+        const auto solve_y = [&](bool from_y_cur) -> double {
+            std::vector<double> z0((size_t) N, 0.0);
+            if (from_y_cur) check(c, slsgp_whiten(c, y_cur.data(), z0.data()), "slsgp_whiten");
+            const internal::Objective neg = [&](const std::vector<double>& zz, std::vector<double>& g) {
+                ++evals;
+                double             f = 0.0;
+                const slsgp_status s = slsgp_map_objective_pref_whitened(c, zz.data(), m_btl_scale, &f, g.data(), nullptr);
+                if (s == SLSGP_ERR_NAN) return std::numeric_limits<double>::infinity();
+                check(c, s, "slsgp_map_objective_pref_whitened");
+                if (!std::isfinite(f)) return std::numeric_limits<double>::infinity(); // BTL overflow far from the optimum
+                for (auto& v : g) v = -v;
+                return -f;
+            };
+            const std::vector<double>      lo((size_t) N, -1e3), hi((size_t) N, 1e3);
+            const internal::MinimizeResult r = internal::minimize_bounded(neg, z0, lo, hi, 600, 1e-9);
+            if (!std::isfinite(r.f)) return -std::numeric_limits<double>::infinity();
+            double f = 0.0;
+            check(c, slsgp_map_objective_pref_whitened(c, r.x.data(), m_btl_scale, &f, nullptr, y_cur.data()), "slsgp_map_objective_pref_whitened");
+            for (double& v : y_cur) v = std::min(std::max(v, -1e+01), 1e+01); // the reference's box; never active in practice
+            return f;
         };
-        internal::MinimizeResult r = internal::minimize_bounded(neg, x0, lo, hi, std::max(200u, 20u * num_iters), 1e-8);
-        m_num_map_evaluations      = evals;
-        if (!std::isfinite(r.f)) throw std::runtime_error("PreferenceRegressor: the MAP objective could not be evaluated at the initial point");
-        for (int i = N; i < n; ++i) r.x[(size_t) i] = std::exp(r.x[(size_t) i]);
+        const auto build_model = [&](const std::vector<double>& w) -> bool {
+            std::vector<double> theta((size_t) D + 1);
+            theta[0] = std::exp(w[0]);
+            for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = std::exp(w[(size_t) 2 + i]);
+            check(c, slsgp_gram(c, kt, theta.data(), std::exp(w[1]), nullptr), "slsgp_gram");
+            const slsgp_status s = slsgp_factor(c, nullptr, nullptr);
+            if (s == SLSGP_ERR_NOT_SPD) return false;
+            check(c, s, "slsgp_factor");
+            return true;
+        };
+
+        std::vector<double> w_best = w0;
+        if (!m_use_map_hyperparams)
+        {
+            if (!build_model(w0)) throw std::runtime_error("PreferenceRegressor: K_y is not positive definite for the default hyper-parameters");
+            if (!std::isfinite(solve_y(have_start))) throw std::runtime_error("PreferenceRegressor: the MAP objective could not be evaluated");
+        }
+        else
+        {
+            const int           nh = D + 2;
+            std::vector<double> lo((size_t) nh, std::log(1e-08)), hi((size_t) nh, std::log(1e+01));
+            std::vector<double> x_full((size_t) N + nh), g_full((size_t) N + nh), y_at_best = y_cur;
+            double              f_best = -std::numeric_limits<double>::infinity();
+            bool                first  = true;
+            const internal::Objective outer = [&](const std::vector<double>& w, std::vector<double>& g) {
+                if (!build_model(w)) return std::numeric_limits<double>::infinity();
+                const bool   from_cur = first ? have_start : true;
+                first                 = false;
+                const double f_inner  = solve_y(from_cur);
+                if (!std::isfinite(f_inner)) return std::numeric_limits<double>::infinity();
+                for (int i = 0; i < N; ++i) x_full[(size_t) i] = y_cur[(size_t) i];
+                for (int i = 0; i < nh; ++i) x_full[(size_t) N + i] = std::exp(w[(size_t) i]);
+                ++evals;
+                double             f = 0.0;
+                const slsgp_status s = slsgp_map_objective_pref(c, kt, x_full.data(), N + nh, 1, m_default_kernel_signal_var, m_default_kernel_length_scale,
+                                                                m_default_noise_level, m_kernel_hyperparams_prior_var, m_btl_scale, &f, g_full.data());
+                if (s == SLSGP_ERR_NOT_SPD || s == SLSGP_ERR_NAN) return std::numeric_limits<double>::infinity();
+                check(c, s, "slsgp_map_objective_pref");
+                if (!std::isfinite(f)) return std::numeric_limits<double>::infinity();
+                for (int i = 0; i < nh; ++i) g[(size_t) i] = -g_full[(size_t) N + i] * x_full[(size_t) N + i]; // d/d log x
+                if (f > f_best) f_best = f, y_at_best = y_cur, w_best = w;
+                return -f;
+            };
+            for (int i = 0; i < nh; ++i) w0[(size_t) i] = std::min(std::max(w0[(size_t) i], lo[(size_t) i]), hi[(size_t) i]);
+            const internal::MinimizeResult r = internal::minimize_bounded(outer, w0, lo, hi, std::max(60u, num_iters), 1e-7, 1e-13);
+            if (!std::isfinite(f_best)) throw std::runtime_error("PreferenceRegressor: the MAP objective could not be evaluated at the initial point");
+            (void) r;
+            y_cur = y_at_best;
+        }
+        m_num_map_evaluations = evals;
 
         m_y = VectorXd::Zero(N);
-        for (int i = 0; i < N; ++i) m_y(i) = r.x[(size_t) i];
-        if (m_use_map_hyperparams)
+        for (int i = 0; i < N; ++i) m_y(i) = y_cur[(size_t) i];
+        m_kernel_hyperparams    = VectorXd::Zero(D + 1);
+        m_kernel_hyperparams(0) = std::exp(w_best[0]);
+        for (int i = 0; i < D; ++i) m_kernel_hyperparams(i + 1) = std::exp(w_best[(size_t) 2 + i]);
+        m_noise_hyperparam = std::exp(w_best[1]);
+        if (!m_use_map_hyperparams) // exact defaults, not exp(log(.))
         {
-            m_kernel_hyperparams    = VectorXd::Zero(D + 1);
-            m_kernel_hyperparams(0) = r.x[(size_t) N + 0];
-            for (int i = 0; i < D; ++i) m_kernel_hyperparams(i + 1) = r.x[(size_t) N + 2 + i];
-            m_noise_hyperparam = r.x[(size_t) N + 1];
+            m_kernel_hyperparams    = VectorXd::Constant(D + 1, m_default_kernel_length_scale);
+            m_kernel_hyperparams(0) = m_default_kernel_signal_var;
+            m_noise_hyperparam      = m_default_noise_level;
         }
     }
 

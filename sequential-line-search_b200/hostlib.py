@@ -16,10 +16,10 @@ c_up = C.POINTER(C.c_uint)
 _lib = None
 
 _DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value")
-_POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_regressor")
+_POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
 HOST_SYMBOLS = [
     "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy",
-    "b200_gpr_regressor", "b200_gpr_get_state", "b200_pref_create", "b200_pref_destroy", "b200_pref_regressor",
+    "b200_gpr_regressor", "b200_gpr_get_state", "b200_pref_create", "b200_pref_create_warm", "b200_pref_destroy", "b200_pref_regressor",
     "b200_pref_objective", "b200_pref_num_map_evaluations", "b200_pref_get_state", "b200_pref_find_arg_max",
     "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
@@ -108,10 +108,16 @@ class Host:
         return dict(K=K, Kinv=Kinv, theta=theta, b=b.value)
 
     # PreferenceRegressor
-    def pref_create(self, kt, X, offsets, idx, use_map, a, r, b, prior_var, btl_scale, num_iters=100):
+    def pref_create(self, kt, X, offsets, idx, use_map, a, r, b, prior_var, btl_scale, num_iters=100, warm_from=None):
         X = _f64(X)
         D, N = X.shape
         offsets, idx = np.ascontiguousarray(offsets, dtype=np.uint32), np.ascontiguousarray(idx, dtype=np.uint32)
+        if warm_from is not None:
+            h = self.lib.b200_pref_create_warm(warm_from, kt, D, N, _p(X), len(offsets) - 1, offsets.ctypes.data_as(c_up),
+                                               idx.ctypes.data_as(c_up), int(use_map), C.c_double(a), C.c_double(r), C.c_double(b),
+                                               C.c_double(prior_var), C.c_double(btl_scale), C.c_uint(num_iters))
+            self._ok(h)
+            return C.c_void_p(h)
         h = self.lib.b200_pref_create(kt, D, N, _p(X), len(offsets) - 1, offsets.ctypes.data_as(c_up), idx.ctypes.data_as(c_up),
                                       int(use_map), C.c_double(a), C.c_double(r), C.c_double(b), C.c_double(prior_var),
                                       C.c_double(btl_scale), C.c_uint(num_iters))

@@ -285,3 +285,26 @@ def test_device_maximiser_improves_on_the_sweep_and_reaches_a_stationary_point(c
     # no iterations == the sweep winner; a split range (two GPUs) gives the same slice winners' maximum
     x0, v0, _, _ = ctx.acq_maximize(acq, 1.0, seed, first, count, n_starts=256, n_iters=0)
     assert v0 == v_sweep
+
+
+@pytest.mark.parametrize("kt,D,N", [(S.SE, 4, 30), (S.MATERN, 8, 130)])
+def test_whitened_map_objective_is_the_same_function(ctx, kt, D, N):
+    """slsgp_map_objective_pref_whitened(z) == slsgp_map_objective_pref(y = L z, fixed hyper-parameters); its gradient is
+    L^T grad_y; slsgp_whiten inverts y = L z."""
+    X = S.make_X(N, D, "sls")
+    offsets, idx = S.make_tuples(X)
+    theta, b, btl = S.make_theta(D, "perturbed"), 0.005, 0.01
+    ctx.set_data(X)
+    ctx.gram(kt, theta, b, want=False)
+    _, L = ctx.factor(want_L=True)
+    ctx.set_preferences(offsets, idx)
+    rng = np.random.default_rng(6)
+    z = 0.05 * rng.standard_normal(N)
+    f_w, g_w, y = ctx.map_objective_pref_whitened(z, btl)
+    np.testing.assert_allclose(y, L @ z, rtol=1e-12, atol=1e-15)
+    f, g_y = ctx.map_objective_pref(kt, y, False, 0.5, 0.5, b, 0.25, btl)
+    assert abs(f_w - f) <= 1e-10 * abs(f)
+    np.testing.assert_allclose(g_w, L.T @ g_y, rtol=1e-7, atol=1e-9 * np.max(np.abs(g_w)))
+    np.testing.assert_allclose(ctx.whiten(y), z, rtol=1e-8, atol=1e-12)
+    f_only, g_none, _ = ctx.map_objective_pref_whitened(z, btl, want_grad=False)
+    assert f_only == f_w and g_none is None
