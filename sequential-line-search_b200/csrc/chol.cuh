@@ -21,12 +21,24 @@
 #pragma once
 
 #include "common.cuh"
-#include "gram.cuh" // lower_tile
+#include "dense.cuh" // dmma_8x8x4
+#include "gram.cuh"  // lower_tile
 
 namespace slsgp
 {
-    constexpr int CHOL_LDS        = TILE + 2; // shared-memory leading dimension (even: keeps rows 16-byte aligned)
+    constexpr int CHOL_LDS        = TILE + 4; // shared-memory leading dimension: rows 16-byte aligned, DMMA fragment reads conflict-free
     constexpr int CHOL_SMEM_BYTES = 2 * TILE * CHOL_LDS * (int) sizeof(double);
+
+    // 1 / d to double precision without the IEEE-division sequence: MUFU seed (about 20 bits) + two Newton steps. The pivot
+    // loop below waits on this once per column, 64 columns per launch, 32 launches in a row at N = 2048.
+    __device__ __forceinline__ double fast_reciprocal(double d)
+    {
+        double x;
+        asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+        x = fma(x, fma(-d, x, 1.0), x);
+        x = fma(x, fma(-d, x, 1.0), x);
+        return x;
+    }
 
     // Cholesky + inverse of a 64 x 64 SPD tile held in REGISTERS, c[i][q] = S[tx + 16 i][ty + 16 q], lower triangle =
     // the tile, strict upper triangle = 0.
@@ -70,7 +82,7 @@ namespace slsgp
                     }
                 }
                 __syncthreads();
-                const double inv_d = 1.0 / col[TILE];
+                const double inv_d = fast_reciprocal(col[TILE]);
                 double       rowv[4], colv[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) rowv[i] = col[tx + 16 * i] * inv_d;
@@ -95,22 +107,25 @@ namespace slsgp
         __syncthreads();
     }
 
-    // acc[i][j] += sum_k As[k][tx + 16 i] * Bs[k][ty + 16 j], k in [0, 64).
-    __device__ __forceinline__ void tile_mma_64(double (*As)[CHOL_LDS], double (*Bs)[CHOL_LDS], int tx, int ty,
-                                                double acc[4][4])
+    // acc += As^T Bs over k in [0, 64) on the FP64 tensor pipe: As[k][m], Bs[k][n]; warp w owns the 32 (m) x 16 (n) block at
+    // (wm, wn) = ((w & 1) * 32, (w >> 1) * 16) as 4 x 2 DMMA tiles; acc[i][j][h] = element (wm + 8 i + lane / 4,
+    // wn + 8 j + 2 (lane % 4) + h).
+    __device__ __forceinline__ void tile_dmma_64(double (*As)[CHOL_LDS], double (*Bs)[CHOL_LDS], int wm, int wn, int lane,
+                                                 double acc[4][2][2])
     {
-#pragma unroll 8
-        for (int kk = 0; kk < TILE; ++kk)
+        const int lr = lane >> 2, lc = lane & 3;
+#pragma unroll 4
+        for (int ks = 0; ks < TILE; ks += 4)
         {
-            double a[4], b[4];
+            double a[4], b[2];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+            for (int i = 0; i < 4; ++i) a[i] = As[ks + lc][wm + i * 8 + lr];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+            for (int j = 0; j < 2; ++j) b[j] = Bs[ks + lc][wn + j * 8 + lr];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
 
@@ -154,6 +169,37 @@ namespace slsgp
         }
         double* Ct = L + (size_t) tm * TILE + (size_t) tn * TILE * ld;
 
+        const int warp = tid >> 5, lane = tid & 31, wm = (warp & 1) * 32, wn = (warp >> 1) * 16, lr = lane >> 2, lc = lane & 3;
+        double    upd[4][2][2]; // L[tm,k] L[tn,k]^T in DMMA fragment layout
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) upd[i][j][0] = upd[i][j][1] = 0.0;
+
+        if (t >= rem) // plain trailing tile: C -= update, read and written in fragment layout
+        {
+            double cf[4][2][2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) cf[i][j][h] = Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wn + j * 8 + lc * 2 + h) * ld];
+            load_tile_64(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            load_tile_64(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            __syncthreads();
+            tile_dmma_64(As, Bs, wm, wn, lane, upd);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 2; ++j)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wn + j * 8 + lc * 2 + h) * ld] = cf[i][j][h] - upd[i][j][h];
+            return;
+        }
+
+        // tiles of the next block column: the register-resident factorisation wants the interleaved layout
         double c[4][4]; // the tile itself first (independent of the operand loads), then tile - update
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -164,25 +210,19 @@ namespace slsgp
             load_tile_64(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid, false);
             load_tile_64(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid, false);
             __syncthreads();
-            double acc[4][4];
+            tile_dmma_64(As, Bs, wm, wn, lane, upd);
+            __syncthreads(); // operands consumed: As becomes the re-layout buffer, As[n][m] = update(m, n)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-            tile_mma_64(As, Bs, tx, ty, acc);
+                for (int j = 0; j < 2; ++j)
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) c[i][j] -= acc[i][j];
-        }
-
-        if (t >= rem) // plain trailing tile
-        {
+                    for (int h = 0; h < 2; ++h) As[wn + j * 8 + lc * 2 + h][wm + i * 8 + lr] = upd[i][j][h];
+            __syncthreads();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-                for (int i = 0; i < 4; ++i) Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld] = c[i][j];
-            return;
+                for (int i = 0; i < 4; ++i) c[i][j] -= As[ty + 16 * j][tx + 16 * i];
         }
 
         __syncthreads(); // everyone is done reading As / Bs
@@ -245,15 +285,17 @@ namespace slsgp
         // Bs[n][cc] = W(cc, n): W is column-major, so row n of Bs is column n of W
         load_tile_64(Bs, W + (size_t) tn * TILE * ((size_t) ld + 1), ld, tid, true);
         __syncthreads();
-        double acc[4][4];
+        double acc[4][2][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
-        tile_mma_64(As, Bs, tx, ty, acc);
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        tile_dmma_64(As, Bs, wm, wn, lane, acc);
 #pragma unroll
-        for (int j = 0; j < 4; ++j)
+        for (int i = 0; i < 4; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld] = acc[i][j];
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wn + j * 8 + lc * 2 + h) * ld] = acc[i][j][h];
     }
 } // namespace slsgp

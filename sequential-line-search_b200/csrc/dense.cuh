@@ -116,6 +116,114 @@ namespace slsgp
             }
     }
 
+    // D (8x8) += A (8x4, row) * B (4x8, col) in IEEE double on the FP64 tensor pipe (DMMA). Per lane: a = A[lane/4][lane%4],
+    // b = B[lane%4][lane/4], c0/c1 = C[lane/4][2*(lane%4) + {0,1}].
+    __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b)
+    {
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+    }
+
+    // Same contract as gemm64_kernel (64 x 64 output tile per CTA, the triangular k-range pruning, batching, in-place
+    // panel updates), with the inner product on the FP64 tensor pipe: 8 warps, warp = 32 (m) x 16 (n) = 4 x 2 DMMA tiles,
+    // 16-deep shared-memory stages (row stride 68 doubles: the fragment reads of a half-warp hit 16 distinct 8-byte
+    // slots), the next stage's global loads issued into registers before the current stage is multiplied.
+    constexpr int DMMA_LDS = TILE + 4;
+    template <bool TA, bool TB> __global__ void __launch_bounds__(256) gemm64_dmma_kernel(const GemmArgs g)
+    {
+        const int tm = blockIdx.x, tn = blockIdx.y, z = blockIdx.z;
+        if (g.lower_only && tn > tm) return;
+        if (g.row0 + z * g.row_step + tm * TILE >= g.row_limit) return;
+
+        const double* __restrict__ A = g.A + z * g.sA;
+        const double* __restrict__ B = g.B + z * g.sB;
+        double* C                    = g.C + z * g.sC; // may alias A (in-place panel update)
+
+        int k_lo = 0, k_hi = g.k;
+        if (g.k_lo_mode == 1) k_lo = tn * TILE;
+        if (g.k_lo_mode == 2) k_lo = max(tm, tn) * TILE;
+        if (g.k_hi_mode == 1) k_hi = min(g.k, (tm + 1) * TILE);
+
+        __shared__ double As[16][DMMA_LDS]; // As[k][m]
+        __shared__ double Bs[16][DMMA_LDS]; // Bs[k][n]
+
+        const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+        const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16; // this warp's corner inside the tile
+        const int lr = lane >> 2, lc = lane & 3;
+        double    acc[4][2][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        double ra[4], rb[4];
+        const auto fetch = [&](int k0) {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const int e = tid + r * 256;
+                if (!TA)
+                    ra[r] = A[(size_t) (tm * TILE + (e & 63)) + (size_t) (k0 + (e >> 6)) * g.lda];
+                else
+                    ra[r] = A[(size_t) (k0 + (e & 15)) + (size_t) (tm * TILE + (e >> 4)) * g.lda];
+                if (!TB)
+                    rb[r] = B[(size_t) (k0 + (e & 15)) + (size_t) (tn * TILE + (e >> 4)) * g.ldb];
+                else
+                    rb[r] = B[(size_t) (tn * TILE + (e & 63)) + (size_t) (k0 + (e >> 6)) * g.ldb];
+            }
+        };
+        const auto stash = [&]() {
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+            {
+                const int e = tid + r * 256;
+                if (!TA)
+                    As[e >> 6][e & 63] = ra[r];
+                else
+                    As[e & 15][e >> 4] = ra[r];
+                if (!TB)
+                    Bs[e & 15][e >> 4] = rb[r];
+                else
+                    Bs[e >> 6][e & 63] = rb[r];
+            }
+        };
+
+        if (k_lo < k_hi) fetch(k_lo);
+        for (int k0 = k_lo; k0 < k_hi; k0 += 16)
+        {
+            stash();
+            __syncthreads();
+            if (k0 + 16 < k_hi) fetch(k0 + 16); // in flight while this stage is multiplied
+#pragma unroll
+            for (int ks = 0; ks < 16; ks += 4)
+            {
+                double a[4], b[2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = As[ks + lc][wm + i * 8 + lr];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) b[j] = Bs[ks + lc][wn + j * 8 + lr];
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+            }
+            __syncthreads();
+        }
+
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                {
+                    const int    m = tm * TILE + wm + i * 8 + lr, n = tn * TILE + wn + j * 8 + lc * 2 + h;
+                    const size_t idx = (size_t) m + (size_t) n * g.ldc;
+                    double       v   = g.alpha * acc[i][j][h];
+                    if (g.beta != 0.0) v += g.beta * C[idx];
+                    C[idx] = v;
+                }
+    }
+
     // Cholesky of one 64 x 64 diagonal block (in place, lower; the strict upper part of the block is zeroed) and
     // its inverse W = L^-1 (lower) written to Wd. info[0] receives 1 + global index of the first bad pivot.
     //

@@ -210,7 +210,11 @@ namespace
     template <bool TA, bool TB> slsgp_status launch_gemm(slsgp_ctx* ctx, const GemmArgs& g, int batch = 1)
     {
         dim3 grid(g.m / TILE, g.n / TILE, batch);
-        gemm64_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g);
+        static const bool simt = std::getenv("SLSGP_FP64_GEMM") && std::string(std::getenv("SLSGP_FP64_GEMM")) == "simt";
+        if (simt)
+            gemm64_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g);      // DFMA reference implementation
+        else
+            gemm64_dmma_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g); // FP64 tensor pipe (mma.sync m8n8k4)
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
