@@ -58,3 +58,31 @@ def all_gather_winner(value: float, index: int, device=None, group=None) -> tupl
     out = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
     dist.all_gather(out, mine, group=group)
     return select_winner(torch.stack(out).cpu().numpy())
+
+
+def select_best_point(values, points) -> tuple[float, np.ndarray, int]:
+    """values: (world,), points: (world, D): the refined maximiser of every rank (slsgp_acq_maximize on its own candidate
+    range). Highest value wins, the lowest rank breaks ties, NaN never wins. Returns (value, point, winning rank)."""
+    values = np.asarray(values, dtype=np.float64).reshape(-1)
+    points = np.asarray(points, dtype=np.float64).reshape(len(values), -1)
+    ok = ~np.isnan(values)
+    if not ok.any():
+        raise ValueError("select_best_point: every rank reported NaN")
+    r = int(np.flatnonzero(ok)[np.argmax(values[ok])])  # argmax returns the first (lowest-rank) maximum
+    return float(values[r]), points[r].copy(), r
+
+
+def all_gather_best_point(value: float, point, device=None, group=None) -> tuple[float, np.ndarray, int]:
+    """Multi-GPU form of slsgp_acq_maximize: every rank contributes (value, x) of its local maximiser, 8 (1 + D) bytes;
+    every rank returns the same global one."""
+    import torch
+    import torch.distributed as dist
+
+    point = np.asarray(point, dtype=np.float64).reshape(-1)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return select_best_point([value], [point])
+    mine = torch.tensor(np.concatenate([[value], point]), dtype=torch.float64, device=device)
+    out = [torch.empty_like(mine) for _ in range(dist.get_world_size(group))]
+    dist.all_gather(out, mine, group=group)
+    allv = torch.stack(out).cpu().numpy()
+    return select_best_point(allv[:, 0], allv[:, 1:])

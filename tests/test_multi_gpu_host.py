@@ -93,3 +93,30 @@ def test_sharded_argmax_equals_single_process(world, total):
     assert len(out) == world
     for r in range(world):
         assert out[r] == want, (r, out[r], want)
+
+
+def test_select_best_point_rules():
+    v, x, r = sharding.select_best_point([0.1, 0.7, 0.7], [[0, 0], [1, 1], [2, 2]])
+    assert (v, r) == (0.7, 1) and np.array_equal(x, [1.0, 1.0])                  # tie -> lowest rank
+    v, x, r = sharding.select_best_point([float("nan"), 0.2], [[0, 0], [3, 4]])
+    assert (v, r) == (0.2, 1) and np.array_equal(x, [3.0, 4.0])                  # NaN never wins
+    with pytest.raises(ValueError):
+        sharding.select_best_point([float("nan")], [[0.0]])
+
+
+def _point_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank "maximised" its own range: rank r found value r / 10 at the point (r, r + 0.5, r + 1)
+    out[rank] = sharding.all_gather_best_point(rank / 10.0, np.array([rank, rank + 0.5, rank + 1.0]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_all_gather_best_point_world_2():
+    out = mp.get_context("spawn").Manager().dict()
+    mp.spawn(_point_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in range(2):
+        v, x, w = out[r]
+        assert v == 0.1 and w == 1 and np.array_equal(x, [1.0, 1.5, 2.0])
