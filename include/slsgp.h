@@ -62,7 +62,8 @@ extern "C"
     typedef enum
     {
         SLSGP_SWEEP_FP64      = 0, /* IEEE double throughout; parity 1e-5 relative (north_star "FP64") */
-        /* fp16 operands on the tcgen05 tensor pipe, fp32 accumulation in TMEM (ARD squared-exponential kernel, D <= 67).
+        /* fp16 operands on the tcgen05 tensor pipe, fp32 accumulation in TMEM (both library kernels; D <= 67, 66 for Matern,
+         * whose gradient weight travels as a second fp16 operand).
          * K^-1 and k* are each split into two fp16 terms; the contraction is evaluated as
          *   TENSOR     k16.A16 + k16.A_lo + k_lo.A16   fp32-class result, parity 1e-3 on every test distribution
          *   TENSOR_X2  k16.A16 + k16.A_lo              sigma / EI value fp32-class, gradients limited by k16 (~2e-3)

@@ -405,10 +405,10 @@ namespace
         cap           = round_up64(cap, tensor ? TC_BM * ctx->tc_ncta : TILE);
         if (tensor && ctx->tc_Mcap < cap)
         {
-            // two shard buffers (the k* of shard s + 1 is generated while shard s is contracted), each: rows [0, cap)
-            // k16, rows [cap, 2 cap) its fp16 rounding residual (read only by the split-precision passes)
-            TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 4 * (size_t) cap * ctx->ldt));
-            TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 4 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
+            // two shard buffers, each: rows [0, cap) k16, [cap, 2 cap) its fp16 rounding residual (read only by the split-precision
+            // passes), [2 cap, 3 cap) / [3 cap, 4 cap) the Matern gradient weight g16 and its residual
+            TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 8 * (size_t) cap * ctx->ldt));
+            TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 8 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
             ctx->tc_Mcap = cap;
         }
         if (ctx->Mcap >= cap) return SLSGP_OK;
@@ -487,10 +487,10 @@ namespace
     slsgp_status prepare_tensor(slsgp_ctx* ctx)
     {
         if (ctx->tc_ready) return SLSGP_OK;
-        if (ctx->kernel_type != SLSGP_KERNEL_ARD_SQUARED_EXP)
-            return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR supports the ARD squared-exponential kernel only");
-        const int XP = tc_xp(ctx->D);
-        if (!XP) return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR supports D <= 67");
+        const bool matern = ctx->kernel_type == SLSGP_KERNEL_ARD_MATERN52;
+        if (matern && ctx->tc_ncta != 2) return fail(ctx, SLSGP_ERR_INVALID, "the Matern tensor sweep needs the CTA-pair kernel (SLSGP_TC_PAIR=1)");
+        const int XP = tc_xp(ctx->D + (matern ? 1 : 0)); // Matern carries one more reduction column (gb = sum g_i u_i)
+        if (!XP) return fail(ctx, SLSGP_ERR_INVALID, "SLSGP_SWEEP_TENSOR supports D <= 67 (66 for the Matern kernel)");
         const int ldt = round_up(ctx->N, TC_BN);
         ctx->XP = XP, ctx->ldt = ldt;
         const size_t brows = 2 * (size_t) ldt + TC_BN;
@@ -510,7 +510,7 @@ namespace
             dp(ctx->Kinv), ctx->ld, ctx->N, ctx->D, XP, ldt, dp(ctx->alpha), dp(ctx->X), ptr<TcScales>(ctx->tcs),
             ptr<__half>(ctx->Bmat));
         LAUNCH_CHECK();
-        tc_pack_x_kernel<<<(ldt + 255) / 256, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, XP, ldt, dp(ctx->inv_l),
+        tc_pack_x_kernel<<<(ldt + 255) / 256, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, XP, ldt, dp(ctx->inv_l), matern ? 2 : 1,
                                                                     ptr<float>(ctx->Xt), ptr<float>(ctx->Xs32));
         LAUNCH_CHECK();
         TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN / ctx->tc_ncta));
@@ -530,7 +530,7 @@ namespace
         return cap;
     }
 
-    template <int XP, int NCTA> slsgp_status launch_tc_gemm_n(slsgp_ctx* ctx, const TcGemmParams& prm_in, int n_sm)
+    template <int XP, int NCTA, bool MATERN> slsgp_status launch_tc_gemm_n(slsgp_ctx* ctx, const TcGemmParams& prm_in, int n_sm)
     {
         TcGemmParams prm   = prm_in;
         const size_t fixed = (size_t) tc_xs_cols(XP) * XP * sizeof(float) + 1024;
@@ -541,13 +541,13 @@ namespace
         static size_t attr_smem = 0;
         if (attr_smem < smem)
         {
-            CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP, NCTA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+            CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP, NCTA, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
             attr_smem = smem;
         }
         const int groups = prm.n_cand_blocks / NCTA * prm.split; // work items: candidate groups x column-block halves
         const int grid   = std::min(groups, n_sm / NCTA) * NCTA;
         if (NCTA == 1)
-            tc_sweep_gemm_kernel<XP, NCTA><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
+            tc_sweep_gemm_kernel<XP, NCTA, MATERN><<<grid, TC_THREADS, smem, ctx->stream>>>(ctx->tmA, ctx->tmB, prm);
         else
         {
             cudaLaunchConfig_t  cfg = {};
@@ -556,7 +556,7 @@ namespace
             attr[0].id               = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = NCTA, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr, cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_sweep_gemm_kernel<XP, NCTA>, ctx->tmA, ctx->tmB, prm));
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, tc_sweep_gemm_kernel<XP, NCTA, MATERN>, ctx->tmA, ctx->tmB, prm));
         }
         LAUNCH_CHECK();
         return SLSGP_OK;
@@ -564,16 +564,17 @@ namespace
 
     template <int XP> slsgp_status launch_tc_gemm(slsgp_ctx* ctx, const TcGemmParams& prm, int n_sm)
     {
-        return ctx->tc_ncta == 2 ? launch_tc_gemm_n<XP, 2>(ctx, prm, n_sm) : launch_tc_gemm_n<XP, 1>(ctx, prm, n_sm);
+        if (prm.matern) return launch_tc_gemm_n<XP, 2, true>(ctx, prm, n_sm); // CTA-pair kernel only (prepare_tensor checks)
+        return ctx->tc_ncta == 2 ? launch_tc_gemm_n<XP, 2, false>(ctx, prm, n_sm) : launch_tc_gemm_n<XP, 1, false>(ctx, prm, n_sm);
     }
 
     slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
-                              int n_parts = 0)
+                              int n_parts = 0, double x_shift = 0.0)
     {
         ProfScope ps(ctx, "sweep_finish");
         sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
             d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
-            acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x));
+            acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x), x_shift);
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -583,8 +584,10 @@ namespace
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
-        __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) buf * 2 * ctx->tc_Mcap * ldt;
+        __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) buf * 4 * ctx->tc_Mcap * ldt;
         __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
+        __half*         Gs    = Ks + (size_t) 2 * ctx->tc_Mcap * ldt; // Matern only
+        __half*         Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
         ProfScope       ps(ctx, "tc_kstar", st);
         const size_t    smem = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + D * 128);
         static bool     kstar_attr = false;
@@ -595,7 +598,7 @@ namespace
             kstar_attr = true;
         }
         kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, st>>>(
-            d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo);
+            d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo, ctx->kernel_type, Gs, Gs_lo);
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -605,7 +608,7 @@ namespace
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
-        const long long row0 = (long long) buf * 2 * ctx->tc_Mcap;
+        const long long row0 = (long long) buf * 4 * ctx->tc_Mcap;
         __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) row0 * ldt;
         __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
         static int      n_sm = 0;
@@ -618,6 +621,8 @@ namespace
             prm.stage_bytes = 0;
             prm.n_cand_blocks = (int) (Mpad / TC_BM), prm.Mc = Mc, prm.a_row0 = (int) row0;
             prm.passes = passes, prm.a_lo_row = (int) ctx->tc_Mcap, prm.b_lo_row = ldt + TC_BN, prm.Ks_lo = Ks_lo;
+            prm.matern = ctx->kernel_type == SLSGP_KERNEL_ARD_MATERN52, prm.g_row = (int) (2 * ctx->tc_Mcap);
+            prm.Gs = Ks + (size_t) 2 * ctx->tc_Mcap * ldt, prm.Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
             prm.Ks = Ks, prm.Xt = ptr<float>(ctx->Xt), prm.sc = ptr<TcScales>(ctx->tcs);
             prm.se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
             prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2), prm.ldp = ctx->Dp;
@@ -636,7 +641,7 @@ namespace
                 default: return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: unsupported D");
             }
         }
-        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1);
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1, 0.5);
     }
 
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,

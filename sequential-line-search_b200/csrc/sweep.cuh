@@ -97,7 +97,7 @@ namespace slsgp
                             const double* __restrict__ P1, const double* __restrict__ P2, int ldp,
                             const double* __restrict__ theta, const double* __restrict__ f_best_ptr, int acq_type,
                             double ucb_beta, SweepOut o, int n_parts = 0, long long part_stride = 0,
-                            const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr)
+                            const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr, double x_shift = 0.0)
     {
         const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (m >= Mc) return;
@@ -138,7 +138,7 @@ namespace slsgp
         {
             const double l   = theta[1 + d];
             const double il2 = 1.0 / (l * l);
-            const double x   = Xq[(size_t) d + (size_t) m * D];
+            const double x   = Xq[(size_t) d + (size_t) m * D] - x_shift; // P1 / P2 were accumulated against X - x_shift
             const double dmu = (x * s.z - P1[(size_t) d + (size_t) m * ldp]) * il2;
             double p2 = P2[(size_t) d + (size_t) m * ldp];
             for (int h = 0; h < n_parts; ++h) p2 += P2x[(size_t) h * ldp * part_stride + (size_t) d + (size_t) m * ldp];

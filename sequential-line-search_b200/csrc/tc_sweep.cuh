@@ -105,7 +105,7 @@ namespace slsgp
             const int e = i - ldt, c = e >> 1;
             if (c <= D)
             {
-                const double xhat = c == 0 ? 1.0 : X[(size_t) (c - 1) + (size_t) j * D];
+                const double xhat = c == 0 ? 1.0 : X[(size_t) (c - 1) + (size_t) j * D] - 0.5; // centred, as Xt
                 const float  full = (float) (alpha[j] * xhat * (double) sc->sE);
                 const float  hi   = __half2float(__float2half_rn(full));
                 v                 = (e & 1) ? full - hi : hi;
@@ -117,15 +117,18 @@ namespace slsgp
     // Xt[i][c] = (1, X_0i, .., X_{D-1}i, 0..) in fp32 for the epilogue; Xs32[d][j] = -(X_dj - 1/2) / l_d (negated: kstar16
     // forms q - x with a packed add).
     __global__ void __launch_bounds__(256)
-        tc_pack_x_kernel(const double* __restrict__ X, int N, int D, int XP, int ldt, const double* __restrict__ inv_l,
+        tc_pack_x_kernel(const double* __restrict__ X, int N, int D, int XP, int ldt, const double* __restrict__ inv_l, int n_ones,
                          float* __restrict__ Xt, float* __restrict__ Xs32)
     {
+        // Xt columns: n_ones ones (SE: 1, the q column; Matern: 2, q and gb = sum g_i u_i), then X_0i - 1/2 .. X_{D-1}i - 1/2, then
+        // zeros. Centring on the box centre halves |X| and with it the fp32 cancellation error of (x_d gb - P2_d) near data points;
+        // sweep_finish_kernel applies the same shift to the candidate (x_shift).
         const int i = blockIdx.x * 256 + threadIdx.x;
         if (i >= ldt) return;
         for (int c = 0; c < XP; ++c)
         {
             float v = 0.f;
-            if (i < N) v = c == 0 ? 1.f : (c <= D ? (float) X[(size_t) (c - 1) + (size_t) i * D] : 0.f);
+            if (i < N) v = c < n_ones ? 1.f : (c < n_ones + D ? (float) (X[(size_t) (c - n_ones) + (size_t) i * D] - 0.5) : 0.f);
             Xt[(size_t) i * XP + c] = v;
         }
         for (int d = 0; d < D; ++d)
@@ -141,7 +144,8 @@ namespace slsgp
     __global__ void __launch_bounds__(256)
         kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
                        const float* __restrict__ Xs32, const double* __restrict__ inv_l,
-                       const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo)
+                       const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo, int kernel_type,
+                       __half* __restrict__ Gs, __half* __restrict__ Gs_lo)
     {
         extern __shared__ __align__(16) float ksm[];
         const int               DQ = (D + 3) & ~3; // row stride of sq: 16-byte aligned rows
@@ -202,20 +206,38 @@ namespace slsgp
         for (int i = 0; i < 4; ++i)
         {
             const long long m = m_base + tm * 4 + i;
-            __half2         h[4], hl[4];
+            __half2         h[4], hl[4], gh[4], gl[4];
 #pragma unroll
             for (int jj = 0; jj < 4; ++jj)
             {
-                const int j  = j_base + (jj >> 1) * 64 + tj * 4 + (jj & 1) * 2;
-                float     v0 = tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)), v1 = tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0));
+                const int j = j_base + (jj >> 1) * 64 + tj * 4 + (jj & 1) * 2;
+                float     v0, v1, g0 = 0.f, g1 = 0.f;
+                if (kernel_type == 0)
+                    v0 = tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)), v1 = tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0));
+                else
+                {
+                    // Matern 5/2 (kernel-functions.cpp:95-112, :179-212): s = sqrt(5) r, k = a (1 + s + s^2/3) e^-s and the
+                    // x-gradient weight g = -(5/3) a (1 + s) e^-s (so that dk/dx_d = g (x_d - X_d) / l_d^2); both scaled by sK
+                    const float s0 = sqrtf(5.f * r2[i][jj].x), s1 = sqrtf(5.f * r2[i][jj].y);
+                    const float e0 = tc::ex2_approx(fmaf(s0, -1.44269504088896340736f, c0));
+                    const float e1 = tc::ex2_approx(fmaf(s1, -1.44269504088896340736f, c0));
+                    v0 = e0 * fmaf(s0, fmaf(s0, 0.33333333333333333f, 1.f), 1.f), v1 = e1 * fmaf(s1, fmaf(s1, 0.33333333333333333f, 1.f), 1.f);
+                    g0 = -1.66666666666666667f * e0 * (1.f + s0), g1 = -1.66666666666666667f * e1 * (1.f + s1);
+                }
                 if (!interior)
                 {
-                    if (!(m < Mc && j < N)) v0 = 0.f;
-                    if (!(m < Mc && j + 1 < N)) v1 = 0.f;
+                    if (!(m < Mc && j < N)) v0 = 0.f, g0 = 0.f;
+                    if (!(m < Mc && j + 1 < N)) v1 = 0.f, g1 = 0.f;
                 }
                 h[jj]          = __floats2half2_rn(v0, v1);
                 const float2 b = __half22float2(h[jj]);
                 hl[jj]         = __floats2half2_rn(v0 - b.x, v1 - b.y); // rounding residual (second fp16 term)
+                if (kernel_type != 0)
+                {
+                    gh[jj]         = __floats2half2_rn(g0, g1);
+                    const float2 c = __half22float2(gh[jj]);
+                    gl[jj]         = __floats2half2_rn(g0 - c.x, g1 - c.y);
+                }
             }
             const size_t off = (size_t) m * ldt + j_base + tj * 4;
             *reinterpret_cast<uint2*>(Ks + off)      = *reinterpret_cast<const uint2*>(&h[0]);
@@ -224,6 +246,16 @@ namespace slsgp
             {
                 *reinterpret_cast<uint2*>(Ks_lo + off)      = *reinterpret_cast<const uint2*>(&hl[0]);
                 *reinterpret_cast<uint2*>(Ks_lo + off + 64) = *reinterpret_cast<const uint2*>(&hl[2]);
+            }
+            if (kernel_type != 0)
+            {
+                *reinterpret_cast<uint2*>(Gs + off)      = *reinterpret_cast<const uint2*>(&gh[0]);
+                *reinterpret_cast<uint2*>(Gs + off + 64) = *reinterpret_cast<const uint2*>(&gh[2]);
+                if (Gs_lo)
+                {
+                    *reinterpret_cast<uint2*>(Gs_lo + off)      = *reinterpret_cast<const uint2*>(&gl[0]);
+                    *reinterpret_cast<uint2*>(Gs_lo + off + 64) = *reinterpret_cast<const uint2*>(&gl[2]);
+                }
             }
         }
     }
@@ -244,6 +276,10 @@ namespace slsgp
         int              b_lo_row;  // row offset of the Kinv residuals inside the Bmat tensor map
         const __half*    Ks_lo;     // k residuals (null when passes == 1)
         const __half*    Ks;
+        int              matern;    // Matern 5/2: the gradient weight g is its own operand (SE: g = -c k)
+        int              g_row;     // row offset (relative to a_row0) of the g operand inside the Ks tensor map
+        const __half*    Gs;        // g values / residuals, same layout as Ks / Ks_lo (Matern only)
+        const __half*    Gs_lo;
         const float*     Xt;
         const TcScales*  sc;
         double           se_factor; // c
@@ -272,7 +308,7 @@ namespace slsgp
     // NCTA = 1: one CTA per SM, UMMA 128 x 256. NCTA = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) works on 256
     // candidates with UMMA 256 x 256; each CTA stages its own 128 k rows and HALF of every Kinv tile, the leader (cluster
     // rank 0) issues the MMAs for both SMs, and each CTA runs the epilogue of its own 128 TMEM lanes.
-    template <int XP, int NCTA>
+    template <int XP, int NCTA, bool MATERN>
     __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_sweep_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                              const TcGemmParams p)
@@ -344,12 +380,14 @@ namespace slsgp
             for (int w = cid; w < n_groups * p.split; w += ncl)
             {
                 const int g = w / p.split, h = w - g * p.split;
-                const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb : cb_end - 1;
-                const int cbk = g * NCTA + (int) rank, a_row = p.a_row0 + cbk * TC_BM;
+                // the owner of the extras takes block ncb (extras x k) and, for Matern, block ncb + 1 (extras x g)
+                const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb + (MATERN ? 1 : 0) : cb_end - 1;
+                const int cbk = g * NCTA + (int) rank, a_row_k = p.a_row0 + cbk * TC_BM;
                 for (int cb = cb_begin; cb <= last; ++cb)
                 {
-                    const bool     extras = cb == p.ncb;
+                    const bool     extras = cb >= p.ncb;
                     const bool     two_b  = P >= 2 && !extras;
+                    const int      a_row  = a_row_k + ((MATERN && cb == p.ncb + 1) ? p.g_row : 0);
                     const int      b_row  = extras ? p.ldt + (int) rank * (EC / NCTA) : cb * TC_BN + (int) rank * BH_ROWS;
                     const uint32_t tx     = (uint32_t) NCTA * (TC_A_BYTES * (P == 3 ? 2 : 1) + BH_BYTES * (two_b ? 2 : 1));
                     for (int k = 0; k < p.kb; ++k, ++it)
@@ -394,10 +432,10 @@ namespace slsgp
                 for (int w = cid; w < n_groups * p.split; w += ncl)
                 {
                     const int h = w % p.split;
-                    const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb : cb_end - 1;
+                    const int cb_begin = h * half_cb, cb_end = min(p.ncb, cb_begin + half_cb), last = (h == p.split - 1) ? p.ncb + (MATERN ? 1 : 0) : cb_end - 1;
                     for (int cb = cb_begin; cb <= last; ++cb, ++t)
                     {
-                        const bool     extras = cb == p.ncb;
+                        const bool     extras = cb >= p.ncb;
                         const bool     two_b = P >= 2 && !extras, two_a = P == 3;
                         const uint32_t slot = t & 1, use = t >> 1;
                         tc::mbar_wait(tc::smem_u32(&tempty_bar[slot]), (use & 1) ^ 1, p.err, 2);
@@ -471,6 +509,16 @@ namespace slsgp
 #pragma unroll
                 for (int v = 0; v < 4; ++v)
                     kn[v] = __ldg(kbase + cb_begin * (TC_BN / 8) + v), ln[v] = lrow ? __ldg(lbase + cb_begin * (TC_BN / 8) + v) : make_uint4(0, 0, 0, 0);
+                // Matern: the gradient weight g_i is not a multiple of k_i and travels as its own operand
+                const uint4* gbase  = MATERN ? reinterpret_cast<const uint4*>(p.Gs + (size_t) m * p.ldt) : nullptr;
+                const uint4* glbase = (MATERN && p.Gs_lo) ? reinterpret_cast<const uint4*>(p.Gs_lo + (size_t) m * p.ldt) : nullptr;
+                uint4        gn[MATERN ? 4 : 1], gln[MATERN ? 4 : 1];
+                if constexpr (MATERN)
+                {
+#pragma unroll
+                    for (int v = 0; v < 4; ++v)
+                        gn[v] = __ldg(gbase + cb_begin * (TC_BN / 8) + v), gln[v] = glbase ? __ldg(glbase + cb_begin * (TC_BN / 8) + v) : make_uint4(0, 0, 0, 0);
+                }
 
                 for (int cb = cb_begin; cb < cb_end; ++cb, ++t)
                 {
@@ -499,30 +547,48 @@ namespace slsgp
                             uint32_t  r[32];
                             tc::tmem_ld_x32(taddr + ch * 32, r);
                             // this chunk's k values were fetched one chunk ago; fetch the next chunk's now
-                            uint4 kv[4], lv[4];
+                            uint4 kv[4], lv[4], gv[MATERN ? 4 : 1], glv[MATERN ? 4 : 1];
 #pragma unroll
                             for (int v = 0; v < 4; ++v) kv[v] = kn[v], lv[v] = ln[v];
+                            if constexpr (MATERN)
                             {
-                                const int gn = min(cb * (TC_BN / 32) + ch + 1, p.ncb * (TC_BN / 32) - 1);
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) kn[v] = __ldg(kbase + gn * 4 + v);
+                                for (int v = 0; v < 4; ++v) gv[v] = gn[v], glv[v] = gln[v];
+                            }
+                            {
+                                const int nx = min(cb * (TC_BN / 32) + ch + 1, p.ncb * (TC_BN / 32) - 1);
 #pragma unroll
-                                for (int v = 0; v < 4; ++v) ln[v] = lrow ? __ldg(lbase + gn * 4 + v) : make_uint4(0, 0, 0, 0);
+                                for (int v = 0; v < 4; ++v) kn[v] = __ldg(kbase + nx * 4 + v);
+#pragma unroll
+                                for (int v = 0; v < 4; ++v) ln[v] = lrow ? __ldg(lbase + nx * 4 + v) : make_uint4(0, 0, 0, 0);
+                                if constexpr (MATERN)
+                                {
+#pragma unroll
+                                    for (int v = 0; v < 4; ++v) gn[v] = __ldg(gbase + nx * 4 + v), gln[v] = glbase ? __ldg(glbase + nx * 4 + v) : make_uint4(0, 0, 0, 0);
+                                }
                             }
                             tc::tmem_ld_wait();
-                            const __half2* kh = reinterpret_cast<const __half2*>(kv);
-                            const __half2* lh = reinterpret_cast<const __half2*>(lv);
+                            const __half2* kh  = reinterpret_cast<const __half2*>(kv);
+                            const __half2* lh  = reinterpret_cast<const __half2*>(lv);
+                            const __half2* gh  = reinterpret_cast<const __half2*>(gv);
+                            const __half2* glh = reinterpret_cast<const __half2*>(glv);
 #pragma unroll
                             for (int c2 = 0; c2 < 16; ++c2)
                             {
                                 const float2 kf = __half22float2(kh[c2]), lf = __half22float2(lh[c2]);
+                                float2       gf = make_float2(0.f, 0.f);
+                                if constexpr (MATERN)
+                                {
+                                    const float2 g1 = __half22float2(gh[c2]), g2 = __half22float2(glh[c2]);
+                                    gf              = make_float2(g1.x + g2.x, g1.y + g2.y);
+                                }
 #pragma unroll
                                 for (int h = 0; h < 2; ++h)
                                 {
                                     const int     c  = c2 * 2 + h;
                                     const float   u  = __uint_as_float(r[c]);
                                     const float   k1 = h ? kf.y : kf.x, dk = h ? lf.y : lf.x;
-                                    const float   tv = (k1 + dk) * u;            // gradient sums
+                                    const float   tv = MATERN ? (h ? gf.y : gf.x) * u : (k1 + dk) * u; // gradient sums
                                     const float   tq = fmaf(qw * dk, u, k1 * u); // quadratic form
                                     const float4* xr = reinterpret_cast<const float4*>(Xs + (chl * 32 + c) * XP);
                                     const float2  t2 = make_float2(tv, tv), tq2 = make_float2(tq, tv);
@@ -544,20 +610,27 @@ namespace slsgp
                         tc::mbar_arrive(slot ? tempty1 : tempty0);
                 }
 
+                // Xt columns: SE [1 | X_0 ..]: acc = (q, P2_0 ..) and gb = -c q, P2 = -c (.);  Matern [1 | 1 | X_0 ..]: acc = (q, gb, P2_0 ..)
+                constexpr int XO = MATERN ? 2 : 1;
                 const bool   live = m < p.Mc;
-                const double c    = p.se_factor;
+                const double c    = MATERN ? -1.0 : p.se_factor; // common factor -c of the SE sums; Matern sums carry g itself
                 const double q    = (double) acc[0].x * (double) inv_u;
+                const double gb   = MATERN ? (double) acc[0].y * (double) inv_u : -c * q;
                 double*      P2o  = owns_extras ? p.P2 : p.P2x + (size_t) h * p.ldp * p.part_stride;
                 if (live)
                 {
 #pragma unroll
-                    for (int d = 0; d < XP - 1; ++d)
-                        if (d < p.D) P2o[(size_t) d + (size_t) m * p.ldp] = -c * (double) (((1 + d) & 1) ? acc[(1 + d) >> 1].y : acc[(1 + d) >> 1].x) * (double) inv_u;
-                    if (!owns_extras) p.qx[(size_t) h * p.part_stride + m] = make_double2(q, -c * q);
+                    for (int d = 0; d < XP - XO; ++d)
+                        if (d < p.D) P2o[(size_t) d + (size_t) m * p.ldp] = -c * (double) (((XO + d) & 1) ? acc[(XO + d) >> 1].y : acc[(XO + d) >> 1].x) * (double) inv_u;
+                    if (!owns_extras) p.qx[(size_t) h * p.part_stride + m] = make_double2(q, gb);
                 }
                 if (!owns_extras) continue;
 
-                // extras block: column 2c = hi, 2c + 1 = lo of sum_j k_mj alpha_j (1, X_0j, ..)[c]
+                // extras blocks: column 2c = hi, 2c + 1 = lo of sum_j w_mj alpha_j (1, X_0j, ..)[c]; w = k (mu; for SE also ga and
+                // P1 up to the factor -c), then for Matern a second block with w = g (ga, P1)
+                double mu_k = 0.0;
+#pragma unroll 1
+                for (int eb = 0; eb < (MATERN ? 2 : 1); ++eb)
                 {
                     const uint32_t slot = t & 1, use = t >> 1;
                     tc::mbar_wait(tc::smem_u32(&tfull_bar[slot]), use & 1, p.err, 5);
@@ -574,12 +647,26 @@ namespace slsgp
                         {
                             const int    cc = ch * 8 + i;
                             const double S  = (double) (__uint_as_float(r[2 * i]) + __uint_as_float(r[2 * i + 1])) * (double) inv_e;
-                            if (live)
+                            if (!MATERN)
+                            {
+                                if (live)
+                                {
+                                    if (cc == 0)
+                                        p.stats[m] = make_double4(S, q, -c * S, gb);
+                                    else if (cc <= p.D)
+                                        p.P1[(size_t) (cc - 1) + (size_t) m * p.ldp] = -c * S;
+                                }
+                            }
+                            else if (eb == 0)
+                            {
+                                if (cc == 0) mu_k = S;
+                            }
+                            else if (live)
                             {
                                 if (cc == 0)
-                                    p.stats[m] = make_double4(S, q, -c * S, -c * q);
+                                    p.stats[m] = make_double4(mu_k, q, S, gb);
                                 else if (cc <= p.D)
-                                    p.P1[(size_t) (cc - 1) + (size_t) m * p.ldp] = -c * S;
+                                    p.P1[(size_t) (cc - 1) + (size_t) m * p.ldp] = S;
                             }
                         }
                     }

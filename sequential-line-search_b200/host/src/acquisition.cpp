@@ -139,8 +139,8 @@ namespace sequential_line_search
             {
                 std::lock_guard<std::mutex> lock(d->DeviceMutex());
                 slsgp_ctx*                  c = d->Device();
-                // the tensor-core sweep pays off for large candidate counts (ARD-SE kernel only); the polish is FP64
-                const bool tensor = regressor.GetKernelType() == KernelType::ArdSquaredExponentialKernel && count >= 32768 && D <= 67;
+                // the tensor-core sweep pays off for large candidate counts; the ascent and the polish are FP64
+                const bool tensor = count >= 32768 && D <= (regressor.GetKernelType() == KernelType::ArdSquaredExponentialKernel ? 67u : 66u);
                 check(c, slsgp_set_sweep_mode(c, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), "slsgp_set_sweep_mode");
                 // global sweep + batched multi-start ascent, all on the device; the winner is polished below
                 double             v0 = 0.0;

@@ -53,8 +53,10 @@ SIZES = [(4, 1), (6, 63), (7, 96), (8, 65), (11, 300), (16, 448), (16, 700), (33
 
 @pytest.mark.parametrize("D,N", SIZES)
 @pytest.mark.parametrize("xkind", ["uniform", "sls"])
-def test_tensor_sweep_matches_oracle(ctx, slsb, oracle, D, N, xkind):
-    kt, noise = S.SE, 0.005
+@pytest.mark.parametrize("kt", [S.SE, S.MATERN])
+def test_tensor_sweep_matches_oracle(ctx, slsb, oracle, D, N, xkind, kt):
+    """Both library kernels: for Matern 5/2 (the reference's default) the gradient weight g travels as its own fp16 operand."""
+    noise = 0.005
     X, theta = S.make_X(N, D, xkind), S.make_theta(D, "perturbed")
     y = S.make_y(X)
     ctx.fit(X, kt, theta, noise, y)
@@ -102,6 +104,25 @@ def test_tensor_modes_full_size_vs_fp64(ctx, slsb):
         check("grad UCB", gucb, gucb0, tol_g)
         assert int(np.argmax(val)) == int(np.argmax(val0)) or val0[np.argmax(val)] >= val0.max() * (1 - tol_v)
     ctx.set_sweep_mode(slsb.SWEEP_FP64)
+
+
+def test_tensor_matern_full_size_vs_fp64(ctx, slsb):
+    """N=2048, D=16 with the Matern 5/2 kernel (the reference's default), clustered data: 3-pass tensor sweep vs the FP64 sweep."""
+    D, N, M = 16, 2048, 4000
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "default")
+    ctx.fit(X, S.MATERN, theta, 0.005, S.make_y(X))
+    Q = S.make_queries(M, D)
+    v0, g0 = ctx.acq_batch(0, 1.0, Q)
+    mu0, s0, dmu0, ds0 = ctx.posterior_batch(Q)
+    ctx.set_sweep_mode(slsb.SWEEP_TENSOR)
+    v, g = ctx.acq_batch(0, 1.0, Q)
+    mu, sg, dmu, ds = ctx.posterior_batch(Q)
+    check("mu", mu, mu0)
+    check("sigma", sg, s0)
+    check("dmu", dmu, dmu0, floor=grad_floor(theta))
+    check("dsigma", ds, ds0, floor=grad_floor(theta))
+    check("EI", v, v0)
+    check("grad EI", g, g0, floor=grad_floor(theta))
 
 
 def test_tensor_full_size_clustered_data(ctx, slsb):
@@ -177,14 +198,14 @@ def test_tensor_mode_tracks_model_updates(ctx, slsb):
 
 
 def test_tensor_mode_limits_are_reported(ctx, slsb):
-    X = S.make_X(50, 6, "uniform")
-    ctx.fit(X, S.MATERN, S.make_theta(6), 0.005, S.make_y(X))
+    X = S.make_X(40, 67, "uniform")   # the Matern sweep carries one more reduction column: D <= 66
+    ctx.fit(X, S.MATERN, S.make_theta(67), 0.005, S.make_y(X))
     ctx.set_sweep_mode(slsb.SWEEP_TENSOR)
     with pytest.raises(slsb.SlsgpError) as e:
-        ctx.acq_batch(0, 1.0, S.make_queries(8, 6))
-    assert e.value.status == slsb.ERR_INVALID and "squared-exponential" in str(e.value)
+        ctx.acq_batch(0, 1.0, S.make_queries(8, 67))
+    assert e.value.status == slsb.ERR_INVALID
     ctx.set_sweep_mode(slsb.SWEEP_FP64)
-    ctx.acq_batch(0, 1.0, S.make_queries(8, 6))  # the FP64 sweep still serves the Matern model
+    ctx.acq_batch(0, 1.0, S.make_queries(8, 67))  # the FP64 sweep serves any D
     X = S.make_X(40, 70, "uniform")
     ctx.fit(X, S.SE, S.make_theta(70), 0.005, S.make_y(X))
     ctx.set_sweep_mode(slsb.SWEEP_TENSOR)
