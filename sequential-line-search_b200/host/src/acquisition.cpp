@@ -206,19 +206,35 @@ namespace sequential_line_search
                       "slsgp_acq_from_posterior");
             };
 
-            const long count = (long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter;
-            MatrixXd   cand  = MatrixXd::Zero(D, count);
+            // global stage: the counter-based candidate sequence in chunks (bounded host memory), tensor sweep for large counts
+            const long count = std::min<long>((long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter, 1L << 21);
+            const long chunk = std::min<long>(count, 1L << 17);
+            const bool tensor = count >= 32768 && D <= 66;
+            const auto set_mode = [&](const DeviceRegressor& r, slsgp_sweep_mode mode) {
+                std::lock_guard<std::mutex> lock(r.DeviceMutex());
+                check(r.Device(), slsgp_set_sweep_mode(r.Device(), mode), "slsgp_set_sweep_mode");
+            };
+            MatrixXd cand = MatrixXd::Zero(D, chunk);
             for (unsigned i = 0; i < num_points; ++i)
             {
+                VectorXd x_best  = VectorXd::Constant(D, 0.5);
+                double   v_best  = -std::numeric_limits<double>::infinity();
+                const uint64_t seed = search_seed(regressor) + 0x51ED27ull * (i + 1);
+                if (tensor) set_mode(*orig, SLSGP_SWEEP_TENSOR), set_mode(*temp, SLSGP_SWEEP_TENSOR);
+                for (long first = 0; first < count; first += chunk)
                 {
-                    std::lock_guard<std::mutex> lock(orig->DeviceMutex());
-                    check(orig->Device(), slsgp_candidates(orig->Device(), search_seed(regressor) + 0x51ED27ull * (i + 1), 0, count, cand.data()), "slsgp_candidates");
+                    const long n = std::min(chunk, count - first);
+                    if (n != cand.cols()) cand = MatrixXd::Zero(D, n);
+                    {
+                        std::lock_guard<std::mutex> lock(orig->DeviceMutex());
+                        check(orig->Device(), slsgp_candidates(orig->Device(), seed, first, n, cand.data()), "slsgp_candidates");
+                    }
+                    VectorXd val;
+                    pair_acq(cand, val, nullptr);
+                    for (long m = 0; m < n; ++m)
+                        if (val(m) > v_best) v_best = val(m), x_best = cand.col(m); // NaN never wins, lowest index wins ties
                 }
-                VectorXd val;
-                pair_acq(cand, val, nullptr);
-                long best = 0;
-                for (long m = 1; m < count; ++m)
-                    if (val(m) > val(best)) best = m; // NaN never wins, lowest index wins ties
+                if (tensor) set_mode(*orig, SLSGP_SWEEP_FP64), set_mode(*temp, SLSGP_SWEEP_FP64);
                 const VectorXd x_star = polish(
                     [&](const VectorXd& x, VectorXd& g) {
                         MatrixXd X1 = MatrixXd::Zero(D, 1), G;
@@ -228,7 +244,7 @@ namespace sequential_line_search
                         g = G.col(0);
                         return v(0);
                     },
-                    cand.col(best), num_local_search_iters);
+                    x_best, num_local_search_iters);
                 points.push_back(x_star);
 
                 if (points.size() != num_points)
