@@ -25,11 +25,8 @@ def _sources():
 
 
 def needs_build() -> bool:
-    if not os.path.exists(LIB_PATH):
-        return True
-    t = os.path.getmtime(LIB_PATH)
     hdr = os.path.join(os.path.dirname(PKG_DIR), "include", "slsgp.h")
-    return any(os.path.getmtime(s) > t for s in _sources() + [hdr])
+    return not _is_current(LIB_PATH, _sources() + [hdr])
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -46,6 +43,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
+    _stamp(LIB_PATH, _sources() + [os.path.join(os.path.dirname(PKG_DIR), "include", "slsgp.h")])
     return LIB_PATH
 
 
@@ -53,15 +51,46 @@ HOST_DIR = os.path.join(PKG_DIR, "host")
 HOST_LIB_PATH = os.path.join(LIB_DIR, "libsls_b200_host.so")
 
 
+def _tree_hash(paths) -> str:
+    """Content hash of source files. Staleness is decided by content, not by mtime: the snapshot that travels to the GPU
+    box does not preserve modification times, and a spurious rebuild there costs GPU-minutes."""
+    import hashlib
+    h = hashlib.sha256()
+    for p in sorted(paths):
+        h.update(p.encode())
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def _is_current(out: str, sources) -> bool:
+    stamp = out + ".srchash"
+    return os.path.exists(out) and os.path.exists(stamp) and open(stamp).read().strip() == _tree_hash(sources)
+
+
+def _stamp(out: str, sources) -> None:
+    with open(out + ".srchash", "w") as f:
+        f.write(_tree_hash(sources))
+
+
+def _host_sources():
+    inc = os.path.join(HOST_DIR, "include", "sequential-line-search")
+    src = os.path.join(HOST_DIR, "src")
+    return ([os.path.join(inc, f) for f in os.listdir(inc)] + [os.path.join(src, f) for f in os.listdir(src)] +
+            [os.path.join(HOST_DIR, "Makefile"), os.path.join(os.path.dirname(PKG_DIR), "include", "slsgp.h")])
+
+
 def build_host(force: bool = False) -> str:
     """Build libsls_b200_host.so: the C++ mirror of the reference's Regressor / acquisition_func interface above the
     C ABI (g++, links libslsgp.so with an $ORIGIN rpath). Uses the system Eigen when EIGEN_INC names it, else the
     repository's eigen-lite subset."""
     build()
-    cmd = ["make", "-s", "-C", HOST_DIR] + (["-B"] if force else [])
-    res = subprocess.run(cmd, capture_output=True, text=True)
+    if not force and _is_current(HOST_LIB_PATH, _host_sources()):
+        return HOST_LIB_PATH
+    res = subprocess.run(["make", "-s", "-B", "-C", HOST_DIR], capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("host layer build failed:\n" + res.stdout + res.stderr)
+    _stamp(HOST_LIB_PATH, _host_sources())
     return HOST_LIB_PATH
 
 
@@ -78,9 +107,8 @@ def build_python_module(force: bool = False) -> str:
     sequential-line-search_b200/lib on sys.path."""
     build_host()
     out = python_module_path()
-    deps = [PY_SRC, HOST_LIB_PATH] + [os.path.join(HOST_DIR, "include", "sequential-line-search", f)
-                                      for f in os.listdir(os.path.join(HOST_DIR, "include", "sequential-line-search"))]
-    if not force and os.path.exists(out) and all(os.path.getmtime(d) <= os.path.getmtime(out) for d in deps):
+    deps = [PY_SRC] + _host_sources()
+    if not force and _is_current(out, deps):
         return out
     import pybind11
     import sysconfig
@@ -91,6 +119,7 @@ def build_python_module(force: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("pySequentialLineSearch build failed:\n" + res.stdout + res.stderr)
+    _stamp(out, deps)
     return out
 
 
