@@ -289,11 +289,11 @@ namespace
         double* W = dp(ctx->W);
         TRY(ensure(ctx, ctx->chol_flags, sizeof(int) * (size_t) nb));
         CUDA_TRY(cudaMemsetAsync(ctx->chol_flags.p, 0, sizeof(int) * (size_t) nb, ctx->stream));
-        static bool chol_attr = false;
-        if (!chol_attr)
+        static bool chol_attr[64] = {}; // function attributes are per device
+        if (!chol_attr[ctx->device & 63])
         {
             CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
-            chol_attr = true;
+            chol_attr[ctx->device & 63] = true;
         }
         // launch k finishes block column k+1 (diagonal factor + panel) while updating the rest of the trailing matrix
         for (int k = -1; k <= nb - 2; ++k)
@@ -538,7 +538,8 @@ namespace
         prm.stages         = (int) std::min<size_t>(TC_MAX_STAGES, (232448 - 512 - fixed) / prm.stage_bytes);
         if (prm.stages < 2) return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: pipeline does not fit in shared memory");
         const size_t smem  = (size_t) prm.stages * prm.stage_bytes + fixed;
-        static size_t attr_smem = 0;
+        static size_t attr_smem_dev[64] = {}; // function attributes are per device
+        size_t&       attr_smem = attr_smem_dev[ctx->device & 63];
         if (attr_smem < smem)
         {
             CUDA_TRY(cudaFuncSetAttribute(tc_sweep_gemm_kernel<XP, NCTA, MATERN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
@@ -590,7 +591,8 @@ namespace
         __half*         Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
         ProfScope       ps(ctx, "tc_kstar", st);
         const size_t    smem = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + D * 128);
-        static bool     kstar_attr = false;
+        static bool     kstar_attr_dev[64] = {};
+        bool&           kstar_attr = kstar_attr_dev[ctx->device & 63];
         if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
         {
             CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -611,8 +613,8 @@ namespace
         const long long row0 = (long long) buf * 4 * ctx->tc_Mcap;
         __half*         Ks    = ptr<__half>(ctx->Ks) + (size_t) row0 * ldt;
         __half*         Ks_lo = passes > 1 ? Ks + (size_t) ctx->tc_Mcap * ldt : nullptr;
-        static int      n_sm = 0;
-        if (!n_sm) CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+        int n_sm = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
         int split = 1;
         {
             ProfScope    ps(ctx, "tc_gemm");

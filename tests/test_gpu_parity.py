@@ -308,3 +308,32 @@ def test_whitened_map_objective_is_the_same_function(ctx, kt, D, N):
     np.testing.assert_allclose(ctx.whiten(y), z, rtol=1e-8, atol=1e-12)
     f_only, g_none, _ = ctx.map_objective_pref_whitened(z, btl, want_grad=False)
     assert f_only == f_w and g_none is None
+
+
+def test_new_entry_points_validate_their_arguments(ctx, slsb):
+    X = S.make_X(20, 3)
+    c = slsb.Context(0)
+    try:
+        c.set_data(X)
+        with pytest.raises(slsb.SlsgpError) as e:          # no factor yet
+            c.map_objective_pref_whitened(np.zeros(20), 0.01)
+        assert e.value.status == slsb.ERR_STATE
+        with pytest.raises(slsb.SlsgpError) as e:
+            c.whiten(np.zeros(20))
+        assert e.value.status == slsb.ERR_STATE
+        with pytest.raises(slsb.SlsgpError) as e:          # no model yet
+            c.acq_maximize(0, 1.0, 1, 0, 100)
+        assert e.value.status == slsb.ERR_STATE
+        c.fit(X, S.SE, S.make_theta(3), 0.005, S.make_y(X))
+        with pytest.raises(slsb.SlsgpError) as e:
+            c.acq_maximize(0, 1.0, 1, 0, 0)                # empty range
+        assert e.value.status == slsb.ERR_INVALID
+        with pytest.raises(slsb.SlsgpError) as e:
+            c.map_objective_pref_whitened(np.full(20, np.nan), 0.01)
+        assert e.value.status == slsb.ERR_NAN
+        # fewer candidates than requested starts: one start per candidate, still the sweep winner or better
+        _, v_sweep, _, _ = c.acq_argmax(0, 1.0, 5, 0, 7)
+        x, v, g, v0 = c.acq_maximize(0, 1.0, 5, 0, 7, n_starts=1024, n_iters=10)
+        assert v0 == v_sweep and v >= v_sweep and x.shape == (3,)
+    finally:
+        c.close()
