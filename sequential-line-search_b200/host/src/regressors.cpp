@@ -16,15 +16,55 @@ namespace sequential_line_search
 {
     namespace internal
     {
+        // Contexts are recycled: the optimisers build a fresh regressor every iteration (as the reference does,
+        // src/sequential-line-search.cpp:94-103), and a libslsgp context owns streams, events and device buffers that only
+        // ever grow - handing a released context to the next regressor saves their re-creation (cudaMalloc / cudaFree of
+        // the sweep workspaces) on every SubmitFeedbackData. A regressor always starts with slsgp_set_data, which
+        // invalidates everything the previous owner left behind.
+        namespace
+        {
+            std::mutex                           g_pool_mutex;
+            std::vector<std::pair<int, slsgp_ctx*>> g_pool; // (device, idle context)
+            struct PoolDrain                     // destroy what is still pooled at process exit
+            {
+                ~PoolDrain()
+                {
+                    for (auto& e : g_pool) slsgp_ctx_destroy(e.second);
+                    g_pool.clear();
+                }
+            } g_pool_drain;
+        } // namespace
+
         std::shared_ptr<slsgp_ctx> make_device()
         {
-            const char* env = std::getenv("SLS_B200_DEVICE");
-            slsgp_ctx*  raw = nullptr;
-            const slsgp_status s = slsgp_ctx_create(env ? std::atoi(env) : 0, &raw);
-            if (s != SLSGP_OK || !raw)
-                throw std::runtime_error(std::string("libslsgp: no usable CUDA device (") + slsgp_status_string(s) +
-                                         "); this library has no CPU path");
-            return std::shared_ptr<slsgp_ctx>(raw, [](slsgp_ctx* c) { slsgp_ctx_destroy(c); });
+            const char* env    = std::getenv("SLS_B200_DEVICE");
+            const int   device = env ? std::atoi(env) : 0;
+            slsgp_ctx*  raw    = nullptr;
+            {
+                std::lock_guard<std::mutex> lock(g_pool_mutex);
+                for (size_t i = 0; i < g_pool.size(); ++i)
+                    if (g_pool[i].first == device)
+                    {
+                        raw = g_pool[i].second;
+                        g_pool.erase(g_pool.begin() + (long) i);
+                        break;
+                    }
+            }
+            if (!raw)
+            {
+                const slsgp_status s = slsgp_ctx_create(device, &raw);
+                if (s != SLSGP_OK || !raw)
+                    throw std::runtime_error(std::string("libslsgp: no usable CUDA device (") + slsgp_status_string(s) +
+                                             "); this library has no CPU path");
+            }
+            return std::shared_ptr<slsgp_ctx>(raw, [device](slsgp_ctx* c) {
+                slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
+                std::lock_guard<std::mutex> lock(g_pool_mutex);
+                if (g_pool.size() < 4)
+                    g_pool.emplace_back(device, c);
+                else
+                    slsgp_ctx_destroy(c);
+            });
         }
     } // namespace internal
 
