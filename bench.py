@@ -361,8 +361,9 @@ def main_graft(args):
         peak = peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops"))
         sweep_total = sum(v[0] for v in prof.values())
         if args.mode == "fp64":
-            kname = "gemm64_kernel<NN> (beta = K^-1 k*, FP64 DFMA)"
-            note = "the kernel runs on the FP64 pipe; the tensor peak is quoted for scale only"
+            kname = "gemm64_dmma_kernel<NN> (beta = K^-1 k*, mma.sync.m8n8k4.f64)"
+            peak, peak_src = 37.0, "nominal B200 dense FP64 (datasheet; no FP64 figure in MEASURED_PEAKS.json),"
+            note = "the kernel runs on the FP64 tensor pipe (DMMA)"
         else:
             kname = (f"tc_sweep_gemm_kernel<20, 2> (tcgen05.mma cta_group::2 kind::f16, 256x256x16, {PASSES[args.mode]} split-fp16 "
                      "pass(es) per pipeline stage, fused epilogue)")
@@ -391,12 +392,13 @@ def main_graft(args):
                     "candidates_per_gpu_per_step": Me, "api": "slsgp_acq_batch (host buffers)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": kname,
+            "roofline": {"bound": "tensor", "kernel": kname,  # fp64 mode: the FP64 tensor pipe
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                          "executed_tflops": (PASSES[args.mode] * achieved) if achieved else None,
                          "executed_frac": (PASSES[args.mode] * achieved / peak) if achieved else None,
-                         "peak_source": f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)", "note": note,
+                         "peak_source": (f"{peak_src} TFLOP/s" if args.mode == "fp64" else f"{peak_src} bf16 sustained (MEASURED_PEAKS.json)"),
+                         "note": note,
                          "launches_timed": gemm_n, "avg_launch_ms": gemm_ms / max(gemm_n, 1),
                          "share_of_sweep": gemm_ms / sweep_total if sweep_total else None,
                          "kernel_ms": {k: v[0] for k, v in prof.items()}},

@@ -570,11 +570,11 @@ namespace
     }
 
     slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
-                              int n_parts = 0, double x_shift = 0.0)
+                              int n_parts = 0, double x_shift = 0.0, int ldp = 0)
     {
         ProfScope ps(ctx, "sweep_finish");
         sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
-            d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
+            d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ldp ? ldp : ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
             acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x), x_shift);
         LAUNCH_CHECK();
         return SLSGP_OK;
@@ -627,7 +627,8 @@ namespace
             prm.Gs = Ks + (size_t) 2 * ctx->tc_Mcap * ldt, prm.Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
             prm.Ks = Ks, prm.Xt = ptr<float>(ctx->Xt), prm.sc = ptr<TcScales>(ctx->tcs);
             prm.se_factor = (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0;
-            prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2), prm.ldp = ctx->Dp;
+            prm.stats = ptr<double4>(ctx->stats), prm.P1 = dp(ctx->P1), prm.P2 = dp(ctx->P2);
+            prm.ldp = D; // packed: one candidate's D sums are contiguous (the FP64 path's GEMM output needs the 64-row padding)
             prm.err = ptr<int>(ctx->tc_err);
             static const int split_env = std::getenv("SLSGP_TC_SPLIT") ? std::atoi(std::getenv("SLSGP_TC_SPLIT")) : 2;
             prm.split = std::max(1, std::min(std::min(split_env, 4), prm.ncb));
@@ -643,7 +644,7 @@ namespace
                 default: return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: unsupported D");
             }
         }
-        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1, 0.5);
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1, 0.5, D);
     }
 
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
