@@ -5,6 +5,8 @@
 
 #include <sequential-line-search/optimizers.hpp>
 
+#include "optimizer.hpp"
+
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -183,6 +185,38 @@ extern "C"
         const Slider s(vector(end_0, D), vector(end_1, D), enlarge != 0, scale, minimum_length);
         store(s.end_0, out_0);
         store(s.end_1, out_1);
+    }
+
+    // ---- the bound-constrained quasi-Newton driver on two closed-form problems (CPU-only test hook) ---------------------------
+    // problem 0: sum_i w_i (x_i - t_i)^2 with w_i = 1 + i and targets t_i = 2 i / n - 0.5 (some outside the box [0, 1]^n);
+    // problem 1: the Rosenbrock valley in n dimensions on [-2, 2]^n. Returns the number of evaluations; x_out holds the solution.
+    int b200_test_minimize(int problem, int n, const double* x0, unsigned max_evals, double* x_out, double* f_out)
+    {
+        std::vector<double> lo((size_t) n, problem == 0 ? 0.0 : -2.0), hi((size_t) n, problem == 0 ? 1.0 : 2.0), start(x0, x0 + n);
+        const internal::Objective fun = [&](const std::vector<double>& x, std::vector<double>& g) {
+            double f = 0.0;
+            if (problem == 0)
+                for (int i = 0; i < n; ++i)
+                {
+                    const double w = 1.0 + i, t = 2.0 * i / n - 0.5;
+                    f += w * (x[(size_t) i] - t) * (x[(size_t) i] - t), g[(size_t) i] = 2.0 * w * (x[(size_t) i] - t);
+                }
+            else
+            {
+                for (auto& v : g) v = 0.0;
+                for (int i = 0; i + 1 < n; ++i)
+                {
+                    const double a = x[(size_t) i + 1] - x[(size_t) i] * x[(size_t) i], b = 1.0 - x[(size_t) i];
+                    f += 100.0 * a * a + b * b;
+                    g[(size_t) i] += -400.0 * a * x[(size_t) i] - 2.0 * b, g[(size_t) i + 1] += 200.0 * a;
+                }
+            }
+            return f;
+        };
+        const internal::MinimizeResult r = internal::minimize_bounded(fun, start, lo, hi, max_evals, 1e-9);
+        std::memcpy(x_out, r.x.data(), sizeof(double) * (size_t) n);
+        *f_out = r.f;
+        return (int) r.evals;
     }
 
     // ---- Regressor virtual interface ------------------------------------------------------------------------------------

@@ -23,7 +23,7 @@ HOST_SYMBOLS = [
     "b200_pref_objective", "b200_pref_num_map_evaluations", "b200_pref_get_state", "b200_pref_find_arg_max",
     "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
-    "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider",
+    "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
 ]
 
 
@@ -172,6 +172,12 @@ class Host:
         a, b = np.empty(len(end_0)), np.empty(len(end_0))
         self.lib.b200_slider(len(end_0), _p(end_0), _p(end_1), int(enlarge), C.c_double(scale), C.c_double(minimum_length), _p(a), _p(b))
         return a, b
+
+    def test_minimize(self, problem, x0, max_evals=2000):
+        x0 = _f64(x0)
+        x, f = np.empty(len(x0)), C.c_double()
+        evals = self.lib.b200_test_minimize(problem, len(x0), _p(x0), C.c_uint(max_evals), _p(x), C.byref(f))
+        return x, f.value, int(evals)
 
     # Regressor virtuals + acquisition
     def predict(self, reg, x):

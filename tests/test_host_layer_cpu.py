@@ -133,3 +133,19 @@ def test_python_module_surface_matches_the_reference_binding():
     opts = q.get_current_options()
     assert len(opts) == 4 and np.allclose(opts[2], 0.5)
     np.testing.assert_array_equal(q.get_maximizer(), opts[0])
+
+
+def test_quasi_newton_driver_on_closed_form_problems():
+    """host/src/optimizer.hpp (used where the reference calls NLopt): bounds are honoured, active-set solution of a box-constrained
+    quadratic is exact, the Rosenbrock valley is descended to its minimum, the evaluation budget is respected."""
+    host = pkg.hostlib.Host()
+    n = 12
+    x, f, evals = host.test_minimize(0, np.full(n, 0.3))
+    want = np.clip(2.0 * np.arange(n) / n - 0.5, 0.0, 1.0)            # projection of the targets onto the box
+    np.testing.assert_allclose(x, want, atol=1e-8)
+    assert evals < 200
+    x, f, evals = host.test_minimize(1, np.full(6, -1.2), max_evals=5000)
+    np.testing.assert_allclose(x, np.ones(6), atol=1e-5)
+    assert f < 1e-10 and evals < 5000
+    x, f, evals = host.test_minimize(1, np.full(6, -1.2), max_evals=30)   # budget: stops early, still inside the box
+    assert evals <= 30 + 8 and np.all(np.abs(x) <= 2.0) and f > 1e-10
