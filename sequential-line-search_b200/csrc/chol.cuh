@@ -157,6 +157,11 @@ namespace slsgp
         double(*As)[CHOL_LDS] = reinterpret_cast<double(*)[CHOL_LDS]>(csm);
         double(*Bs)[CHOL_LDS] = As + TILE;
 
+        // Programmatic dependent launch: let the next step's CTAs become resident as ours retire (they stop at their own
+        // griddepcontrol.wait until this whole grid has completed and its writes are visible), then wait for the previous step.
+        asm volatile("griddepcontrol.launch_dependents;");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+
         const int rem = nb - k - 1, t = blockIdx.x, tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
         int       tm, tn;
         if (t < rem)

@@ -300,9 +300,14 @@ namespace
         {
             const int rem  = nb - k - 1;
             const int grid = k < 0 ? rem : rem * (rem + 1) / 2;
-            ProfScope ps(ctx, "chol_step");
-            chol_step_kernel<<<grid, 256, CHOL_SMEM_BYTES, ctx->stream>>>(L, W, ld, k, nb, ptr<int>(ctx->chol_flags),
-                                                                          ptr<int>(ctx->info));
+            ProfScope           ps(ctx, "chol_step");
+            cudaLaunchConfig_t  cfg = {};
+            cudaLaunchAttribute attr[1];
+            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(256), cfg.dynamicSmemBytes = CHOL_SMEM_BYTES, cfg.stream = ctx->stream;
+            attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // overlap this launch with the tail of the previous step
+            attr[0].val.programmaticStreamSerializationAllowed = 1;
+            cfg.attrs = attr, cfg.numAttrs = 1;
+            CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel, L, W, ld, k, nb, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
             LAUNCH_CHECK();
         }
         zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
