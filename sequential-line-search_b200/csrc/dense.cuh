@@ -1,5 +1,5 @@
-// FP64 dense building blocks: tiled GEMM with triangular k-range pruning, the 64x64 diagonal-block
-// Cholesky + inverse, and small matrix utilities. Everything works on column-major storage whose leading
+// FP64 dense building blocks: tiled GEMM with triangular k-range pruning (DMMA and DFMA forms) and small matrix
+// utilities. Everything works on column-major storage whose leading
 // dimension is a multiple of TILE (=64); matrices are padded with an identity block so that no kernel needs
 // ragged-edge handling.
 #pragma once
@@ -224,56 +224,6 @@ namespace slsgp
                 }
     }
 
-    // Cholesky of one 64 x 64 diagonal block (in place, lower; the strict upper part of the block is zeroed) and
-    // its inverse W = L^-1 (lower) written to Wd. info[0] receives 1 + global index of the first bad pivot.
-    //
-    // Right-looking on both: at step j, after column j of L is final, the same rank-1 sweep that updates the
-    // trailing part of A also advances the forward substitution L W = I
-    //     W[j][0..j] /= L[j][j];   W[i][0..j] -= L[i][j] * W[j][0..j]   (i > j),
-    // so the inverse costs no extra barriers. W (strictly lower) lives transposed in the unused strict upper
-    // triangle of the shared tile, its diagonal in wd.
-    __global__ void __launch_bounds__(256) potf2_inverse_kernel(double* Ad, int lda, double* Wd, int ldw, int diag0,
-                                                                int* __restrict__ info)
-    {
-        __shared__ double S[TILE][TILE + 1];
-        __shared__ double wd[TILE];
-        const int         tid = threadIdx.x;
-        for (int e = tid; e < TILE * TILE; e += 256)
-        {
-            const int r = e & 63, c = e >> 6;
-            S[r][c]     = (c <= r) ? Ad[(size_t) r + (size_t) c * lda] : 0.0;
-        }
-        __syncthreads();
-        for (int j = 0; j < TILE; ++j)
-        {
-            const double d  = S[j][j];
-            const double sd = sqrt(d);
-            if (tid == 0 && !(d > 0.0)) atomicCAS(info, 0, 1 + diag0 + j);
-            __syncthreads(); // everyone has read S[j][j]
-            if (tid == j) S[j][j] = sd, wd[j] = 1.0 / sd;
-            if (tid > j && tid < TILE) S[tid][j] = S[tid][j] / sd;                  // column j of L
-            if (tid >= TILE && tid - TILE < j) S[tid - TILE][j] = S[tid - TILE][j] / sd; // row j of W (c' < j)
-            __syncthreads();
-            const int w = TILE - 1 - j; // rows j+1 .. 63
-            for (int e = tid; e < w * TILE; e += 256)
-            {
-                const int    r = j + 1 + (e >> 6), cc = e & 63;
-                const double lrj = S[r][j];
-                if (cc <= j) // W[r][cc] -= L[r][j] * W[j][cc]
-                    S[cc][r] = fma(-lrj, (cc == j) ? wd[j] : S[cc][j], S[cc][r]);
-                else if (cc <= r) // A[r][cc] -= L[r][j] * L[cc][j]
-                    S[r][cc] = fma(-lrj, S[cc][j], S[r][cc]);
-            }
-            __syncthreads();
-        }
-        for (int e = tid; e < TILE * TILE; e += 256)
-        {
-            const int r = e & 63, c = e >> 6;
-            Ad[(size_t) r + (size_t) c * lda] = (c <= r) ? S[r][c] : 0.0;
-            Wd[(size_t) r + (size_t) c * ldw] = (c < r) ? S[c][r] : (c == r ? wd[r] : 0.0);
-        }
-    }
-
     // Zero the strict upper triangle of an n x n matrix (after the blocked factorisation the upper tiles still hold
     // the Gram matrix).
     __global__ void zero_upper_kernel(double* __restrict__ A, int n, int lda)
@@ -300,19 +250,6 @@ namespace slsgp
             A[(size_t) (tn * TILE + r) + (size_t) (tm * TILE + c) * lda] = S[c][r];
         }
     }
-    // Diagonal tiles: copy lower to upper inside the tile.
-    __global__ void __launch_bounds__(256) symmetrize_diag_kernel(double* __restrict__ A, int lda)
-    {
-        const int t = blockIdx.x;
-        for (int e = threadIdx.x; e < TILE * TILE; e += 256)
-        {
-            const int r = e & 63, c = e >> 6;
-            if (r < c)
-                A[(size_t) (t * TILE + r) + (size_t) (t * TILE + c) * lda] =
-                    A[(size_t) (t * TILE + c) + (size_t) (t * TILE + r) * lda];
-        }
-    }
-
     // out[0] = 2 * sum_{i<n} log(L_ii)   (mathtoolbox log-determinant.cpp:8-11); single block, fixed order.
     __global__ void __launch_bounds__(256) logdet_kernel(const double* __restrict__ L, int n, int ld,
                                                          double* __restrict__ out)
