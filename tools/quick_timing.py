@@ -7,8 +7,8 @@ import time
 import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
-import support as S  # noqa: E402
+sys.path[:0] = [ROOT, os.path.join(ROOT, "tools")]
+import synth as S  # noqa: E402  (input generators only; no checker code)
 
 pkg = importlib.import_module("sequential-line-search_b200")
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
