@@ -283,7 +283,8 @@ namespace
         ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
         TRY(phase_begin(ctx, "factor"));
         CUDA_TRY(cudaMemcpyAsync(ctx->L.p, ctx->K.p, mat, cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(cudaMemsetAsync(ctx->W.p, 0, mat, ctx->stream));
+        // W is written tile by tile (diagonal tiles by the factorisation, the blocks below them by do_trtri); every reader
+        // prunes its k-range to the lower blocks, so W needs no clearing
         CUDA_TRY(cudaMemsetAsync(ctx->info.p, 0, sizeof(int), ctx->stream));
         double* L = dp(ctx->L);
         double* W = dp(ctx->W);
