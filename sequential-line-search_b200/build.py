@@ -56,8 +56,9 @@ def _tree_hash(paths) -> str:
     box does not preserve modification times, and a spurious rebuild there costs GPU-minutes."""
     import hashlib
     h = hashlib.sha256()
+    root = os.path.dirname(PKG_DIR)
     for p in sorted(paths):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, root).encode())  # relative: the repository lives under a different path on the GPU box
         with open(p, "rb") as f:
             h.update(f.read())
     return h.hexdigest()

@@ -42,6 +42,76 @@ namespace slsgp
         grad_y[i] = alpha ? s + -alpha[i] : s; // alpha == null: the likelihood part alone (whitened objective)
     }
 
+    // The whitened MAP objective (slsgp_map_objective_pref_whitened) for N <= 1024 in ONE single-block launch: at these sizes
+    // the five kernels of the general path are pure launch latency, and the quasi-Newton driver calls this hundreds of times
+    // per fit.  y = L z  ->  BTL terms of every tuple  ->  gather  ->  gz = L^T g - z.   out = [loglik | gz (N) | y (N)].
+    // One thread per row for the triangular products' row form, one warp per column for the transposed one.
+    __global__ void __launch_bounds__(1024)
+        map_whitened_fused_kernel(const double* __restrict__ L, int N, int ld, const double* __restrict__ z_in,
+                                  const uint32_t* __restrict__ off, const uint32_t* __restrict__ idx, int P, double scale,
+                                  const uint32_t* __restrict__ slot_off, const uint32_t* __restrict__ slot_list,
+                                  double* __restrict__ contrib, double* __restrict__ y_dev, int want_grad, double* __restrict__ out)
+    {
+        extern __shared__ double fsm[];
+        double*   z = fsm;          // [N]
+        double*   y = fsm + N;      // [N]
+        double*   g = fsm + 2 * N;  // [N]
+        double*   red = fsm + 3 * N; // [32]
+        const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+        for (int i = tid; i < N; i += 1024) z[i] = z_in[i];
+        __syncthreads();
+        for (int i = tid; i < N; i += 1024) // y_i = sum_{j <= i} L_ij z_j: consecutive threads read consecutive rows of column j
+        {
+            double s = 0.0;
+#pragma unroll 4
+            for (int j = 0; j <= i; ++j) s = fma(L[(size_t) i + (size_t) j * ld], z[j], s);
+            y[i] = s, y_dev[i] = s, out[1 + N + i] = s;
+        }
+        __syncthreads();
+        double ll = 0.0;
+        for (int t = tid; t < P; t += 1024) // btl_tuple_kernel, same arithmetic
+        {
+            const uint32_t b = off[t], e = off[t + 1];
+            const double   f0 = y[idx[b]];
+            double         sum = 0.0;
+            for (uint32_t i = b; i < e; ++i) sum += exp((1.0 / scale) * y[idx[i]]);
+            const double btl = exp((1.0 / scale) * f0) / sum;
+            ll += log(btl);
+            if (want_grad)
+            {
+                const double tmp = -btl * btl / scale;
+                double       s2  = 0.0;
+                for (uint32_t i = b + 1; i < e; ++i) s2 += exp((y[idx[i]] - f0) / scale);
+                contrib[b] = (tmp * (-s2)) / btl;
+                for (uint32_t i = b + 1; i < e; ++i) contrib[i] = (tmp * exp((y[idx[i]] - f0) / scale)) / btl;
+            }
+        }
+        ll = warp_sum(ll);
+        if (lane == 0) red[warp] = ll;
+        __syncthreads(); // also publishes contrib[] (global) to the block
+        if (tid == 0)
+        {
+            double s = 0.0;
+            for (int w = 0; w < 32; ++w) s += red[w];
+            out[0] = s;
+        }
+        if (!want_grad) return;
+        for (int i = tid; i < N; i += 1024)
+        {
+            double s = 0.0;
+            for (uint32_t p = slot_off[i]; p < slot_off[i + 1]; ++p) s += contrib[slot_list[p]];
+            g[i] = s;
+        }
+        __syncthreads();
+        for (int j = warp; j < N; j += 32) // gz_j = sum_{i >= j} L_ij g_i - z_j
+        {
+            double s = 0.0;
+            for (int i = j + lane; i < N; i += 32) s = fma(L[(size_t) i + (size_t) j * ld], g[i], s);
+            s = warp_sum(s);
+            if (lane == 0) out[1 + j] = s - z[j];
+        }
+    }
+
     // Deterministic sum of n doubles into out[0] (single block).
     __global__ void __launch_bounds__(256) sum_kernel(const double* __restrict__ v, int n, double* __restrict__ out)
     {

@@ -1536,6 +1536,29 @@ extern "C"
             zz += z[i] * z[i];
         }
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (N <= 1024 && (size_t) (2 * N + 1) * sizeof(double) <= ctx->pinned_bytes)
+        {
+            // small problems: one single-block launch, operands and results through the pinned staging area
+            TRY(ensure(ctx, ctx->comb, sizeof(double) * (size_t) (2 * N + 1)));
+            TRY(phase_begin(ctx, "map"));
+            std::memcpy(ctx->pinned, z, sizeof(double) * N);
+            CUDA_TRY(cudaMemcpyAsync(ctx->vec.p, ctx->pinned, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+            const size_t smem = sizeof(double) * (size_t) (3 * N + 32);
+            map_whitened_fused_kernel<<<1, 1024, smem, ctx->stream>>>(dp(ctx->L), N, ld, dp(ctx->vec), ptr<uint32_t>(ctx->pref_off),
+                                                                      ptr<uint32_t>(ctx->pref_idx), ctx->P, btl_scale,
+                                                                      ptr<uint32_t>(ctx->slot_off), ptr<uint32_t>(ctx->slot_list),
+                                                                      dp(ctx->contrib), dp(ctx->y), grad_z_out ? 1 : 0, dp(ctx->comb));
+            LAUNCH_CHECK();
+            ctx->has_alpha = false; // y changed under the cached alpha
+            TRY(phase_end(ctx, "map"));
+            CUDA_TRY(cudaMemcpyAsync(ctx->pinned, ctx->comb.p, sizeof(double) * (size_t) (2 * N + 1), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            const double* res = ctx->pinned;
+            if (grad_z_out) std::memcpy(grad_z_out, res + 1, sizeof(double) * N);
+            if (y_out) std::memcpy(y_out, res + 1 + N, sizeof(double) * N);
+            *f_out = res[0] + -0.5 * zz + -0.5 * ctx->logdet_host + -0.5 * N * std::log(2.0 * kPi);
+            return SLSGP_OK;
+        }
         TRY(phase_begin(ctx, "map"));
         const int blocks = (ld * 32 + 255) / 256;
         CUDA_TRY(cudaMemsetAsync(ctx->vec.p, 0, sizeof(double) * ld, ctx->stream));

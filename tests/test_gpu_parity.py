@@ -287,7 +287,7 @@ def test_device_maximiser_improves_on_the_sweep_and_reaches_a_stationary_point(c
     assert v0 == v_sweep
 
 
-@pytest.mark.parametrize("kt,D,N", [(S.SE, 4, 30), (S.MATERN, 8, 130)])
+@pytest.mark.parametrize("kt,D,N", [(S.SE, 4, 30), (S.MATERN, 8, 130), (S.SE, 6, 1024), (S.SE, 6, 1100)])   # fused kernel up to N = 1024
 def test_whitened_map_objective_is_the_same_function(ctx, kt, D, N):
     """slsgp_map_objective_pref_whitened(z) == slsgp_map_objective_pref(y = L z, fixed hyper-parameters); its gradient is
     L^T grad_y; slsgp_whiten inverts y = L z."""
