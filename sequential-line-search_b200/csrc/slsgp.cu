@@ -734,10 +734,15 @@ namespace
         if (n_shards == 0) return SLSGP_OK;
         static const bool overlap = !(std::getenv("SLSGP_PIPELINE") && std::atoi(std::getenv("SLSGP_PIPELINE")) == 0);
         static const bool kstar_overlap = std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) != 0;
-        cudaStream_t main = ctx->stream, pre = overlap ? ctx->pre_stream : main, post = overlap ? ctx->post_stream : main;
-        CUDA_TRY(cudaEventRecord(ctx->ev_start, main));
-        CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_start, 0));
-        CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_start, 0));
+        // a single shard has nothing to overlap with: keep it on one stream (one-candidate calls are latency-bound)
+        const bool   multi = overlap && n_shards > 1;
+        cudaStream_t main = ctx->stream, pre = multi ? ctx->pre_stream : main, post = multi ? ctx->post_stream : main;
+        if (multi)
+        {
+            CUDA_TRY(cudaEventRecord(ctx->ev_start, main));
+            CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_start, 0));
+            CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_start, 0));
+        }
 
         auto xq_of = [&](long long s) -> const double* {
             return job.d_Xq ? job.d_Xq + (size_t) (s * cap) * D : dp(ctx->Xq) + (size_t) (s & 1) * D * cap;
@@ -757,7 +762,7 @@ namespace
             // The k* generator can ride on `pre` too (SLSGP_KSTAR_OVERLAP=1). Default off: under the tensor load the chip is
             // power-capped, the two kernels share one budget, and the measured step is shorter when they run back to back.
             if (tensor && kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre));
-            CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
+            if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
             return SLSGP_OK;
         };
 
@@ -769,7 +774,7 @@ namespace
             if (s + 1 < n_shards) TRY(stage_in(s + 1));
 
             // ---- main
-            CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_in[b], 0));
+            if (multi) CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_in[b], 0));
             if (job.host_out && s >= 2) CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[b], 0)); // result buffer b drained
             SweepOut o;
             if (job.host_out)
@@ -808,12 +813,12 @@ namespace
                                                                                    s_lo, job.slice_best);
                 LAUNCH_CHECK();
             }
-            CUDA_TRY(cudaEventRecord(ctx->ev_main[b], main));
+            if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_main[b], main));
 
             // ---- out
             if (job.host_out)
             {
-                CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_main[b], 0));
+                if (multi) CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_main[b], 0));
                 const size_t sv = sizeof(double) * (size_t) Mc, sg = sv * D;
                 if (job.mu) CUDA_TRY(cudaMemcpyAsync(job.mu + m0, o.mu, sv, cudaMemcpyDeviceToHost, post));
                 if (job.sigma) CUDA_TRY(cudaMemcpyAsync(job.sigma + m0, o.sigma, sv, cudaMemcpyDeviceToHost, post));
@@ -821,10 +826,10 @@ namespace
                 if (job.dmu) CUDA_TRY(cudaMemcpyAsync(job.dmu + (size_t) m0 * D, o.dmu, sg, cudaMemcpyDeviceToHost, post));
                 if (job.dsigma) CUDA_TRY(cudaMemcpyAsync(job.dsigma + (size_t) m0 * D, o.dsigma, sg, cudaMemcpyDeviceToHost, post));
                 if (job.grad) CUDA_TRY(cudaMemcpyAsync(job.grad + (size_t) m0 * D, o.grad, sg, cudaMemcpyDeviceToHost, post));
-                CUDA_TRY(cudaEventRecord(ctx->ev_out[b], post));
+                if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_out[b], post));
             }
         }
-        if (job.host_out)
+        if (job.host_out && multi)
             for (long long s = std::max<long long>(0, n_shards - 2); s < n_shards; ++s)
                 CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[s & 1], 0));
         return SLSGP_OK;

@@ -162,8 +162,16 @@ namespace sequential_line_search
                     if (v > best) best = v, x0 = x;
                 }
             }
+            const DeviceRegressor* dev = device_of(regressor);
             return polish(
                 [&](const VectorXd& x, VectorXd& g) {
+                    if (dev) // value and gradient from ONE sweep call
+                    {
+                        double v = 0.0;
+                        g        = VectorXd::Zero(x.size());
+                        device_acq(*dev, x.data(), 1, func_type, hyperparam, &v, g.data());
+                        return v;
+                    }
                     g = CalcAcquisitionValueDerivative(regressor, x, func_type, hyperparam);
                     return CalcAcquisitionValue(regressor, x, func_type, hyperparam);
                 },
