@@ -428,6 +428,18 @@ namespace sequential_line_search
         {
             const int           nh = D + 2;
             std::vector<double> lo((size_t) nh, std::log(1e-08)), hi((size_t) nh, std::log(1e+01));
+            // The joint objective has a degenerate maximum where K_y collapses: -1/2 logdet K_y grows like
+            // N/2 log(1 / (a + b)) (or, with long length scales, (N - 1)/2 log(1 / b)) while the log-normal priors only cost
+            // (log x - mu)^2 / (2 var), so for N above ~100 a converged optimiser walks to the reference's lower bound 1e-8
+            // and returns a useless model with y = 0 (the reference never gets there only because LD_TNEWTON is cut off
+            // after `num_iters` evaluations). The signal variance and the noise level are therefore kept above their prior
+            // mean minus four prior standard deviations (a factor exp(-4 sqrt(var)), 1/7.4 for the default variance 0.25);
+            // the length scales and all upper bounds stay at the reference's box.
+            {
+                const double span = 4.0 * std::sqrt(m_kernel_hyperparams_prior_var);
+                lo[0] = std::max(lo[0], std::log(m_default_kernel_signal_var) - span);
+                lo[1] = std::max(lo[1], std::log(m_default_noise_level) - span);
+            }
             std::vector<double> x_full((size_t) N + nh), g_full((size_t) N + nh), y_at_best = y_cur;
             double              f_best = -std::numeric_limits<double>::infinity();
             bool                first  = true;

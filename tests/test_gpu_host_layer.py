@@ -101,9 +101,11 @@ def test_preference_regressor_map_is_a_maximiser_of_the_reference_objective(host
             away = sol * (1.0 + 0.05 * np.random.default_rng(9).standard_normal(len(sol)))
             assert S.rel_err(host.pref_objective(h, away)[1], ref.pref_objective(hr, away)[1]) < 1e-6
             # first-order optimality of the reference objective at our solution, bounds respected
-            lo = np.concatenate([np.full(N, -10.0), np.full(2 + D, 1e-8)]) if use_map else np.full(N, -10.0)
+            # (signal variance and noise level are held above exp(-4 sqrt(prior_var)) x their prior mean: DESIGN.md 4.4)
+            floor = np.exp(-4.0 * np.sqrt(pv))
+            lo = np.concatenate([np.full(N, -10.0), [a * floor, b * floor], np.full(D, 1e-8)]) if use_map else np.full(N, -10.0)
             hi = np.full(len(sol), 10.0)
-            pg = np.where(((sol <= lo) & (g_r < 0)) | ((sol >= hi) & (g_r > 0)), 0.0, g_r)
+            pg = np.where(((sol <= lo * (1 + 1e-9)) & (g_r < 0)) | ((sol >= hi) & (g_r > 0)), 0.0, g_r)
             if use_map:   # hyper-parameters live on a log scale (b ~ 5e-3): d F / d log x = x dF/dx
                 pg[N:] *= sol[N:]
             scale = max(1.0, abs(f_r))
