@@ -121,6 +121,14 @@ extern "C"
     slsgp_status slsgp_solve_alpha(slsgp_ctx* ctx, const double* y, double* alpha_out);
     slsgp_status slsgp_get_f_best(slsgp_ctx* ctx, double* f_best_out, int* index_out);
 
+    /* Append one data point (x[D], y_new) to a factored model in O(N^2): bordered update of K_y, L, L^-1, K_y^-1 and of
+     * the log-determinant, then alpha and f_best again if slsgp_solve_alpha had been called. Replaces the rebuild +
+     * `.inverse()` of the temporary GaussianProcessRegressor that FindNextPoints grows by one pending point per option
+     * (src/acquisition-function.cpp:281-296). Hyper-parameters, kernel and noise are those of the last slsgp_gram. The
+     * preference tuples are dropped. K_col_out: the new last column of K_y (N + 1 values) or NULL; Kinv_out: the new
+     * (N + 1) x (N + 1) inverse or NULL. SLSGP_ERR_NOT_SPD (model unchanged) when the Schur complement is not positive. */
+    slsgp_status slsgp_append_point(slsgp_ctx* ctx, const double* x, double y_new, double* K_col_out, double* Kinv_out);
+
     /* ---- K4: batched posterior and acquisition sweep --------------------------------------------------------------
      * For each of M query points (Xq: D x M, column-major, host memory):
      *   mu      Regressor::PredictMu               (src/preference-regressor.cpp:293-297)
@@ -218,7 +226,7 @@ extern "C"
     /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
     uint64_t     slsgp_launch_count(const slsgp_ctx* ctx);
     /* Milliseconds (CUDA events on the context's stream) spent in the most recent call of the named phase:
-     * "gram", "factor", "inverse", "alpha", "sweep", "map", "maximize". Returns < 0 for an unknown name. */
+     * "gram", "factor", "inverse", "alpha", "sweep", "map", "maximize", "append". Returns < 0 for an unknown name. */
     double       slsgp_last_phase_ms(const slsgp_ctx* ctx, const char* phase);
     /* Per-kernel device timing: while enabled, every launch of the named hot kernels is bracketed by CUDA events on
      * the context's stream. slsgp_profile_read synchronises, returns the summed duration and launch count of

@@ -36,6 +36,7 @@ _API = [
     ("slsgp_factor", C.c_int, [C.c_void_p, c_dp, c_dp]),
     ("slsgp_inverse", C.c_int, [C.c_void_p, c_dp]),
     ("slsgp_solve_alpha", C.c_int, [C.c_void_p, c_dp, c_dp]),
+    ("slsgp_append_point", C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, c_dp]),
     ("slsgp_get_f_best", C.c_int, [C.c_void_p, c_dp, C.POINTER(C.c_int)]),
     ("slsgp_posterior_batch", C.c_int, [C.c_void_p, c_dp, C.c_int64, c_dp, c_dp, c_dp, c_dp]),
     ("slsgp_acq_batch", C.c_int, [C.c_void_p, C.c_int, C.c_double, c_dp, C.c_int64, c_dp, c_dp]),
@@ -163,6 +164,17 @@ class Context:
         alpha = np.empty(self.N)
         self._check(self.lib.slsgp_solve_alpha(self.h, _p(y), _p(alpha)))
         return alpha
+
+    def append_point(self, x, y_new, want=True):
+        """slsgp_append_point: bordered O(N^2) update by one data point; returns (new K column, new Kinv) when asked."""
+        x = _f64(x)
+        if x.size != self.D:
+            raise ValueError("x has the wrong length")
+        kcol = np.empty(self.N + 1) if want else None
+        Kinv = np.empty((self.N + 1, self.N + 1), order="F") if want else None
+        self._check(self.lib.slsgp_append_point(self.h, _p(x), float(y_new), _p(kcol) if want else None, _p(Kinv) if want else None))
+        self.N += 1
+        return (kcol, Kinv) if want else None
 
     def f_best(self):
         f, i = C.c_double(), C.c_int()

@@ -15,6 +15,7 @@
 #include "gram.cuh"
 #include "map.cuh"
 #include "sweep.cuh"
+#include "append.cuh"
 #include "maximize.cuh"
 #include "tc_sweep.cuh"
 
@@ -1027,7 +1028,7 @@ extern "C"
         ctx->Mcap = 0; // sweep workspace depends on ld
         ctx->tc_Mcap = 0, ctx->tc_ready = false;
         const size_t ld = ctx->ld, mat = sizeof(double) * ld * ld;
-        TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) N * D));
+        TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) ctx->ld * D)); // room for slsgp_append_point up to ld points
         TRY(ensure(ctx, ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld));
         TRY(ensure(ctx, ctx->XT1, sizeof(double) * ld * ctx->ldx));
         TRY(ensure(ctx, ctx->theta, sizeof(double) * (D + 1)));
@@ -1098,6 +1099,91 @@ extern "C"
             CUDA_TRY(cudaMemcpyAsync(alpha_out, ctx->alpha.p, sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
         return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_append_point(slsgp_ctx* ctx, const double* x, double y_new, double* K_col_out, double* Kinv_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!x) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_append_point: x is null");
+        if (!ctx->has_factor) return fail(ctx, SLSGP_ERR_STATE, "slsgp_append_point before slsgp_factor");
+        const int N = ctx->N, D = ctx->D, ld = ctx->ld;
+        for (int d = 0; d < D; ++d)
+            if (!std::isfinite(x[d])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_append_point: non-finite coordinate");
+        if (!std::isfinite(y_new)) return fail(ctx, SLSGP_ERR_NAN, "slsgp_append_point: non-finite y");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const bool had_alpha = ctx->has_alpha;
+
+        if (N + 1 > ld)
+        {
+            // the padded leading dimension is exhausted (once every 64 appended points): rebuild at the next size
+            std::vector<double> Xh((size_t) (N + 1) * D), yh((size_t) N + 1);
+            CUDA_TRY(cudaMemcpyAsync(Xh.data(), ctx->X.p, sizeof(double) * (size_t) N * D, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(yh.data(), ctx->y.p, sizeof(double) * (size_t) N, cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            for (int d = 0; d < D; ++d) Xh[(size_t) N * D + d] = x[d];
+            yh[(size_t) N]                  = y_new;
+            const std::vector<double> theta = ctx->theta_host;
+            const int                 kt    = ctx->kernel_type;
+            const double              noise = ctx->noise;
+            TRY(slsgp_set_data(ctx, Xh.data(), N + 1, D));
+            TRY(do_gram(ctx, kt, theta.data(), noise));
+            TRY(do_factor(ctx, nullptr));
+            TRY(do_inverse(ctx));
+            if (had_alpha)
+            {
+                CUDA_TRY(cudaMemcpyAsync(ctx->y.p, yh.data(), sizeof(double) * (size_t) (N + 1), cudaMemcpyHostToDevice, ctx->stream));
+                TRY(do_alpha(ctx));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            }
+        }
+        else
+        {
+            TRY(do_inverse(ctx)); // W and Kinv of the current model
+            TRY(phase_begin(ctx, "append"));
+            double* h = ctx->pinned;
+            for (int d = 0; d < D; ++d) h[d] = x[d];
+            h[D] = y_new;
+            CUDA_TRY(cudaMemcpyAsync(dp(ctx->X) + (size_t) N * D, h, sizeof(double) * D, cudaMemcpyHostToDevice, ctx->stream));
+            CUDA_TRY(cudaMemsetAsync(ctx->info.p, 0, sizeof(int), ctx->stream));
+            double *k = dp(ctx->vec), *l = dp(ctx->Kalpha), *u = dp(ctx->grad_y);
+            append_kvec_kernel<<<(ld + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), N, D, ld, dp(ctx->theta), dp(ctx->inv_l), ctx->noise,
+                                                                         ctx->kernel_type, k, dp(ctx->scalars));
+            LAUNCH_CHECK();
+            const int blocks = (ld * 32 + 255) / 256;
+            gemv_kernel<false><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->W), ld, ld, k, l, 1); // l = W k   (rows j <= i)
+            LAUNCH_CHECK();
+            gemv_kernel<true><<<blocks, 256, 0, ctx->stream>>>(dp(ctx->W), ld, ld, l, u, 1);  // u = W^T l (columns j >= i)
+            LAUNCH_CHECK();
+            append_rows_kernel<<<1, 1024, 0, ctx->stream>>>(N, ld, l, u, dp(ctx->L), dp(ctx->W), dp(ctx->scalars), ptr<int>(ctx->info));
+            LAUNCH_CHECK();
+            int    info = 0;
+            double s    = 0.0;
+            CUDA_TRY(cudaMemcpyAsync(&info, ctx->info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaMemcpyAsync(&s, dp(ctx->scalars) + 10, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            if (info != 0)
+                return fail(ctx, SLSGP_ERR_NOT_SPD,
+                            "slsgp_append_point: non-positive Schur complement " + std::to_string(s) + " (the model is unchanged)");
+            append_commit_kernel<<<dim3((N + 1 + 255) / 256, N + 1), 256, 0, ctx->stream>>>(N, ld, k, u, dp(ctx->scalars), dp(ctx->K),
+                                                                                          dp(ctx->Kinv));
+            LAUNCH_CHECK();
+            CUDA_TRY(cudaMemcpyAsync(dp(ctx->y) + N, h + D, sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+            ctx->N = N + 1;
+            ctx->logdet_host += std::log(s);
+            ctx->P = 0, ctx->pref_total = 0; // the per-point tuple lists were built for N points
+            ctx->tc_ready  = false;
+            ctx->has_alpha = false;
+            pack_x_kernel<<<(ld + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), ctx->N, D, ld, ctx->Dp, ctx->ldx, dp(ctx->Xpad), dp(ctx->XT1));
+            LAUNCH_CHECK();
+            TRY(phase_end(ctx, "append"));
+            if (had_alpha) TRY(do_alpha(ctx));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream)); // the pinned staging area is reused by later calls
+        }
+        if (K_col_out)
+            CUDA_TRY(cudaMemcpyAsync(K_col_out, dp(ctx->K) + (size_t) (ctx->N - 1) * ctx->ld, sizeof(double) * (size_t) ctx->N,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+        if (K_col_out) CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        return copy_matrix_out(ctx, ctx->Kinv, Kinv_out, ctx->N);
     }
 
     slsgp_status slsgp_get_f_best(slsgp_ctx* ctx, double* f_best_out, int* index_out)

@@ -135,6 +135,21 @@ namespace sequential_line_search
                                  double                 noise_hyperparam,
                                  const KernelType       kernel_type = KernelType::ArdMatern52Kernel);
 
+        // Additions. DeviceOnly: the same model without the host copies m_K_y / m_K_y_inv (they stay empty), for
+        // regressors that only serve predictions, like the temporary one inside FindNextPoints.
+        struct DeviceOnly
+        {
+        };
+        GaussianProcessRegressor(const Eigen::MatrixXd& X,
+                                 const Eigen::VectorXd& y,
+                                 const Eigen::VectorXd& kernel_hyperparams,
+                                 double                 noise_hyperparam,
+                                 const KernelType       kernel_type,
+                                 DeviceOnly);
+        // Grows the model by one observation in O(N^2) (slsgp_append_point: bordered update of the factor and the inverse)
+        // instead of constructing a new regressor; hyper-parameters stay as they are.
+        void AppendPoint(const Eigen::VectorXd& x, double y);
+
         Eigen::MatrixXd m_K_y;
         Eigen::MatrixXd m_K_y_inv;
 

@@ -191,7 +191,11 @@ namespace sequential_line_search
             const double   noise = regressor.GetNoiseHyperparam();
             // As in the reference (:259-260) the temporary regressor is built with GaussianProcessRegressor's DEFAULT
             // kernel type (Matern 5/2) whatever kernel `regressor` uses; kept for parity.
-            std::unique_ptr<GaussianProcessRegressor> temp(new GaussianProcessRegressor(regressor.GetLargeX(), regressor.GetSmallY(), theta, noise));
+            // It lives on the device only and grows by a bordered O(N^2) update per pending point
+            // where the reference constructs, and inverts, a new regressor per option.
+            std::unique_ptr<GaussianProcessRegressor> temp(new GaussianProcessRegressor(regressor.GetLargeX(), regressor.GetSmallY(), theta, noise,
+                                                                                        KernelType::ArdMatern52Kernel,
+                                                                                        GaussianProcessRegressor::DeviceOnly()));
 
             double f_best = 0.0;
             {
@@ -258,13 +262,7 @@ namespace sequential_line_search
                 if (points.size() != num_points)
                 {
                     // the pending point joins the temporary model with its predicted value (which never influences sigma)
-                    const long N = temp->GetLargeX().cols();
-                    MatrixXd   new_X = MatrixXd::Zero(D, N + 1);
-                    VectorXd   new_y = VectorXd::Zero(N + 1);
-                    for (long j = 0; j < N; ++j) new_X.col(j) = temp->GetLargeX().col(j), new_y(j) = temp->GetSmallY()(j);
-                    new_X.col(N) = x_star;
-                    new_y(N)     = temp->PredictMu(x_star);
-                    temp.reset(new GaussianProcessRegressor(new_X, new_y, theta, noise));
+                    temp->AppendPoint(x_star, temp->PredictMu(x_star));
                 }
             }
             return points;

@@ -87,6 +87,15 @@ extern "C"
     {
         return guarded([&]() -> void* { return new GaussianProcessRegressor(matrix(X, D, N), vector(y, N), kernel_type(kt)); }, nullptr);
     }
+    int b200_gpr_append_point(void* h, int D, const double* x, double y)
+    {
+        return guarded(
+            [&]() {
+                static_cast<GaussianProcessRegressor*>(h)->AppendPoint(vector(x, D), y);
+                return 0;
+            },
+            1);
+    }
     void        b200_gpr_destroy(void* h) { delete static_cast<GaussianProcessRegressor*>(h); }
     const void* b200_gpr_regressor(void* h) { return static_cast<const Regressor*>(static_cast<GaussianProcessRegressor*>(h)); }
     void        b200_gpr_get_state(void* hv, double* K_y, double* K_y_inv, double* theta, double* b)

@@ -208,6 +208,43 @@ namespace sequential_line_search
         FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, &m_K_y, &m_K_y_inv, nullptr);
     }
 
+    GaussianProcessRegressor::GaussianProcessRegressor(const MatrixXd& X, const VectorXd& y, const VectorXd& kernel_hyperparams,
+                                                       double noise_hyperparam, const KernelType kernel_type, DeviceOnly)
+        : DeviceRegressor(kernel_type), m_X(X), m_y(y), m_kernel_hyperparams(kernel_hyperparams), m_noise_hyperparam(noise_hyperparam)
+    {
+        if (X.rows() == 0 || X.cols() == 0) return;
+        FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, nullptr, nullptr, nullptr);
+    }
+
+    void GaussianProcessRegressor::AppendPoint(const VectorXd& x, double y)
+    {
+        if (!m_fitted) throw std::logic_error("AppendPoint needs a fitted regressor");
+        const long D = m_X.rows(), N = m_X.cols();
+        if (x.size() != D) throw std::invalid_argument("the new point must have the dimension of the data");
+        const bool mirror = m_K_y.rows() == N && m_K_y_inv.rows() == N; // false for DeviceOnly regressors
+        VectorXd   k_col  = VectorXd::Zero(N + 1);
+        MatrixXd   Kinv;
+        if (mirror) Kinv = MatrixXd::Zero(N + 1, N + 1);
+        {
+            std::lock_guard<std::mutex> lock(*m_mutex);
+            check(m_device.get(), slsgp_append_point(m_device.get(), x.data(), y, mirror ? k_col.data() : nullptr, mirror ? Kinv.data() : nullptr),
+                  "slsgp_append_point");
+        }
+        MatrixXd new_X = MatrixXd::Zero(D, N + 1);
+        VectorXd new_y = VectorXd::Zero(N + 1);
+        for (long j = 0; j < N; ++j) new_X.col(j) = m_X.col(j), new_y(j) = m_y(j);
+        new_X.col(N) = x, new_y(N) = y;
+        m_X = new_X, m_y = new_y;
+        if (mirror)
+        {
+            MatrixXd K = MatrixXd::Zero(N + 1, N + 1);
+            for (long j = 0; j < N; ++j)
+                for (long i = 0; i < N; ++i) K(i, j) = m_K_y(i, j);
+            for (long i = 0; i <= N; ++i) K(i, N) = k_col(i), K(N, i) = k_col(i);
+            m_K_y = K, m_K_y_inv = Kinv;
+        }
+    }
+
     // Maximise log p(y | X, a, b, r) + log-normal priors over (a, b, r_1..r_D) in [1e-8, 50]^(D+2), starting from the
     // prior means (:274-299). The reference runs DIRECT (300 evaluations) then LD_TNEWTON (1000); here a scrambled
     // low-discrepancy probe of the box in log-space picks extra starting points and the bound-constrained quasi-Newton

@@ -18,7 +18,7 @@ _lib = None
 _DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value")
 _POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
 HOST_SYMBOLS = [
-    "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy",
+    "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy", "b200_gpr_append_point",
     "b200_gpr_regressor", "b200_gpr_get_state", "b200_pref_create", "b200_pref_create_warm", "b200_pref_destroy", "b200_pref_regressor",
     "b200_pref_objective", "b200_pref_num_map_evaluations", "b200_pref_get_state", "b200_pref_find_arg_max",
     "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
@@ -94,6 +94,10 @@ class Host:
             h = self.lib.b200_gpr_create(kt, D, N, _p(X), _p(y), _p(_f64(theta)), C.c_double(b))
         self._ok(h)
         return C.c_void_p(h)
+
+    def gpr_append_point(self, h, x, y):
+        x = _f64(x)
+        self._ok(self.lib.b200_gpr_append_point(h, x.size, _p(x), C.c_double(y)) == 0)
 
     def gpr_destroy(self, h):
         self.lib.b200_gpr_destroy(h)

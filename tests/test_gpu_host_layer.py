@@ -60,6 +60,32 @@ def test_gaussian_process_regressor_matches_reference(host, ref, kt, D, N, kind,
         ref.gpr_destroy(hr)
 
 
+@pytest.mark.parametrize("kt,D,N0,n_add", [(S.SE, 6, 40, 4), (S.MATERN, 5, 62, 5)])
+def test_append_point_equals_the_reference_regressor_of_the_grown_data(host, ref, kt, D, N0, n_add):
+    """GaussianProcessRegressor::AppendPoint (addition; the O(N^2) replacement of the rebuild at
+    src/acquisition-function.cpp:281-296) against the reference regressor constructed on all the points."""
+    N = N0 + n_add
+    X, theta, b = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed"), 0.005
+    y = S.make_y(X)
+    h, hr = host.gpr_create(kt, X[:, :N0], y[:N0], theta, b), ref.gpr_create(kt, X, y, theta, b)
+    try:
+        for n in range(N0, N):
+            host.gpr_append_point(h, X[:, n], y[n])
+        st = host.gpr_state(h, N, D)
+        K_r, Kinv_r = ref.gpr_state(hr, N)
+        assert S.rel_err(st["K"], K_r) < 1e-12 and S.rel_err(st["Kinv"], Kinv_r) < RT
+        reg, reg_r = host.gpr_regressor(h), ref.gpr_regressor(hr)
+        np.testing.assert_array_equal(host.x_best(reg, D), ref.x_best(reg_r, D))
+        Q = S.make_queries(10, D)
+        for m in range(Q.shape[1]):
+            got, want = host.predict(reg, Q[:, m]), ref.predict(reg_r, Q[:, m])
+            for i in range(4):
+                assert np.max(np.abs(np.asarray(got[i]) - np.asarray(want[i]))) < RT * max(1.0, np.max(np.abs(want[i]))), (m, i)
+    finally:
+        host.gpr_destroy(h)
+        ref.gpr_destroy(hr)
+
+
 def test_calc_large_ky_free_function(host, ref):
     X, theta = S.make_X(33, 5, "sls"), S.make_theta(5, "perturbed")
     for kt in (S.SE, S.MATERN):

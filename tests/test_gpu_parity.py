@@ -337,3 +337,57 @@ def test_new_entry_points_validate_their_arguments(ctx, slsb):
         assert v0 == v_sweep and v >= v_sweep and x.shape == (3,)
     finally:
         c.close()
+
+
+@pytest.mark.parametrize("kt,D,N0,n_add", [(S.SE, 5, 40, 6), (S.MATERN, 8, 61, 8), (S.SE, 16, 190, 5), (S.MATERN, 3, 1, 3)])
+def test_append_point_equals_a_fresh_fit(ctx, oracle, kt, D, N0, n_add):
+    """slsgp_append_point (bordered O(N^2) update; crosses the 64-row padding at 61 + 8 and 190 + 5) against the
+    oracle's from-scratch model of the grown data set after every appended point."""
+    N = N0 + n_add
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    y, noise = S.make_y(X), 0.005
+    ctx.fit(X[:, :N0], kt, theta, noise, y[:N0])
+    Q = S.make_queries(40, D)
+    for n in range(N0, N):
+        kcol, Kinv = ctx.append_point(X[:, n], y[n])
+        K_o = oracle.large_ky(kt, X[:, :n + 1], theta, noise)
+        check("K column", kcol, K_o[:, n], 1e-13)
+        check("Kinv", Kinv, oracle.inverse(K_o), 1e-7)
+        assert np.array_equal(Kinv, Kinv.T)
+        m = oracle.model(kt, X[:, :n + 1], theta, noise, y[:n + 1])
+        i_best, f_best = oracle.f_best(m)
+        f, i = ctx.f_best()
+        assert i == i_best
+        check("f_best", f, f_best, 1e-9)
+        mu, sigma, dmu, dsg = ctx.posterior_batch(Q)
+        want = [oracle.predict(m, Q[:, j]) for j in range(Q.shape[1])]
+        check("mu", mu, [w[0] for w in want])
+        check("sigma", sigma, [w[1] for w in want], RT, atol=1e-9)
+    # the grown state behaves like a fresh fit of all N points
+    val_inc, grad_inc = ctx.acq_batch(0, 0.0, Q)
+    ctx.fit(X, kt, theta, noise, y)
+    val_new, grad_new = ctx.acq_batch(0, 0.0, Q)
+    check("EI after appends", val_inc, val_new, 1e-7, atol=1e-12)
+    check("grad EI after appends", grad_inc, grad_new, 1e-6, atol=1e-10)
+
+
+def test_append_point_failure_keeps_the_model(ctx):
+    """An exact duplicate with zero noise makes the bordered matrix singular: the Schur complement is zero up to rounding.
+    Whether rounding leaves it positive or not, a refused append must leave the model as it was."""
+    X, theta = S.make_X(20, 4, "uniform"), S.make_theta(4, "default")
+    y = S.make_y(X)
+    ctx.fit(X, S.SE, theta, 0.0, y)
+    Q = S.make_queries(10, 4)
+    before = ctx.posterior_batch(Q)
+    try:
+        ctx.append_point(X[:, 3], 0.1)
+    except Exception as e:
+        assert "Schur" in str(e) and ctx.N == 20
+        for a, b in zip(before, ctx.posterior_batch(Q)):
+            assert np.array_equal(a, b)
+    else:
+        assert ctx.N == 21
+    with pytest.raises(Exception):
+        ctx.append_point(np.full(4, np.nan), 0.1)
+    with pytest.raises(ValueError):
+        ctx.append_point(np.zeros(3), 0.1)
