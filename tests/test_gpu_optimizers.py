@@ -77,3 +77,23 @@ def test_preferential_bayesian_optimizer_loop(sls):
     # custom feedback (points that were never options)
     opt.submit_custom_feedback_data(np.array([0.3, 0.3]), [np.array([0.9, 0.9]), np.array([0.1, 0.8])])
     assert opt.get_raw_data_points().shape[0] == 2
+
+
+def test_the_reference_nd_demo_source_runs_unmodified_on_the_host_layer(tmp_path):
+    """Source-level drop-in: oracle/_ref/sls_nd_demo_dropin is the reference's own demos/sequential_line_search_nd/main.cpp
+    (D = 8, 3 trials x 10 iterations, MAP hyper-parameters), compiled WITHOUT changes against this repository's headers
+    and libsls_b200_host.so by oracle/Makefile (`dropin`). It must run, converge and write its three CSV reports."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "sls_nd_demo_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/sls_nd_demo_dropin was not built (the reference tree is needed at build time)")
+    res = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    maxima = [float(v) for v in re.findall(r"Found maximum: ([0-9.eE+-]+)", res.stdout)]
+    assert len(maxima) == 3 and min(maxima) > 0.7, maxima      # f(x) = exp(-|x - 0.4|^2), maximum 1
+    for name in ("objective_values.csv", "residual_norms.csv", "elapsed_times.csv"):
+        rows = (tmp_path / name).read_text().strip().split("\n")
+        assert len(rows) == 10 and all(len(r.split(",")) == 3 for r in rows), name
+    obj = np.array([[float(v) for v in r.split(",")] for r in (tmp_path / "objective_values.csv").read_text().strip().split("\n")])
+    assert np.all(obj[-1] >= obj[0] - 1e-12)                    # the chosen slider positions improve over the run
