@@ -97,3 +97,19 @@ def test_the_reference_nd_demo_source_runs_unmodified_on_the_host_layer(tmp_path
         assert len(rows) == 10 and all(len(r.split(",")) == 3 for r in rows), name
     obj = np.array([[float(v) for v in r.split(",")] for r in (tmp_path / "objective_values.csv").read_text().strip().split("\n")])
     assert np.all(obj[-1] >= obj[0] - 1e-12)                    # the chosen slider positions improve over the run
+
+
+def test_the_reference_bo_1d_demo_source_runs_unmodified_on_the_host_layer(tmp_path):
+    """oracle/_ref/bo_1d_demo_dropin: the reference's demos/bayesian_optimization_1d/{main,core}.cpp, unmodified, on this
+    repository's GaussianProcessRegressor (hyper-parameters by MAP of the marginal likelihood) + acquisition_func::FindNextPoint.
+    f(x) = 1 - 1.5 x sin(13 x) on [0, 1]: global maximum 2.274 at x = 0.852, a local one of 1.556 at x = 0.378."""
+    import re
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "bo_1d_demo_dropin")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/bo_1d_demo_dropin was not built (the reference tree is needed at build time)")
+    res = subprocess.run([exe], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    maxima = [float(v) for v in re.findall(r"Found maximum: ([0-9.eE+-]+)", res.stdout)]
+    assert len(maxima) == 5 and min(maxima) > 1.5, maxima                 # 5 trials x 15 iterations, every one at a maximum
+    assert sum(m > 2.25 for m in maxima) >= 3, maxima                       # most at the global one
