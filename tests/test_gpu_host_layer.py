@@ -249,3 +249,59 @@ def test_warm_started_map_reaches_the_same_optimum_in_fewer_evaluations(host):
     finally:
         for h in (prev, cold, warm):
             host.pref_destroy(h)
+
+
+def test_regressor_lifetimes_do_not_leak_device_memory(host):
+    """The reference rebuilds its regressors every iteration (src/sequential-line-search.cpp:94-103); here each one borrows a
+    device context from a pool. 300 lifetimes of alternating sizes must leave the free device memory where it was."""
+    import torch
+    rng = np.random.default_rng(0)
+
+    def lifetime(i):
+        N, D = (20, 4) if i % 2 else (150, 7)
+        X = rng.random((D, N))
+        h = host.gpr_create(S.SE, X, S.make_y(X), S.make_theta(D, "default"), 0.005)
+        host.predict(host.gpr_regressor(h), X[:, 0])
+        host.gpr_destroy(h)
+
+    for i in range(20):          # fill the pool / reach the steady state
+        lifetime(i)
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info(0)
+    for i in range(300):
+        lifetime(i)
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info(0)
+    assert free0 - free1 < 8 << 20, (free0, free1)
+
+
+def test_concurrent_predictions_on_one_regressor_are_serialised(host):
+    """With the reference's parallel multi-start search, hardware_concurrency threads call Predict* on ONE shared const
+    Regressor (src/acquisition-function.cpp:125-144). Calls on a context are serialised inside the host layer."""
+    import threading
+    X = S.make_X(120, 6, "sls")
+    h = host.gpr_create(S.MATERN, X, S.make_y(X), S.make_theta(6, "perturbed"), 0.005)
+    try:
+        reg, Q = host.gpr_regressor(h), S.make_queries(16, 6)
+        want = [host.predict(reg, Q[:, m]) for m in range(Q.shape[1])]
+        errors = []
+
+        def worker(t):
+            try:
+                for rep in range(20):
+                    m = (t + rep) % Q.shape[1]
+                    got = host.predict(reg, Q[:, m])
+                    for a, b in zip(got, want[m]):
+                        if not np.array_equal(np.asarray(a), np.asarray(b)):
+                            errors.append((t, rep, m))
+            except Exception as e:  # noqa: BLE001
+                errors.append(repr(e))
+
+        threads = [threading.Thread(target=worker, args=(t,)) for t in range(8)]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        assert not errors, errors[:3]
+    finally:
+        host.gpr_destroy(h)
