@@ -125,9 +125,9 @@ namespace slsgp
 
     // Same contract as gemm64_kernel (64 x 64 output tile per CTA, the triangular k-range pruning, batching, in-place
     // panel updates), with the inner product on the FP64 tensor pipe: 8 warps, warp = 32 (m) x 16 (n) = 4 x 2 DMMA tiles,
-    // 16-deep shared-memory stages (row stride 68 doubles: the fragment reads of a half-warp hit 16 distinct 8-byte
-    // slots), the next stage's global loads issued into registers before the current stage is multiplied.
-    constexpr int DMMA_LDS = TILE + 4;
+    // 16-deep double-buffered shared-memory stages (one barrier per stage), the next stage's global loads issued into
+    // registers before the current stage is multiplied and parked in the other buffer after it.
+    constexpr int DMMA_LDS = TILE + 4, DMMA_LDK = 16 + 4;
     template <bool TA, bool TB> __global__ void __launch_bounds__(256) gemm64_dmma_kernel(const GemmArgs g)
     {
         const int tm = blockIdx.x, tn = blockIdx.y, z = blockIdx.z;
@@ -143,8 +143,12 @@ namespace slsgp
         if (g.k_lo_mode == 2) k_lo = max(tm, tn) * TILE;
         if (g.k_hi_mode == 1) k_hi = min(g.k, (tm + 1) * TILE);
 
-        __shared__ double As[16][DMMA_LDS]; // As[k][m]
-        __shared__ double Bs[16][DMMA_LDS]; // Bs[k][n]
+        // Two stages per operand. An operand that arrives k-contiguous from global memory (A^T, or B as stored) is kept
+        // [row][k] with a row stride of 20 doubles, one that arrives row-contiguous [k][row] with a stride of 68: in both
+        // forms the 16 lanes of a half-warp store, and later read their fragments from, 16 distinct 8-byte banks.
+        constexpr int ST_KM = 16 * DMMA_LDS, ST_MK = TILE * DMMA_LDK, ST = ST_MK > ST_KM ? ST_MK : ST_KM;
+        __shared__ double As[2][ST];
+        __shared__ double Bs[2][ST];
 
         const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
         const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16; // this warp's corner inside the tile
@@ -171,42 +175,51 @@ namespace slsgp
                     rb[r] = B[(size_t) (tn * TILE + (e & 63)) + (size_t) (k0 + (e >> 6)) * g.ldb];
             }
         };
-        const auto stash = [&]() {
+        const auto stash = [&](int buf) {
 #pragma unroll
             for (int r = 0; r < 4; ++r)
             {
                 const int e = tid + r * 256;
                 if (!TA)
-                    As[e >> 6][e & 63] = ra[r];
+                    As[buf][(e >> 6) * DMMA_LDS + (e & 63)] = ra[r];
                 else
-                    As[e & 15][e >> 4] = ra[r];
+                    As[buf][(e >> 4) * DMMA_LDK + (e & 15)] = ra[r];
                 if (!TB)
-                    Bs[e & 15][e >> 4] = rb[r];
+                    Bs[buf][(e >> 4) * DMMA_LDK + (e & 15)] = rb[r];
                 else
-                    Bs[e >> 6][e & 63] = rb[r];
+                    Bs[buf][(e >> 6) * DMMA_LDS + (e & 63)] = rb[r];
             }
         };
 
-        if (k_lo < k_hi) fetch(k_lo);
+        int buf = 0;
+        if (k_lo < k_hi)
+        {
+            fetch(k_lo);
+            stash(0);
+        }
+        __syncthreads();
         for (int k0 = k_lo; k0 < k_hi; k0 += 16)
         {
-            stash();
-            __syncthreads();
-            if (k0 + 16 < k_hi) fetch(k0 + 16); // in flight while this stage is multiplied
+            const bool more = k0 + 16 < k_hi;
+            if (more) fetch(k0 + 16); // in flight while this stage is multiplied
+            const double* as = As[buf];
+            const double* bs = Bs[buf];
 #pragma unroll
             for (int ks = 0; ks < 16; ks += 4)
             {
                 double a[4], b[2];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) a[i] = As[ks + lc][wm + i * 8 + lr];
+                for (int i = 0; i < 4; ++i) a[i] = TA ? as[(wm + i * 8 + lr) * DMMA_LDK + ks + lc] : as[(ks + lc) * DMMA_LDS + wm + i * 8 + lr];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) b[j] = Bs[ks + lc][wn + j * 8 + lr];
+                for (int j = 0; j < 2; ++j) b[j] = TB ? bs[(ks + lc) * DMMA_LDS + wn + j * 8 + lr] : bs[(wn + j * 8 + lr) * DMMA_LDK + ks + lc];
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
 #pragma unroll
                     for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
             }
+            if (more) stash(buf ^ 1); // the stage the previous iteration read; every warp is past that iteration's barrier
             __syncthreads();
+            buf ^= 1;
         }
 
 #pragma unroll
