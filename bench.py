@@ -374,7 +374,7 @@ def main_graft(args):
         sweep_total = sum(v[0] for v in prof.values())
         if args.mode == "fp64":
             kname = "gemm64_dmma_kernel<NN> (beta = K^-1 k*, mma.sync.m8n8k4.f64)"
-            peak, peak_src = 37.0, "nominal B200 dense FP64 (datasheet; no FP64 figure in MEASURED_PEAKS.json),"
+            peak, peak_src = 35.46, "measured cuBLAS DGEMM n=8192 on this pool (profiles/r01j_fp64_library_points.txt; datasheet 37; no FP64 figure in MEASURED_PEAKS.json),"
             note = "the kernel runs on the FP64 tensor pipe (DMMA)"
         else:
             kname = (f"tc_sweep_gemm_kernel<20, 2> (tcgen05.mma cta_group::2 kind::f16, 256x256x16, {PASSES[args.mode]} split-fp16 "
