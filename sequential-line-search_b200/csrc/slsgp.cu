@@ -16,6 +16,7 @@
 #include "map.cuh"
 #include "sweep.cuh"
 #include "append.cuh"
+#include "small.cuh"
 #include "maximize.cuh"
 #include "tc_sweep.cuh"
 
@@ -1501,6 +1502,23 @@ extern "C"
     // Shared GP part of both objectives, for y already in ctx->y and the model (K, L, [Kinv]) current:
     //   alpha = Kinv y; returns -1/2 y.alpha - 1/2 logdet - N/2 log(2 pi); if want_hyper also the data-fit part of the
     //   gradient wrt (a, b, l_1..l_D) into g_hyper (D + 2 values, reference ordering a, b, r).
+    // host part of the GP term: value and hyper-gradient from the device scalars (y.alpha, alpha.alpha, tr Kinv) and g_l
+    static void gp_term_host(const slsgp_ctx* ctx, double logdet, const double* sc, const double* gl, bool want_hyper, double* value,
+                             double* g_hyper)
+    {
+        const int    N = ctx->N, D = ctx->D;
+        const double y_alpha = sc[0], alpha_alpha = sc[1], tr_kinv = sc[2];
+        *value = -0.5 * y_alpha + -0.5 * logdet + -0.5 * N * std::log(2.0 * kPi);
+        if (want_hyper)
+        {
+            const double a = ctx->theta_host[0], b = ctx->noise;
+            // dK/da = K_f / a and K_f = K_y - b I:  1/2 alpha^T K_f alpha - 1/2 tr(Kinv K_f), all over a
+            g_hyper[0] = 0.5 / a * ((y_alpha - b * alpha_alpha) - (N - b * tr_kinv));
+            g_hyper[1] = 0.5 * alpha_alpha - 0.5 * tr_kinv; // dK/db = I
+            for (int t = 0; t < D; ++t) g_hyper[2 + t] = gl[(size_t) t];
+        }
+    }
+
     static slsgp_status gp_term(slsgp_ctx* ctx, double logdet, bool want_hyper, double* value, double* g_hyper)
     {
         const int ld = ctx->ld, N = ctx->N, D = ctx->D;
@@ -1524,16 +1542,70 @@ extern "C"
         std::vector<double> gl((size_t) D);
         if (want_hyper) CUDA_TRY(cudaMemcpyAsync(gl.data(), ctx->g_l.p, sizeof(double) * (size_t) D, cudaMemcpyDeviceToHost, ctx->stream));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        const double y_alpha = sc[0], alpha_alpha = sc[1], tr_kinv = sc[2];
-        *value = -0.5 * y_alpha + -0.5 * logdet + -0.5 * N * std::log(2.0 * kPi);
-        if (want_hyper)
+        gp_term_host(ctx, logdet, sc, gl.data(), want_hyper, value, g_hyper);
+        return SLSGP_OK;
+    }
+
+    // Small models (small.cuh): hyper-parameters and y up, ONE launch, scalars down. Leaves the context exactly as
+    // slsgp_gram + slsgp_factor + slsgp_inverse + slsgp_solve_alpha would (K, L, W, Kinv, alpha, f_best, flags).
+    static bool small_model_applies(const slsgp_ctx* ctx)
+    {
+        static const bool enabled = !(std::getenv("SLSGP_SMALL_FUSED") && std::atoi(std::getenv("SLSGP_SMALL_FUSED")) == 0);
+        return enabled && ctx->has_data && ctx->ld == SMALL_N && ctx->D <= SMALL_DMAX;
+    }
+
+    constexpr int kSmallOutOffset = 1024; // doubles into the pinned staging area: results of the small-model kernel
+
+    // Enqueue: ONE host-to-device copy of [theta | 1 / l | y], the kernel, ONE device-to-host copy of its results.
+    static slsgp_status small_model_launch(slsgp_ctx* ctx, int kernel_type, const double* theta, double noise, const double* y_host, bool want_hyper)
+    {
+        const int N = ctx->N, D = ctx->D;
+        if (kernel_type != 0 && kernel_type != 1) return fail(ctx, SLSGP_ERR_INVALID, "unknown kernel_type");
+        if (!std::isfinite(noise)) return fail(ctx, SLSGP_ERR_NAN, "non-finite noise level");
+        for (int i = 0; i <= D; ++i)
+            if (!std::isfinite(theta[i])) return fail(ctx, SLSGP_ERR_NAN, "non-finite kernel hyper-parameter");
+        ctx->theta_host.assign(theta, theta + D + 1);
+        ctx->kernel_type = kernel_type, ctx->noise = noise;
+        ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        ctx->tc_ready = false;
+        double* h = ctx->pinned; // consumed before the API call returns (every caller ends in a stream synchronisation)
+        for (int i = 0; i <= D; ++i) h[i] = theta[i];
+        for (int i = 0; i < D; ++i) h[D + 1 + i] = 1.0 / theta[1 + i];
+        for (int i = 0; i < N; ++i) h[2 * D + 1 + i] = y_host[i];
+        double *in_dev = dp(ctx->Ymat), *out_dev = dp(ctx->T);
+        CUDA_TRY(cudaMemcpyAsync(in_dev, h, sizeof(double) * (size_t) (2 * D + 1 + N), cudaMemcpyHostToDevice, ctx->stream));
+        static bool attr[64] = {};
+        if (!attr[ctx->device & 63])
         {
-            const double a = ctx->theta_host[0], b = ctx->noise;
-            // dK/da = K_f / a and K_f = K_y - b I:  1/2 alpha^T K_f alpha - 1/2 tr(Kinv K_f), all over a
-            g_hyper[0] = 0.5 / a * ((y_alpha - b * alpha_alpha) - (N - b * tr_kinv));
-            g_hyper[1] = 0.5 * alpha_alpha - 0.5 * tr_kinv; // dK/db = I
-            for (int t = 0; t < D; ++t) g_hyper[2 + t] = gl[(size_t) t];
+            CUDA_TRY(cudaFuncSetAttribute(small_model_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMALL_SMEM_BYTES));
+            attr[ctx->device & 63] = true;
         }
+        SmallModelArgs a;
+        a.X = dp(ctx->X), a.in = in_dev;
+        a.N = N, a.D = D, a.kernel_type = kernel_type, a.want_hyper = want_hyper ? 1 : 0, a.noise = noise;
+        a.theta = dp(ctx->theta), a.inv_l = dp(ctx->inv_l), a.y = dp(ctx->y);
+        a.K = dp(ctx->K), a.L = dp(ctx->L), a.W = dp(ctx->W), a.Kinv = dp(ctx->Kinv), a.alpha = dp(ctx->alpha), a.Kalpha = dp(ctx->Kalpha);
+        a.out = out_dev, a.fbest = dp(ctx->fbest), a.fbest_idx = ptr<int>(ctx->fbest_idx);
+        {
+            ProfScope ps(ctx, "small_model");
+            small_model_kernel<<<1, 256, SMALL_SMEM_BYTES, ctx->stream>>>(a);
+            LAUNCH_CHECK();
+        }
+        CUDA_TRY(cudaMemcpyAsync(ctx->pinned + kSmallOutOffset, out_dev, sizeof(double) * (size_t) (5 + D), cudaMemcpyDeviceToHost, ctx->stream));
+        return SLSGP_OK;
+    }
+
+    // After the stream has been synchronised: status, flags, value and hyper-gradient of the GP term.
+    static slsgp_status small_model_collect(slsgp_ctx* ctx, bool want_hyper, double* logdet_out, double* value, double* g_hyper)
+    {
+        const double* r = ctx->pinned + kSmallOutOffset;
+        if (r[4] != 0.0)
+            return fail(ctx, SLSGP_ERR_NOT_SPD,
+                        "Cholesky: non-positive pivot at index " + std::to_string((int) r[4] - 1) + " (K_y is not SPD)");
+        ctx->logdet_host = r[3];
+        ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = true;
+        if (logdet_out) *logdet_out = r[3];
+        gp_term_host(ctx, r[3], r, r + 5, want_hyper, value, g_hyper);
         return SLSGP_OK;
     }
 
@@ -1550,26 +1622,32 @@ extern "C"
             if (!std::isfinite(x[i])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_map_objective_pref: non-finite x");
         CUDA_TRY(cudaSetDevice(ctx->device));
         TRY(phase_begin(ctx, "map"));
-        double logdet = 0.0;
+        double              logdet = 0.0, gp = 0.0;
+        std::vector<double> gh((size_t) D + 2);
+        const bool          want_hyper = grad_out && use_map, small = use_map && small_model_applies(ctx);
         if (use_map)
         {
             std::vector<double> theta((size_t) D + 1);
             theta[0] = x[N + 0];
             for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[N + 2 + i];
-            TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[N + 1]));
-            TRY(do_factor(ctx, &logdet));
+            if (small) // one launch: model, alpha, scalars and the length-scale gradient (small.cuh); read back with the BTL terms
+                TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), x[N + 1], x, want_hyper));
+            else
+            {
+                TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[N + 1]));
+                TRY(do_factor(ctx, &logdet));
+                CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+                TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
+            }
         }
         else
         {
             if (!ctx->has_factor)
                 return fail(ctx, SLSGP_ERR_STATE, "use_map_hyperparams == 0 needs slsgp_gram + slsgp_factor first");
             logdet = ctx->logdet_host;
+            CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
         }
-        CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-        double              gp = 0.0;
-        std::vector<double> gh((size_t) D + 2);
-        const bool          want_hyper = grad_out && use_map;
-        TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
 
         // BTL likelihood of the tuples
         double loglik = 0.0;
@@ -1593,6 +1671,7 @@ extern "C"
         }
         TRY(phase_end(ctx, "map"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (small) TRY(small_model_collect(ctx, want_hyper, &logdet, &gp, gh.data()));
 
         double obj = loglik + gp;
         if (use_map) // log-normal hyper-priors centred on the defaults (:175-192) and their derivatives (:103-112, :69-73)
@@ -1720,13 +1799,21 @@ extern "C"
         std::vector<double> theta((size_t) D + 1);
         theta[0] = x[0];
         for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[2 + i];
-        double logdet = 0.0;
-        TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[1]));
-        TRY(do_factor(ctx, &logdet));
-        CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-        double              gp = 0.0;
+        double              logdet = 0.0, gp = 0.0;
         std::vector<double> gh((size_t) D + 2);
-        TRY(gp_term(ctx, logdet, grad_out != nullptr, &gp, gh.data()));
+        if (small_model_applies(ctx))
+        {
+            TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), x[1], y, grad_out != nullptr));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            TRY(small_model_collect(ctx, grad_out != nullptr, &logdet, &gp, gh.data()));
+        }
+        else
+        {
+            TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[1]));
+            TRY(do_factor(ctx, &logdet));
+            CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
+            TRY(gp_term(ctx, logdet, grad_out != nullptr, &gp, gh.data()));
+        }
         TRY(phase_end(ctx, "map"));
         // fixed log-normal priors of src/gaussian-process-regressor.cpp:18-24
         const double a_mu = std::log(0.500), a_s2 = 0.50, b_mu = std::log(1e-04), b_s2 = 0.50, r_mu = std::log(0.500), r_s2 = 0.50;

@@ -298,7 +298,7 @@ namespace sequential_line_search
         for (size_t s = 0; s < std::min<size_t>(3, starts.size()); ++s)
         {
             if (!std::isfinite(starts[s].first)) continue;
-            internal::MinimizeResult r = internal::minimize_bounded(neg, starts[s].second, lo, hi, 500, 1e-8, 1e-13);
+            internal::MinimizeResult r = internal::minimize_bounded(neg, starts[s].second, lo, hi, 300, 1e-6, 1e-12);
             if (r.f < best.f) best = r;
         }
         if (!std::isfinite(best.f)) throw std::runtime_error("GaussianProcessRegressor: MAP estimation found no admissible hyper-parameters");

@@ -142,7 +142,9 @@ def test_argmax_matches_explicit_sweep(ctx):
         assert win[2] == idx and win[1] == v
 
 
-@pytest.mark.parametrize("kt,D,N", [(S.SE, 6, 30), (S.MATERN, 16, 200), (S.SE, 8, 65)])
+# N <= 64 with D <= 32 takes the single-launch small-model kernel (csrc/small.cuh); (SE, 40, 50) has too many dimensions for it
+@pytest.mark.parametrize("kt,D,N", [(S.SE, 6, 30), (S.MATERN, 16, 200), (S.SE, 8, 65), (S.MATERN, 7, 33), (S.SE, 32, 64), (S.MATERN, 3, 3),
+                                    (S.SE, 40, 50)])
 @pytest.mark.parametrize("use_map", [False, True])
 def test_map_objectives(ctx, oracle, kt, D, N, use_map):
     X = S.make_X(N, D, "sls")
@@ -391,3 +393,38 @@ def test_append_point_failure_keeps_the_model(ctx):
         ctx.append_point(np.full(4, np.nan), 0.1)
     with pytest.raises(ValueError):
         ctx.append_point(np.zeros(3), 0.1)
+
+
+@pytest.mark.parametrize("kt,D,N", [(S.SE, 5, 1), (S.MATERN, 7, 33), (S.SE, 32, 64)])
+def test_small_model_kernel_leaves_the_state_of_the_general_path(ctx, oracle, kt, D, N):
+    """After slsgp_map_objective_gpr on a small model (one fused launch) the context must hold what slsgp_gram + slsgp_factor +
+    slsgp_inverse + slsgp_solve_alpha produce: same matrices, f_best and predictions."""
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    y, noise = S.make_y(X), 0.007
+    Q = S.make_queries(30, D)
+    ctx.set_data(X)
+    ctx.map_objective_gpr(kt, y, np.concatenate([[theta[0], noise], theta[1:]]))
+    Kinv_f = ctx.inverse()                                  # stored by the fused kernel (has_inverse is set)
+    fb_f = ctx.f_best()
+    post_f = ctx.posterior_batch(Q)
+    ctx.set_data(X)
+    K = ctx.gram(kt, theta, noise)
+    logdet, L = ctx.factor(want_L=True)
+    Kinv = ctx.inverse()
+    ctx.solve_alpha(y)
+    check("Kinv", Kinv_f, Kinv, 1e-9)
+    assert np.array_equal(Kinv_f, Kinv_f.T)
+    assert fb_f[1] == ctx.f_best()[1]
+    check("f_best", fb_f[0], ctx.f_best()[0], 1e-10)
+    for name, a, b in zip(("mu", "sigma", "dmu", "dsigma"), post_f, ctx.posterior_batch(Q)):
+        check(name, a, b, 1e-8, atol=1e-11)
+    m = oracle.model(kt, X, theta, noise, y)
+    check("Kinv vs oracle", Kinv_f, oracle.inverse(oracle.large_ky(kt, X, theta, noise)), 1e-7)
+
+
+def test_small_model_kernel_reports_a_matrix_that_is_not_spd(ctx, slsb):
+    X = np.tile(np.linspace(0.1, 0.9, 4)[:, None], (1, 6))   # six identical points, no noise: singular
+    ctx.set_data(X)
+    with pytest.raises(slsb.SlsgpError) as e:
+        ctx.map_objective_gpr(S.SE, np.zeros(6), np.array([0.5, 0.0, 0.5, 0.5, 0.5, 0.5]))
+    assert "SPD" in str(e.value)
