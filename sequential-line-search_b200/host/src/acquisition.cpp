@@ -80,7 +80,7 @@ namespace sequential_line_search
                 for (size_t i = 0; i < n; ++i) g[i] = std::isfinite(ge((long) i)) ? -ge((long) i) : 0.0;
                 return -v;
             };
-            const internal::MinimizeResult r = internal::minimize_bounded(neg, start, lo, hi, std::max(2u, max_evals), 1e-10, 1e-14);
+            const internal::MinimizeResult r = internal::minimize_bounded(neg, start, lo, hi, std::max(2u, max_evals), 1e-7, 1e-12);
             VectorXd                       out = VectorXd::Zero((long) n);
             for (size_t i = 0; i < n; ++i) out((long) i) = r.x[i];
             return out;
