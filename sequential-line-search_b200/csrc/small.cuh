@@ -104,6 +104,7 @@ namespace slsgp
                 if (tid == j) dq[j] = d, dg[j] = rd;
             }
             __syncthreads();
+#pragma unroll 4
             for (int e = tid; e < (N - j - 1) * SMALL_N; e += 256) // columns j + 1 .. N - 1 only
             {
                 const int i = e & 63, c = j + 1 + (e >> 6);
@@ -131,9 +132,18 @@ namespace slsgp
             __syncwarp();
             for (int i = 1; i < N; ++i) // same trip count for the eight columns of a warp: the shuffles are warp-wide
             {
-                double s = 0.0;
+                double s = 0.0, s2 = 0.0;
                 if (i > c)
-                    for (int k = c + q; k < i; k += 4) s = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
+                {
+                    int k = c + q;
+                    for (; k + 4 < i; k += 8)
+                    {
+                        s  = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
+                        s2 = fma(Lb[(k + 4) * SMALL_LD + i], Wb[c * SMALL_LD + k + 4], s2);
+                    }
+                    if (k < i) s = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
+                    s += s2;
+                }
                 s += __shfl_xor_sync(0xffffffffu, s, 1);
                 s += __shfl_xor_sync(0xffffffffu, s, 2);
                 if (i > c && q == 0) Wb[c * SMALL_LD + i] = -s * dg[i];
@@ -150,7 +160,17 @@ namespace slsgp
             const int i = e & 63, j = e >> 6;
             double    s = 0.0;
             if (i < N && j < N)
-                for (int k = i > j ? i : j; k < N; ++k) s = fma(Wb[i * SMALL_LD + k], Wb[j * SMALL_LD + k], s);
+            {
+                double s2 = 0.0;
+                int    k  = i > j ? i : j;
+                for (; k + 1 < N; k += 2)
+                {
+                    s  = fma(Wb[i * SMALL_LD + k], Wb[j * SMALL_LD + k], s);
+                    s2 = fma(Wb[i * SMALL_LD + k + 1], Wb[j * SMALL_LD + k + 1], s2);
+                }
+                if (k < N) s = fma(Wb[i * SMALL_LD + k], Wb[j * SMALL_LD + k], s);
+                s += s2;
+            }
             else
                 s = i == j ? 1.0 : 0.0;
             a.Kinv[e] = s;
@@ -173,22 +193,38 @@ namespace slsgp
             a.Kalpha[tid] = s;
         }
         __syncthreads();
+        if (tid < SMALL_N) // two warps: per-point terms, shuffle reductions, combined by thread 0 through `part`
+        {
+            const bool in = tid < N;
+            double     ya = in ? ys[tid] * al[tid] : 0.0, aa = in ? al[tid] * al[tid] : 0.0, tr = in ? Lb[tid * SMALL_LD + tid] : 0.0;
+            double     ld = in ? log(dq[tid]) : 0.0;
+            ArgMax     best;
+            best.v = in ? ka[tid] - a.noise * al[tid] : 0.0, best.i = in ? tid : -1;
+            ya = warp_sum(ya), aa = warp_sum(aa), tr = warp_sum(tr), ld = warp_sum(ld);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+            {
+                ArgMax other;
+                other.v = __shfl_xor_sync(0xffffffffu, best.v, o), other.i = __shfl_xor_sync(0xffffffffu, best.i, o);
+                best    = argmax_combine(best, other);
+            }
+            if (lane == 0)
+            {
+                double* p = part + warp * 8;
+                p[0] = ya, p[1] = aa, p[2] = tr, p[3] = ld, p[4] = best.v, p[5] = (double) best.i;
+            }
+        }
+        __syncthreads();
         if (tid == 0)
         {
-            double ya = 0.0, aa = 0.0, tr = 0.0, ld = 0.0;
-            ArgMax best;
-            best.v = 0.0, best.i = -1;
-            for (int i = 0; i < N; ++i)
-            {
-                ya = fma(ys[i], al[i], ya), aa = fma(al[i], al[i], aa), tr += Lb[i * SMALL_LD + i];
-                ld += log(dq[i]);
-                ArgMax cnd;
-                cnd.v = ka[i] - a.noise * al[i], cnd.i = i;
-                best = argmax_combine(best, cnd);
-            }
-            a.out[0] = ya, a.out[1] = aa, a.out[2] = tr, a.out[3] = 2.0 * ld, a.out[4] = 0.0;
+            ArgMax b0, b1;
+            b0.v = part[4], b0.i = (long long) part[5], b1.v = part[12], b1.i = (long long) part[13];
+            const ArgMax best = argmax_combine(b0, b1);
+            a.out[0] = part[0] + part[8], a.out[1] = part[1] + part[9], a.out[2] = part[2] + part[10];
+            a.out[3] = 2.0 * (part[3] + part[11]), a.out[4] = 0.0;
             a.fbest[0] = best.v, a.fbest_idx[0] = (int) best.i;
         }
+        __syncthreads(); // `part` is reused by the gradient reduction below
         if (!a.want_hyper) return;
 
         // ---- length-scale gradient: G_t = 1 / (2 l_t) sum_ij (alpha_i alpha_j - Kinv_ij) kl(r2_ij) ((x_it - x_jt) / l_t)^2 ----
