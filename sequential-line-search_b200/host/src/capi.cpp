@@ -4,6 +4,7 @@
 #include "device.hpp"
 
 #include <sequential-line-search/optimizers.hpp>
+#include <sequential-line-search/utils.hpp>
 
 #include "optimizer.hpp"
 
@@ -199,6 +200,24 @@ extern "C"
     // ---- the bound-constrained quasi-Newton driver on two closed-form problems (CPU-only test hook) ---------------------------
     // problem 0: sum_i w_i (x_i - t_i)^2 with w_i = 1 + i and targets t_i = 2 i / n - 0.5 (some outside the box [0, 1]^n);
     // problem 1: the Rosenbrock valley in n dimensions on [-2, 2]^n. Returns the number of evaluations; x_out holds the solution.
+    // ---- utils (include/sequential-line-search/utils.hpp) ---------------------------------------------------------------------
+    double b200_utils_btl(int n, const double* f, double scale, double* derivative /* n values or null */)
+    {
+        const VectorXd fv = vector(f, n);
+        if (derivative) store(utils::CalcBtlDerivative(fv, scale), derivative);
+        return utils::CalcBtl(fv, scale);
+    }
+    void b200_utils_random_vector(unsigned n, double* out) { store(utils::GenerateRandomVector(n), out); }
+    int  b200_utils_export_csv(const char* path, int rows, int cols, const double* X)
+    {
+        return guarded(
+            [&]() {
+                utils::ExportMatrixToCsv(path, matrix(X, rows, cols));
+                return 0;
+            },
+            1);
+    }
+
     int b200_test_minimize(int problem, int n, const double* x0, unsigned max_evals, double* x_out, double* f_out)
     {
         std::vector<double> lo((size_t) n, problem == 0 ? 0.0 : -2.0), hi((size_t) n, problem == 0 ? 1.0 : 2.0), start(x0, x0 + n);

@@ -15,7 +15,7 @@ c_dp = C.POINTER(C.c_double)
 c_up = C.POINTER(C.c_uint)
 _lib = None
 
-_DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value")
+_DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value", "b200_utils_btl")
 _POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
 HOST_SYMBOLS = [
     "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy", "b200_gpr_append_point",
@@ -24,6 +24,7 @@ HOST_SYMBOLS = [
     "b200_pref_damp_data", "b200_predict_mu", "b200_predict_sigma", "b200_predict_mu_derivative",
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
     "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
+    "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
 ]
 
 
@@ -176,6 +177,21 @@ class Host:
         a, b = np.empty(len(end_0)), np.empty(len(end_0))
         self.lib.b200_slider(len(end_0), _p(end_0), _p(end_1), int(enlarge), C.c_double(scale), C.c_double(minimum_length), _p(a), _p(b))
         return a, b
+
+    # utils
+    def btl(self, f, scale=1.0):
+        f = _f64(f)
+        d = np.empty(len(f))
+        return self.lib.b200_utils_btl(len(f), _p(f), C.c_double(scale), _p(d)), d
+
+    def random_vector(self, n):
+        out = np.empty(n)
+        self.lib.b200_utils_random_vector(C.c_uint(n), _p(out))
+        return out
+
+    def export_csv(self, path, X):
+        X = _f64(X)
+        self._ok(self.lib.b200_utils_export_csv(str(path).encode(), X.shape[0], X.shape[1], _p(X)) == 0)
 
     def test_minimize(self, problem, x0, max_evals=2000):
         x0 = _f64(x0)

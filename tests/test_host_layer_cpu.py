@@ -149,3 +149,25 @@ def test_quasi_newton_driver_on_closed_form_problems():
     assert f < 1e-10 and evals < 5000
     x, f, evals = host.test_minimize(1, np.full(6, -1.2), max_evals=30)   # budget: stops early, still inside the box
     assert evals <= 30 + 8 and np.all(np.abs(x) <= 2.0) and f > 1e-10
+
+
+def test_utils_match_the_reference(ref, tmp_path):
+    """sequential_line_search::utils (include/sequential-line-search/utils.hpp:18-58, src/utils.cpp): BTL likelihood and its
+    gradient against the reference's inline functions, uniform random vectors, CSV export."""
+    host = pkg.hostlib.Host()
+    rng = np.random.default_rng(5)
+    for m, scale in ((2, 1.0), (3, 0.01), (5, 0.3), (1, 1.0)):
+        f = rng.standard_normal(m) * 0.02
+        v, d = host.btl(f, scale)
+        v_r, d_r = ref.btl(f, scale)
+        assert abs(v - v_r) <= 1e-13 * abs(v_r) and S.rel_err(d, d_r) < 1e-11
+    v, d = host.btl(np.array([800.0, -800.0, 0.0]), 1.0)      # the reference's exp() overflows to inf / inf here
+    assert v == 1.0 and np.all(np.isfinite(d))
+    for n in (1, 7):
+        x = host.random_vector(n)
+        assert x.shape == (n,) and np.all(x >= 0.0) and np.all(x <= 1.0)
+    assert not np.array_equal(host.random_vector(6), host.random_vector(6))
+    X = np.array([[1.5, -2.0, 3.25], [1e-7, 123456.789, 0.0]])
+    host.export_csv(tmp_path / "m.csv", X)
+    text = (tmp_path / "m.csv").read_text()
+    assert text == "1.5,-2,3.25\n1e-07,123457,0"             # Eigen's StreamPrecision (6 significant digits), no trailing newline
