@@ -231,7 +231,7 @@ extern "C"
     /* Per-kernel device timing: while enabled, every launch of the named hot kernels is bracketed by CUDA events on
      * the context's stream. slsgp_profile_read synchronises, returns the summed duration and launch count of
      * `kernel` ("sweep_gemm", "sweep_kstar", "sweep_reduce", "sweep_grad_gemm", "sweep_finish", "tc_kstar",
-     * "tc_gemm", "gram", "chol_step") since the last read, and clears that kernel's records. */
+     * "tc_gemm", "gram", "chol_step", "small_model") since the last read, and clears that kernel's records. */
     slsgp_status slsgp_profile_enable(slsgp_ctx* ctx, int on);
     slsgp_status slsgp_profile_read(slsgp_ctx* ctx, const char* kernel, double* total_ms_out, uint64_t* launches_out);
 
