@@ -1585,7 +1585,7 @@ extern "C"
         a.N = N, a.D = D, a.kernel_type = kernel_type, a.want_hyper = want_hyper ? 1 : 0, a.noise = noise;
         a.theta = dp(ctx->theta), a.inv_l = dp(ctx->inv_l), a.y = dp(ctx->y);
         a.K = dp(ctx->K), a.L = dp(ctx->L), a.W = dp(ctx->W), a.Kinv = dp(ctx->Kinv), a.alpha = dp(ctx->alpha), a.Kalpha = dp(ctx->Kalpha);
-        a.out = out_dev, a.fbest = dp(ctx->fbest), a.fbest_idx = ptr<int>(ctx->fbest_idx);
+        a.out = out_dev, a.fbest = dp(ctx->fbest), a.fbest_idx = ptr<int>(ctx->fbest_idx), a.info = ptr<int>(ctx->info);
         {
             ProfScope ps(ctx, "small_model");
             small_model_kernel<<<1, 256, SMALL_SMEM_BYTES, ctx->stream>>>(a);

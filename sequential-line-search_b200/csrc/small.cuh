@@ -5,12 +5,14 @@
 // W = L^-1 by forward substitution, K^-1 = W^T W), same buffers, same padding conventions (identity on rows >= N).
 #pragma once
 
+#include "chol.cuh"
 #include "common.cuh"
 #include "sweep.cuh"
 
 namespace slsgp
 {
     constexpr int SMALL_N = 64, SMALL_LD = SMALL_N + 1, SMALL_DMAX = 32;
+    constexpr int SMALL_REGS_FROM = 20; // from this N on: the register-resident 64-pivot factor + inverse of chol.cuh (fixed ~15 us)
     constexpr int SMALL_SMEM_BYTES = (3 * SMALL_N * SMALL_LD + SMALL_DMAX * SMALL_N + 5 * SMALL_N + 8 * SMALL_DMAX + 8) * (int) sizeof(double);
 
     struct SmallModelArgs
@@ -23,7 +25,7 @@ namespace slsgp
         double *      out;                               // [0] y.alpha [1] alpha.alpha [2] tr K^-1 [3] logdet [4] bad pivot + 1 or 0
                                                          // [5 .. 5 + D) length-scale gradient: one device-to-host copy
         double *      fbest;
-        int *         fbest_idx;
+        int *         fbest_idx, *info;
     };
 
     __global__ void __launch_bounds__(256) small_model_kernel(const SmallModelArgs a)
@@ -85,69 +87,107 @@ namespace slsgp
             a.K[e]               = v;
         }
 
-        // ---- right-looking Cholesky of Lb. The diagonal keeps the running pivot until the end (every thread reads it at the
-        // top of its step; the square roots are parked in dq), so a step needs two barriers only. ---------------------------
-        if (tid < SMALL_N) dq[tid] = 1.0, dg[tid] = 1.0; // rows >= N: the identity
-        for (int j = 0; j < N; ++j)
+        static_assert(TILE == SMALL_N, "potf2_inverse_regs works on 64 x 64 tiles");
+        if (N >= SMALL_REGS_FROM)
         {
-            __syncthreads();
-            const double piv = Lb[j * SMALL_LD + j];
-            if (!(piv > 0.0) || !isfinite(piv))
-            {
-                if (tid == 0) *bad = j + 1;
-                break; // uniform: every thread read the same pivot
-            }
-            const double d = sqrt(piv), rd = 1.0 / d;
-            if (tid < SMALL_N)
-            {
-                if (tid > j && tid < N) Lb[j * SMALL_LD + tid] *= rd;
-                if (tid == j) dq[j] = d, dg[j] = rd;
-            }
-            __syncthreads();
-#pragma unroll 4
-            for (int e = tid; e < (N - j - 1) * SMALL_N; e += 256) // columns j + 1 .. N - 1 only
-            {
-                const int i = e & 63, c = j + 1 + (e >> 6);
-                if (i >= c && i < N) Lb[c * SMALL_LD + i] = fma(-Lb[j * SMALL_LD + i], Lb[j * SMALL_LD + c], Lb[c * SMALL_LD + i]);
-            }
-        }
-        __syncthreads();
-        if (*bad != 0)
-        {
-            if (tid == 0) a.out[4] = (double) *bad;
-            return;
-        }
-        if (tid < SMALL_N) Lb[tid * SMALL_LD + tid] = dq[tid];
-        __syncthreads();
-        for (int e = tid; e < SMALL_N * SMALL_N; e += 256) a.L[e] = Lb[(e >> 6) * SMALL_LD + (e & 63)];
-
-        // ---- W = L^-1: column c by forward substitution, four lanes sharing each dot product ----------------------------
-        {
-            const int c = tid >> 2, q = tid & 3;
-            if (q == 0)
-            {
-                for (int i = 0; i < SMALL_N; ++i) Wb[c * SMALL_LD + i] = 0.0;
-                Wb[c * SMALL_LD + c] = dg[c];
-            }
-            __syncwarp();
-            for (int i = 1; i < N; ++i) // same trip count for the eight columns of a warp: the shuffles are warp-wide
-            {
-                double s = 0.0, s2 = 0.0;
-                if (i > c)
+            // ---- factor and triangular inverse in registers (potf2_inverse_regs, chol.cuh: one barrier per pivot) -----------
+            const int tx = tid & 15, ty = tid >> 4;
+            double    c[4][4];
+            __syncthreads(); // Kb complete
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq)
+#pragma unroll
+                for (int iq = 0; iq < 4; ++iq)
                 {
-                    int k = c + q;
-                    for (; k + 4 < i; k += 8)
-                    {
-                        s  = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
-                        s2 = fma(Lb[(k + 4) * SMALL_LD + i], Wb[c * SMALL_LD + k + 4], s2);
-                    }
-                    if (k < i) s = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
-                    s += s2;
+                    const int p = tx + 16 * iq, q = ty + 16 * jq;
+                    c[iq][jq]   = q <= p ? Kb[q * SMALL_LD + p] : 0.0;
                 }
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                if (i > c && q == 0) Wb[c * SMALL_LD + i] = -s * dg[i];
+            potf2_inverse_regs(c, part, part + 2 * (TILE + 2), dg, bad, tx, ty, 0, a.info); // dg = d^-1/2
+            if (*bad != 0x7fffffff)
+            {
+                if (tid == 0) a.out[4] = (double) (*bad + 1);
+                return;
+            }
+#pragma unroll
+            for (int jq = 0; jq < 4; ++jq)
+#pragma unroll
+                for (int iq = 0; iq < 4; ++iq)
+                {
+                    const int    p = tx + 16 * iq, q = ty + 16 * jq;
+                    const double v = c[iq][jq] * dg[q];
+                    Lb[q * SMALL_LD + p] = q <= p ? v : 0.0;                        // L(p, q)
+                    Wb[p * SMALL_LD + q] = q > p ? v : (q == p ? dg[q] : 0.0);      // W(q, p): rows q >= p of column p
+                    if (p == q) dq[p] = v;
+                }
+            __syncthreads();
+            for (int e = tid; e < SMALL_N * SMALL_N; e += 256) a.L[e] = Lb[(e >> 6) * SMALL_LD + (e & 63)];
+        }
+        else
+        {
+            // ---- right-looking Cholesky of Lb. The diagonal keeps the running pivot until the end (every thread reads it at the
+            // top of its step; the square roots are parked in dq), so a step needs two barriers only. ---------------------------
+            if (tid < SMALL_N) dq[tid] = 1.0, dg[tid] = 1.0; // rows >= N: the identity
+            for (int j = 0; j < N; ++j)
+            {
+                __syncthreads();
+                const double piv = Lb[j * SMALL_LD + j];
+                if (!(piv > 0.0) || !isfinite(piv))
+                {
+                    if (tid == 0) *bad = j + 1;
+                    break; // uniform: every thread read the same pivot
+                }
+                const double d = sqrt(piv), rd = 1.0 / d;
+                if (tid < SMALL_N)
+                {
+                    if (tid > j && tid < N) Lb[j * SMALL_LD + tid] *= rd;
+                    if (tid == j) dq[j] = d, dg[j] = rd;
+                }
+                __syncthreads();
+    #pragma unroll 4
+                for (int e = tid; e < (N - j - 1) * SMALL_N; e += 256) // columns j + 1 .. N - 1 only
+                {
+                    const int i = e & 63, c = j + 1 + (e >> 6);
+                    if (i >= c && i < N) Lb[c * SMALL_LD + i] = fma(-Lb[j * SMALL_LD + i], Lb[j * SMALL_LD + c], Lb[c * SMALL_LD + i]);
+                }
+            }
+            __syncthreads();
+            if (*bad != 0)
+            {
+                if (tid == 0) a.out[4] = (double) *bad;
+                return;
+            }
+            if (tid < SMALL_N) Lb[tid * SMALL_LD + tid] = dq[tid];
+            __syncthreads();
+            for (int e = tid; e < SMALL_N * SMALL_N; e += 256) a.L[e] = Lb[(e >> 6) * SMALL_LD + (e & 63)];
+
+            // ---- W = L^-1: column c by forward substitution, four lanes sharing each dot product ----------------------------
+            {
+                const int c = tid >> 2, q = tid & 3;
+                if (q == 0)
+                {
+                    for (int i = 0; i < SMALL_N; ++i) Wb[c * SMALL_LD + i] = 0.0;
+                    Wb[c * SMALL_LD + c] = dg[c];
+                }
                 __syncwarp();
+                for (int i = 1; i < N; ++i) // same trip count for the eight columns of a warp: the shuffles are warp-wide
+                {
+                    double s = 0.0, s2 = 0.0;
+                    if (i > c)
+                    {
+                        int k = c + q;
+                        for (; k + 4 < i; k += 8)
+                        {
+                            s  = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
+                            s2 = fma(Lb[(k + 4) * SMALL_LD + i], Wb[c * SMALL_LD + k + 4], s2);
+                        }
+                        if (k < i) s = fma(Lb[k * SMALL_LD + i], Wb[c * SMALL_LD + k], s);
+                        s += s2;
+                    }
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    if (i > c && q == 0) Wb[c * SMALL_LD + i] = -s * dg[i];
+                    __syncwarp();
+                }
             }
         }
         __syncthreads();
