@@ -124,6 +124,7 @@ extern "C"
             std::memcpy(out + i * size_t(N) * size_t(N), tensor[i].data(), sizeof(double) * size_t(N) * size_t(N));
     }
 
+#ifndef SLS_REF_REAL_NLOPT // these reach the anonymous-namespace MAP objective through the probe NLopt's hook
     // ---- PreferenceRegressor -------------------------------------------------------------------------------
     // Tuples in CSR form: tuple t covers idx[offsets[t] .. offsets[t+1]). `solution` (length N, or N+2+D when
     // use_map != 0, layout [y, a, b, r_1..r_D] as in src/preference-regressor.cpp:137-147) is what the probe NLopt
@@ -188,6 +189,8 @@ extern "C"
         std::memcpy(x_out, x.data(), sizeof(double) * size_t(x.size()));
     }
 
+#endif
+
     // ---- GaussianProcessRegressor ----------------------------------------------------------------------------
     void* ref_gpr_create(int kt, int D, int N, const double* X, const double* y, const double* theta, double b)
     {
@@ -204,6 +207,7 @@ extern "C"
         if (K_y_inv) std::memcpy(K_y_inv, r.m_K_y_inv.data(), sizeof(double) * N * N);
     }
 
+#ifndef SLS_REF_REAL_NLOPT
     // The reference's GPR MAP objective (src/gaussian-process-regressor.cpp:141-193), variables (a, b, r_1..r_D),
     // evaluated at n_points points. It is only reachable from inside the MAP constructor, so the probe hook
     // evaluates it there; the constructor then finishes at the last probe point.
@@ -233,6 +237,7 @@ extern "C"
         GaussianProcessRegressor reg(to_matrix(X, D, N), to_vector(y, N), to_kernel_type(kt));
         nlopt::probe::hook().fn = nullptr;
     }
+#endif
 
     // ---- Regressor virtual interface + acquisition (work on either regressor kind) -----------------------
     double ref_predict_mu(const void* r, int D, const double* x)

@@ -81,11 +81,21 @@ def _host_sources():
             [os.path.join(HOST_DIR, "Makefile"), os.path.join(os.path.dirname(PKG_DIR), "include", "slsgp.h")])
 
 
+def build_nlopt() -> None:
+    """libnlopt.a + nlopt.hpp from the NLopt sources the reference vendors (third_party/nlopt/Makefile). A no-op where those
+    sources are absent (the GPU box): the prebuilt files travel with the snapshot. With them the host layer offers the
+    Reference / Hybrid search drivers; without them it is built Native-only."""
+    res = subprocess.run(["make", "-s", "-C", os.path.join(os.path.dirname(PKG_DIR), "third_party", "nlopt")], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("NLopt build failed:\n" + res.stdout + res.stderr)
+
+
 def build_host(force: bool = False) -> str:
     """Build libsls_b200_host.so: the C++ mirror of the reference's Regressor / acquisition_func interface above the
     C ABI (g++, links libslsgp.so with an $ORIGIN rpath). Uses the system Eigen when EIGEN_INC names it, else the
     repository's eigen-lite subset."""
     build()
+    build_nlopt()
     if not force and _is_current(HOST_LIB_PATH, _host_sources()):
         return HOST_LIB_PATH
     res = subprocess.run(["make", "-s", "-B", "-C", HOST_DIR], capture_output=True, text=True)

@@ -6,6 +6,7 @@
 //   FindNextPoints                      Schonlau's batch criterion (:246-298): mu from the regressor, sigma from a
 //                                       temporary GaussianProcessRegressor that also holds the points chosen so far
 #include "device.hpp"
+#include "nlopt_driver.hpp"
 #include "optimizer.hpp"
 
 #include <cmath>
@@ -86,6 +87,17 @@ namespace sequential_line_search
             return out;
         }
 
+        // FindGlobalSolution exactly as the reference's default build runs it (src/acquisition-function.cpp:112-167): a starting
+        // point from Eigen's Random() (libc rand()), GN_DIRECT with `n_global` evaluations, then LD_LBFGS with `n_local` from
+        // DIRECT's answer, both maximising over [0, 1]^D. SearchDriver::Reference only.
+        VectorXd find_global_solution_reference(const internal::NloptObjective& objective, unsigned D, unsigned n_global, unsigned n_local)
+        {
+            const VectorXd upper = VectorXd::Constant(D, 1.0), lower = VectorXd::Constant(D, 0.0);
+            const VectorXd x_ini = 0.5 * (VectorXd::Random(D) + VectorXd::Ones(D));
+            const VectorXd x_global = internal::nlopt_solve(x_ini, upper, lower, objective, internal::NloptAlgorithm::GN_DIRECT, true, (int) n_global);
+            return internal::nlopt_solve(x_global, upper, lower, objective, internal::NloptAlgorithm::LD_LBFGS, true, (int) n_local);
+        }
+
         uint64_t search_seed(const Regressor& r) { return 0x9E3779B97F4A7C15ull ^ ((uint64_t) r.GetLargeX().cols() << 20) ^ (uint64_t) r.GetNumDims(); }
     } // namespace
 
@@ -132,6 +144,26 @@ namespace sequential_line_search
                                const AcquisitionFuncType func_type, const double hyperparam)
         {
             const unsigned D = regressor.GetNumDims();
+            if (internal::use_nlopt_for_search())
+            {
+                const DeviceRegressor*         d         = device_of(regressor);
+                const internal::NloptObjective objective = [&](const std::vector<double>& x, std::vector<double>& grad) {
+                    const VectorXd xe = Eigen::Map<const VectorXd>(x.data(), (long) x.size());
+                    if (d && regressor.GetSmallY().rows() != 0) // value and gradient from ONE one-candidate sweep
+                    {
+                        double v = 0.0;
+                        device_acq(*d, xe.data(), 1, func_type, hyperparam, &v, grad.empty() ? nullptr : grad.data());
+                        return v;
+                    }
+                    if (!grad.empty())
+                    {
+                        const VectorXd g = CalcAcquisitionValueDerivative(regressor, xe, func_type, hyperparam);
+                        for (size_t i = 0; i < grad.size(); ++i) grad[i] = g((long) i);
+                    }
+                    return CalcAcquisitionValue(regressor, xe, func_type, hyperparam);
+                };
+                return find_global_solution_reference(objective, D, num_global_search_iters, num_local_search_iters);
+            }
             if (regressor.GetSmallY().rows() == 0 || D == 0) return VectorXd::Constant(D, 0.5); // flat objective: the box centre
             const long     count = (long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter;
             VectorXd       x0    = VectorXd::Zero(D);
@@ -217,6 +249,26 @@ namespace sequential_line_search
                                                grad ? dmu.data() : nullptr, grad ? dsigma.data() : nullptr, val.data(), grad ? grad->data() : nullptr),
                       "slsgp_acq_from_posterior");
             };
+
+            if (internal::use_nlopt_for_search())
+            {
+                // the reference's loop (:264-296): DIRECT + L-BFGS on Schonlau's criterion, one-candidate device calls per evaluation
+                for (unsigned i = 0; i < num_points; ++i)
+                {
+                    const internal::NloptObjective objective = [&](const std::vector<double>& x, std::vector<double>& grad) {
+                        MatrixXd X1 = MatrixXd::Zero(D, 1), G;
+                        for (unsigned k = 0; k < D; ++k) X1(k, 0) = x[k];
+                        VectorXd v;
+                        pair_acq(X1, v, grad.empty() ? nullptr : &G);
+                        for (size_t k = 0; k < grad.size(); ++k) grad[k] = G((long) k, 0);
+                        return v(0);
+                    };
+                    const VectorXd x_star = find_global_solution_reference(objective, D, num_global_search_iters, num_local_search_iters);
+                    points.push_back(x_star);
+                    if (points.size() != num_points) temp->AppendPoint(x_star, temp->PredictMu(x_star));
+                }
+                return points;
+            }
 
             // global stage: the counter-based candidate sequence in chunks (bounded host memory), tensor sweep for large counts
             const long count = std::min<long>((long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter, 1L << 21);

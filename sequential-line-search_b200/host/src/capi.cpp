@@ -3,14 +3,18 @@
 // C++ exceptions never cross this boundary: a failing call stores the message (b200_last_error) and returns null / NaN.
 #include "device.hpp"
 
+#include <sequential-line-search/driver.hpp>
 #include <sequential-line-search/optimizers.hpp>
 #include <sequential-line-search/utils.hpp>
 
 #include "optimizer.hpp"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <limits>
+#include <memory>
 #include <string>
 
 using Eigen::MatrixXd;
@@ -37,6 +41,13 @@ namespace
     }
     void store(const VectorXd& v, double* out) { std::memcpy(out, v.data(), sizeof(double) * (size_t) v.size()); }
     void store(const MatrixXd& m, double* out) { std::memcpy(out, m.data(), sizeof(double) * (size_t) m.rows() * (size_t) m.cols()); }
+    // names loop_capi.inl expects
+    KernelType          to_kernel(int kt) { return kernel_type(kt); }
+    AcquisitionFuncType to_acq(int t) { return acq_type(t); }
+    MatrixXd            to_mat(const double* p, int rows, int cols) { return matrix(p, rows, cols); }
+    VectorXd            to_vec(const double* p, int n) { return vector(p, n); }
+    void                put(const VectorXd& v, double* out) { store(v, out); }
+    void                put(const MatrixXd& m, double* out) { store(m, out); }
 
     template <typename F> auto guarded(F&& f, decltype(f()) on_error) -> decltype(f())
     {
@@ -247,6 +258,14 @@ extern "C"
         return (int) r.evals;
     }
 
+    // ---- search driver (sequential-line-search/driver.hpp): 0 Native, 1 Hybrid, 2 Reference -------------------------------------
+    int b200_nlopt_available() { return IsNloptAvailable() ? 1 : 0; }
+    int b200_get_search_driver() { return (int) GetSearchDriver(); }
+    int b200_set_search_driver(int mode)
+    {
+        return guarded([&]() { return SetSearchDriver(mode == 0 ? SearchDriver::Native : mode == 1 ? SearchDriver::Hybrid : SearchDriver::Reference), 0; }, 1);
+    }
+
     // ---- Regressor virtual interface ------------------------------------------------------------------------------------
     double b200_predict_mu(const void* r, int D, const double* x)
     {
@@ -324,4 +343,16 @@ extern "C"
             },
             1);
     }
+    // ---- optimiser front-ends and driver-dependent entry points: the facade the test suite also compiles against the reference's classes -------
+#define SLS_CAPI(name) b200_##name
+#define SLS_CAPI_TRY \
+    g_error.clear(); \
+    try
+#define SLS_CAPI_CATCH(value)       \
+    catch (const std::exception& e) \
+    {                               \
+        g_error = e.what();         \
+        return value;               \
+    }
+#include "loop_capi.inl"
 }

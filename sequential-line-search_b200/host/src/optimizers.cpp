@@ -2,6 +2,7 @@
 // src/preferential-bayesian-optimizer.cpp, src/preference-data-manager.cpp, src/slider.cpp). Pure host bookkeeping around
 // the two device-backed steps: the PreferenceRegressor MAP fit and acquisition_func::FindNextPoint(s).
 #include "device.hpp"
+#include "nlopt_driver.hpp"
 
 #include <sequential-line-search/optimizers.hpp>
 
@@ -66,6 +67,38 @@ namespace sequential_line_search
             return {e_1, e_2};
         }
 
+        // SearchDriver::Reference: the enlargement as the reference solves it (src/slider.cpp:73-122): two 1-D COBYLA runs from
+        // t = 1 over [0, scale] on -(t - scale)^2 subject to "c +- t r needs no cropping" (tolerance 1e-10). The reference passes
+        // 1000 in the position of `is_maximization` (so: maximise, default budget of 1000 evaluations); kept.
+        std::pair<VectorXd, VectorXd> enlarge_reference(const VectorXd& x_1, const VectorXd& x_2, double scale, double minimum_length)
+        {
+            const VectorXd c = 0.5 * (clamp_to_box(x_1) + clamp_to_box(x_2));
+            const VectorXd r = clamp_to_box(x_1) - c;
+            const internal::NloptObjective objective = [&](const std::vector<double>& x, std::vector<double>&) { return -(x[0] - scale) * (x[0] - scale); };
+            const auto constraint_of = [&](double sign) {
+                return internal::NloptObjective([&c, &r, sign](const std::vector<double>& x, std::vector<double>&) {
+                    const VectorXd y   = c + (sign * x[0]) * r;
+                    double         sum = 0.0;
+                    for (int i = 0; i < (int) y.size(); ++i) sum += (clamp_to_box(y(i)) - y(i)) * (clamp_to_box(y(i)) - y(i));
+                    return sum;
+                });
+            };
+            const internal::NloptObjective constraint_p = constraint_of(+1.0), constraint_n = constraint_of(-1.0);
+            const VectorXd x0 = VectorXd::Constant(1, 1.0), upper = VectorXd::Constant(1, scale), lower = VectorXd::Constant(1, 0.0);
+            const double   t_1 = internal::nlopt_solve(x0, upper, lower, objective, internal::NloptAlgorithm::LN_COBYLA, true, 1000, &constraint_p)(0);
+            const double   t_2 = internal::nlopt_solve(x0, upper, lower, objective, internal::NloptAlgorithm::LN_COBYLA, true, 1000, &constraint_n)(0);
+            const VectorXd e_1 = clamp_to_box(c + t_1 * r), e_2 = clamp_to_box(c - t_2 * r);
+            const double   length = (e_1 - e_2).norm();
+            if (length < minimum_length)
+            {
+                const double k = minimum_length / length;
+                if (std::abs(t_1 - t_2) < 1e-10) return {c + k * t_1 * r, c - k * t_2 * r};
+                if (t_1 > t_2) return {c + 2.0 * k * t_1 * r, c - t_2 * r};
+                return {c + t_1 * r, c - 2.0 * k * t_2 * r};
+            }
+            return {e_1, e_2};
+        }
+
         // ---- merging of (nearly) coincident data points (src/preference-data-manager.cpp:14-86) ------------
         bool merge_first_close_pair(double eps_squared, MatrixXd& X, std::vector<Preference>& D)
         {
@@ -106,7 +139,8 @@ namespace sequential_line_search
         : end_0(end_0_in), end_1(end_1_in), original_end_0(end_0_in), original_end_1(end_1_in)
     {
         if (!enlarge_it) return;
-        const auto ends = enlarge(original_end_0, original_end_1, scale, minimum_length);
+        const auto ends = internal::use_nlopt_for_search() ? enlarge_reference(original_end_0, original_end_1, scale, minimum_length)
+                                                            : enlarge(original_end_0, original_end_1, scale, minimum_length);
         end_0 = ends.first, end_1 = ends.second;
     }
 

@@ -2,6 +2,7 @@
 // src/preference-regressor.cpp) re-hosted on libslsgp: the classes keep their state on the host exactly where the
 // reference keeps it (m_X, m_y, hyper-parameters, m_K ..) and delegate every O(N^2) / O(N^3) step to the device.
 #include "device.hpp"
+#include "nlopt_driver.hpp"
 #include "optimizer.hpp"
 
 #include <cmath>
@@ -260,6 +261,33 @@ namespace sequential_line_search
             m_data_on_device = true;
         }
         const slsgp_kernel_type kt = internal::to_abi(m_kernel_type);
+        if (internal::use_nlopt_for_map())
+        {
+            // The reference's procedure, call for call (:274-299): start from the prior means, GN_DIRECT with 300 evaluations, then
+            // LD_TNEWTON with 1000, both over (a, b, r) in [1e-8, 50]^(D+2); the objective and its gradient come from the device.
+            const internal::NloptObjective objective = [&](const std::vector<double>& x, std::vector<double>& grad) {
+                std::lock_guard<std::mutex> lock(*m_mutex);
+                double                      f = 0.0;
+                const slsgp_status          s = slsgp_map_objective_gpr(c, kt, m_y.data(), x.data(), &f, grad.size() == x.size() ? grad.data() : nullptr);
+                if (s == SLSGP_ERR_NOT_SPD || s == SLSGP_ERR_NAN)
+                {
+                    for (auto& g : grad) g = 0.0;
+                    return -1e300; // the reference would carry NaNs from a failed LLT here; keep the optimiser away instead
+                }
+                check(c, s, "slsgp_map_objective_gpr");
+                return f;
+            };
+            VectorXd x_ini = VectorXd::Constant(n, std::exp(std::log(0.500)));
+            x_ini(1)       = std::exp(std::log(1e-04));
+            const VectorXd upper = VectorXd::Constant(n, 5e+01), lower = VectorXd::Constant(n, 1e-08);
+            const VectorXd x_glo = internal::nlopt_solve(x_ini, upper, lower, objective, internal::NloptAlgorithm::GN_DIRECT, true, 300);
+            const VectorXd x_loc = internal::nlopt_solve(x_glo, upper, lower, objective, internal::NloptAlgorithm::LD_TNEWTON, true, 1000);
+            m_kernel_hyperparams    = VectorXd::Zero(D + 1);
+            m_kernel_hyperparams(0) = x_loc(0);
+            for (int i = 0; i < D; ++i) m_kernel_hyperparams(i + 1) = x_loc(2 + i);
+            m_noise_hyperparam = x_loc(1);
+            return;
+        }
         // The driver works on z = log(a, b, r): the three groups differ by orders of magnitude (b ~ 1e-4, a ~ 0.5) and
         // the box [1e-8, 50] is a box in z as well; dF/dz_i = x_i dF/dx_i.
         const internal::Objective neg = [&](const std::vector<double>& z, std::vector<double>& g) {
@@ -394,6 +422,58 @@ namespace sequential_line_search
         check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
         m_data_on_device = true;
         check(c, slsgp_set_preferences(c, offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
+
+        if (internal::use_nlopt_for_map())
+        {
+            // The reference's procedure, call for call (:332-403): the joint vector (y[, a, b, r]) handed to LD_TNEWTON with
+            // `num_iters` evaluations from y = 0 and the default hyper-parameters, box [-10, 10]^N x [1e-8, 10]^(D+2).
+            const int opt_dim = m_use_map_hyperparams ? N + 2 + D : N;
+            VectorXd  upper = VectorXd::Constant(opt_dim, +1e+01), lower = VectorXd::Constant(opt_dim, -1e+01), x_ini = VectorXd::Constant(opt_dim, 0.0);
+            if (m_use_map_hyperparams)
+            {
+                for (int i = 0; i < 2 + D; ++i) lower(N + i) = 1e-08;
+                x_ini(N + 0) = m_default_kernel_signal_var;
+                x_ini(N + 1) = m_default_noise_level;
+                for (int i = 0; i < D; ++i) x_ini(N + 2 + i) = m_default_kernel_length_scale;
+                for (int i = 0; i < opt_dim; ++i) x_ini(i) = std::min(std::max(x_ini(i), lower(i)), upper(i));
+            }
+            else
+            {
+                VectorXd theta = VectorXd::Constant(D + 1, m_default_kernel_length_scale);
+                theta(0)       = m_default_kernel_signal_var;
+                check(c, slsgp_gram(c, kt, theta.data(), m_default_noise_level, nullptr), "slsgp_gram");
+                check(c, slsgp_factor(c, nullptr, nullptr), "slsgp_factor");
+            }
+            unsigned                       evals     = 0;
+            const internal::NloptObjective objective = [&](const std::vector<double>& x, std::vector<double>& grad) {
+                ++evals;
+                double             f = 0.0;
+                const slsgp_status s = slsgp_map_objective_pref(c, kt, x.data(), opt_dim, m_use_map_hyperparams ? 1 : 0, m_default_kernel_signal_var,
+                                                                m_default_kernel_length_scale, m_default_noise_level, m_kernel_hyperparams_prior_var,
+                                                                m_btl_scale, &f, grad.size() == x.size() ? grad.data() : nullptr);
+                if (s == SLSGP_ERR_NOT_SPD || s == SLSGP_ERR_NAN)
+                {
+                    for (auto& g : grad) g = 0.0;
+                    return -1e300; // the reference would carry NaNs from a failed LLT here; keep the optimiser away instead
+                }
+                check(c, s, "slsgp_map_objective_pref");
+                return f;
+            };
+            const VectorXd x_opt = internal::nlopt_solve(x_ini, upper, lower, objective, internal::NloptAlgorithm::LD_TNEWTON, true, (int) num_iters);
+            m_num_map_evaluations = evals;
+            m_y                   = VectorXd::Zero(N);
+            for (int i = 0; i < N; ++i) m_y(i) = x_opt(i);
+            m_kernel_hyperparams = VectorXd::Constant(D + 1, m_default_kernel_length_scale);
+            m_kernel_hyperparams(0) = m_default_kernel_signal_var;
+            m_noise_hyperparam      = m_default_noise_level;
+            if (m_use_map_hyperparams)
+            {
+                m_kernel_hyperparams(0) = x_opt(N + 0);
+                for (int i = 0; i < D; ++i) m_kernel_hyperparams(i + 1) = x_opt(N + 2 + i);
+                m_noise_hyperparam = x_opt(N + 1);
+            }
+            return;
+        }
 
         // starting point: zeros / defaults, or the previous iteration's state for the points that are still there
         std::vector<double> y_start((size_t) N, 0.0);

@@ -25,7 +25,29 @@ HOST_SYMBOLS = [
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
     "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
     "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
-]
+    "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver",
+] + ["b200_" + n for n in (
+    # host/src/loop_capi.inl: optimiser front-ends and driver-dependent entry points (bound by tests/loop_support.py)
+    "srand sls_create sls_destroy sls_set_hyperparams sls_set_ucb_hyperparam sls_submit sls_get_slider_ends sls_get_maximizer sls_calc_point "
+    "sls_num_points sls_get_raw_data_points sls_query pbo_create pbo_destroy pbo_set_hyperparams pbo_submit pbo_determine_next_query "
+    "pbo_get_current_options pbo_get_maximizer pbo_num_points pref_fit pref_fit_destroy pref_fit_regressor pref_fit_get_state "
+    "pref_fit_find_arg_max gpr_fit gpr_given gpr_fit_destroy gpr_fit_regressor loop_find_next_point loop_find_next_points loop_acq_value "
+    "loop_acq_derivative loop_predict loop_slider").split()]
+
+NATIVE, HYBRID, REFERENCE = 0, 1, 2  # sequential_line_search::SearchDriver
+
+
+def nlopt_available() -> bool:
+    return bool(load_host_library().b200_nlopt_available())
+
+
+def set_search_driver(mode: int) -> None:
+    if load_host_library().b200_set_search_driver(mode) != 0:
+        raise RuntimeError(load_host_library().b200_last_error().decode())
+
+
+def get_search_driver() -> int:
+    return load_host_library().b200_get_search_driver()
 
 
 def load_host_library(build_if_missing: bool = True) -> C.CDLL:

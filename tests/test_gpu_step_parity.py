@@ -1,0 +1,266 @@
+"""Step-level parity with the REAL reference loop ("Next" #1).
+
+oracle/_ref/libsls_ref_loop.so is the reference's unmodified code - front-ends, regressors, acquisition search, slider -
+linked against NLopt 2.10.0 built from its own external/nlopt submodule (third_party/nlopt/Makefile). With
+SearchDriver::Reference the host layer hands the same NLopt the same problems (algorithms, budgets, bounds, starting points,
+std::rand() stream) with the objectives evaluated on the GPU, so the two sides can be compared at the level a user sees:
+
+  * each stage of SubmitFeedbackData on IDENTICAL inputs - the MAP fit (y, theta, b), FindNextPoint, FindNextPoints, the
+    GaussianProcessRegressor fit: 1e-5 relative (north_star's FP64 tolerance);
+  * the whole loop (config 1: the nd demo, D = 6, 15 iterations, fixed seed): slider ends per iteration, reporting the first
+    iteration at which the two trajectories part (the optimisers are chaotic in the last bits of their objective values, so a
+    loop-level comparison can only hold for a prefix; each step of that prefix must hold 1e-5);
+  * the GPU-native search (SearchDriver::Hybrid): EI(x_ours) >= EI(x_ref) - tol, x_ref from the real reference.
+"""
+import importlib
+
+import numpy as np
+import pytest
+
+import loop_support as LS
+import support as S
+
+pkg = importlib.import_module("sequential-line-search_b200")
+pytestmark = pytest.mark.gpu
+RT = 1e-5
+DEMO_HYPER = (0.5, 0.5, 0.001, 0.1, 0.01)  # demos/sequential_line_search_nd/main.cpp:11-15
+
+
+@pytest.fixture(scope="module")
+def sides():
+    if not LS.ref_loop_available():
+        pytest.skip("oracle/_ref/libsls_ref_loop.so not built")
+    if not pkg.hostlib.nlopt_available():
+        pytest.skip("host layer built without NLopt")
+    ref, b200 = LS.LoopLib("ref"), LS.LoopLib("b200")
+    previous = pkg.hostlib.get_search_driver()
+    yield ref, b200
+    pkg.hostlib.set_search_driver(previous)
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
+
+
+def _tuples(X):
+    offsets, idx = S.make_tuples(X)
+    return [list(idx[offsets[t]:offsets[t + 1]]) for t in range(len(offsets) - 1)]
+
+
+# ---- MAP fit of the PreferenceRegressor, LD_TNEWTON on both sides ----------------------------------------------------------
+@pytest.mark.parametrize("kt,D,N,use_map,iters", [(S.MATERN, 6, 9, True, 100), (S.MATERN, 6, 31, True, 100), (S.SE, 8, 30, True, 100),
+                                                  (S.MATERN, 6, 31, False, 100), (S.SE, 5, 61, True, 150), (S.MATERN, 16, 90, True, 100)])
+def test_preference_map_fit_equals_the_reference_fit(sides, kt, D, N, use_map, iters):
+    ref, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    X = S.make_X(N, D, "sls")
+    tuples = _tuples(X)
+    fr = ref.pref_fit(kt, X, tuples, use_map, *DEMO_HYPER, num_iters=iters)
+    fb = b200.pref_fit(kt, X, tuples, use_map, *DEMO_HYPER, num_iters=iters)
+    try:
+        (y_r, th_r, b_r), (y_b, th_b, b_b) = fr.state(), fb.state()
+        assert _rel(y_b, y_r) < RT, ("y", _rel(y_b, y_r))
+        assert _rel(th_b, th_r) < RT and abs(b_b - b_r) <= RT * abs(b_r), (th_b, th_r, b_b, b_r)
+        np.testing.assert_array_equal(fb.find_arg_max(), fr.find_arg_max())
+        # and the fitted regressors answer alike
+        Q = S.make_queries(6, D)
+        for m in range(Q.shape[1]):
+            for what in (0, 1):
+                want, got = ref.predict(fr.reg, Q[:, m], what), b200.predict(fb.reg, Q[:, m], what)
+                assert abs(got - want) <= RT * max(abs(want), 1e-3), (what, got, want)
+    finally:
+        fr.close()
+        fb.close()
+
+
+# ---- GaussianProcessRegressor MAP fit: GN_DIRECT(300) + LD_TNEWTON(1000) on both sides --------------------------------------
+@pytest.mark.parametrize("kt,D,N", [(S.MATERN, 1, 12), (S.SE, 3, 25), (S.MATERN, 4, 40)])
+def test_gpr_map_fit_equals_the_reference_fit(sides, kt, D, N):
+    ref, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    X = S.make_X(N, D, "uniform")
+    y = S.make_y(X)
+    gr, gb = ref.gpr_fit(kt, X, y), b200.gpr_fit(kt, X, y)
+    try:
+        assert _rel(gb.theta, gr.theta) < RT and abs(gb.b - gr.b) <= RT * abs(gr.b), (gb.theta, gr.theta, gb.b, gr.b)
+    finally:
+        gr.close()
+        gb.close()
+
+
+# ---- FindNextPoint / FindNextPoints on identical regressors --------------------------------------------------------------------
+SEARCH_CASES = [(S.MATERN, 6, 31, S.EI), (S.SE, 6, 31, S.EI), (S.MATERN, 8, 60, S.UCB), (S.SE, 16, 100, S.EI)]
+
+
+@pytest.mark.parametrize("kt,D,N,acq", SEARCH_CASES)
+def test_find_next_point_reference_driver_equals_the_reference(sides, kt, D, N, acq):
+    ref, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    y = S.make_y(X)
+    gr, gb = ref.gpr_given(kt, X, y, theta, 0.005), b200.gpr_given(kt, X, y, theta, 0.005)
+    try:
+        ref.srand(11)
+        x_r = ref.find_next_point(gr.reg, D, 50 * D, 10 * D, acq, 1.5)
+        b200.srand(11)
+        x_b = b200.find_next_point(gb.reg, D, 50 * D, 10 * D, acq, 1.5)
+        assert np.max(np.abs(x_b - x_r)) < RT, (x_b, x_r)
+    finally:
+        gr.close()
+        gb.close()
+
+
+@pytest.mark.parametrize("kt,D,N,acq", SEARCH_CASES)
+def test_device_maximiser_is_at_least_as_good_as_the_reference_search(sides, kt, D, N, acq):
+    """SearchDriver::Hybrid: the sweep + batched ascent against DIRECT + L-BFGS of the real reference, judged by the
+    REFERENCE's own acquisition function."""
+    ref, b200 = sides
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    y = S.make_y(X)
+    gr, gb = ref.gpr_given(kt, X, y, theta, 0.005), b200.gpr_given(kt, X, y, theta, 0.005)
+    try:
+        ref.srand(5)
+        x_r = ref.find_next_point(gr.reg, D, 50 * D, 10 * D, acq, 1.5)
+        pkg.hostlib.set_search_driver(pkg.hostlib.HYBRID)
+        x_b = b200.find_next_point(gb.reg, D, 50 * D, 10 * D, acq, 1.5)
+        v_r, v_b = ref.acq_value(gr.reg, x_r, acq, 1.5), ref.acq_value(gr.reg, x_b, acq, 1.5)
+        assert np.all(x_b >= 0.0) and np.all(x_b <= 1.0)
+        assert v_b >= v_r - 1e-6 * max(abs(v_r), 1e-12), (v_b, v_r)
+    finally:
+        gr.close()
+        gb.close()
+
+
+@pytest.mark.parametrize("kt,D,N,acq,n_points", [(S.MATERN, 5, 30, S.EI, 3), (S.SE, 6, 45, S.UCB, 2)])
+def test_find_next_points_against_the_reference(sides, kt, D, N, acq, n_points):
+    """Schonlau's batch (src/acquisition-function.cpp:246-298). Reference driver: the same points (the temporary regressor grows
+    by a bordered update here and by a rebuild there). Hybrid driver: every option at least as good under the reference's own
+    criterion, evaluated option by option on the reference side."""
+    ref, b200 = sides
+    X, theta = S.make_X(N, D, "sls"), S.make_theta(D, "perturbed")
+    y = S.make_y(X)
+    gr, gb = ref.gpr_given(kt, X, y, theta, 0.005), b200.gpr_given(kt, X, y, theta, 0.005)
+    try:
+        ref.srand(3)
+        P_r = ref.find_next_points(gr.reg, D, n_points, 40 * D, 10 * D, acq, 1.5)
+        pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+        b200.srand(3)
+        P_b = b200.find_next_points(gb.reg, D, n_points, 40 * D, 10 * D, acq, 1.5)
+        assert np.max(np.abs(P_b[0] - P_r[0])) < RT, (P_b[0], P_r[0])
+        # later options depend on the earlier ones through the grown model: 1e-4 absolute
+        assert np.max(np.abs(P_b - P_r)) < 1e-4, np.max(np.abs(P_b - P_r), axis=1)
+
+        pkg.hostlib.set_search_driver(pkg.hostlib.HYBRID)
+        P_h = b200.find_next_points(gb.reg, D, n_points, 40 * D, 10 * D, acq, 1.5)
+        assert P_h.shape == (n_points, D) and np.all(P_h >= 0) and np.all(P_h <= 1)
+        # first option: plain acquisition maximisation, comparable through the reference's CalcAcquisitionValue
+        # (only when the source kernel is Matern: the temporary regressor of FindNextPoints is ALWAYS Matern)
+        if kt == S.MATERN:
+            v_r, v_h = ref.acq_value(gr.reg, P_r[0], acq, 1.5), ref.acq_value(gr.reg, P_h[0], acq, 1.5)
+            assert v_h >= v_r - 1e-6 * max(abs(v_r), 1e-12), (v_h, v_r)
+        # the options are distinct points
+        for i in range(n_points):
+            for j in range(i):
+                assert np.linalg.norm(P_h[i] - P_h[j]) > 1e-3
+    finally:
+        gr.close()
+        gb.close()
+
+
+# ---- the whole loop: config 1 ------------------------------------------------------------------------------------------------
+def _first_divergence(log_r, log_b, tol):
+    for a, b in zip(log_r, log_b):
+        err = max(np.max(np.abs(a["end_0"] - b["end_0"])), np.max(np.abs(a["end_1"] - b["end_1"])))
+        if not err < tol:
+            return a["iter"], err
+    return None, 0.0
+
+
+@pytest.mark.parametrize("D,iters,seed,kt,use_map", [(6, 15, 1, S.MATERN, True), (6, 15, 2, S.SE, True), (4, 12, 3, S.MATERN, False)])
+def test_config1_submit_to_next_slider_matches_the_reference_loop(sides, D, iters, seed, kt, use_map):
+    ref, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    log_r = LS.run_sls_loop(ref, D, iters, seed, kt=kt, use_map=use_map, hyper=DEMO_HYPER)
+    log_b = LS.run_sls_loop(b200, D, iters, seed, kt=kt, use_map=use_map, hyper=DEMO_HYPER)
+    it, err = _first_divergence(log_r, log_b, RT)
+    matched = iters if it is None else it
+    print(f"\nconfig 1 (D={D}, {iters} iterations, seed {seed}, kernel {kt}, MAP hyper-parameters {use_map}): slider ends agree to {RT:g} for "
+          f"{matched} iterations" + ("" if it is None else f"; first divergence at iteration {it} (max |diff| {err:.3g})"))
+    for a, b in zip(log_r, log_b):
+        d = max(np.max(np.abs(a["end_0"] - b["end_0"])), np.max(np.abs(a["end_1"] - b["end_1"])))
+        print(f"  iter {a['iter']:2d}  N={a['n_points']:3d}  |ends diff| {d:9.2e}   reference {a['ms']:8.1f} ms   B200 {b['ms']:8.1f} ms   "
+              f"f(x+) ref {a['objective']:.4f} B200 {b['objective']:.4f}")
+    # the first iterations (N = 3, 5, 7 ...) must agree; the prefix length beyond that is reported, and both must converge
+    assert matched >= 3, (it, err)
+    assert log_b[-1]["objective"] > 0.9 and log_r[-1]["objective"] > 0.9
+
+
+def test_every_step_matches_when_replayed_from_the_reference_state(sides, ref):
+    """Loop-level divergence says nothing about a single step. Here every iteration of a reference run is replayed as ONE step
+    from the reference's state: both sides fit the regressor on the reference's data (X and the tuples are rebuilt through
+    PreferenceDataManager from the submitted batches), then FindNextPoint and the enlarged slider are compared."""
+    ref_loop, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    D, iters, seed = 6, 10, 4
+    ref_loop.srand(seed)
+    opt = ref_loop.sls(D, False, True, S.MATERN, S.EI)  # no enlargement: the slider ends ARE (x^+, x^EI), the next batch's "other" points
+    opt.set_hyperparams(*DEMO_HYPER)
+    batches, worst = [], {"y": 0.0, "theta": 0.0, "x_next": 0.0, "slider": 0.0}
+    for it in range(iters):
+        e0, e1 = opt.slider_ends()
+        t = LS.best_slider_position(e0, e1)
+        batches.append(np.stack([opt.calc_point(t), e0, e1], axis=1))
+        opt.submit(t)
+        X, offsets, idx = ref.data_manager_run(batches)
+        np.testing.assert_array_equal(X, opt.raw_data_points())
+        tuples = [list(idx[offsets[k]:offsets[k + 1]]) for k in range(len(offsets) - 1)]
+        fr = ref_loop.pref_fit(S.MATERN, X, tuples, True, *DEMO_HYPER, num_iters=100)
+        fb = b200.pref_fit(S.MATERN, X, tuples, True, *DEMO_HYPER, num_iters=100)
+        try:
+            (y_r, th_r, b_r), (y_b, th_b, b_b) = fr.state(), fb.state()
+            worst["y"] = max(worst["y"], _rel(y_b, y_r))
+            worst["theta"] = max(worst["theta"], _rel(th_b, th_r), abs(b_b - b_r) / b_r)
+            ref_loop.srand(100 + it)
+            x_r = ref_loop.find_next_point(fr.reg, D, 50 * D, 10 * D)
+            b200.srand(100 + it)
+            x_b = b200.find_next_point(fb.reg, D, 50 * D, 10 * D)
+            worst["x_next"] = max(worst["x_next"], float(np.max(np.abs(x_b - x_r))))
+            s_r, s_b = ref_loop.slider(fr.find_arg_max(), x_r), b200.slider(fb.find_arg_max(), x_b)
+            worst["slider"] = max(worst["slider"], float(np.max(np.abs(s_r[0] - s_b[0]))), float(np.max(np.abs(s_r[1] - s_b[1]))))
+        finally:
+            fr.close()
+            fb.close()
+    opt.close()
+    print(f"\nreplayed steps, worst differences over {iters} iterations: {worst}")
+    assert max(worst.values()) < RT, worst
+
+
+# ---- PreferentialBayesianOptimizer ---------------------------------------------------------------------------------------------
+def test_pbo_loop_against_the_reference(sides):
+    ref, b200 = sides
+    pkg.hostlib.set_search_driver(pkg.hostlib.REFERENCE)
+    D, n_opt, iters, seed = 4, 3, 6, 9
+    logs = []
+    for L in (ref, b200):
+        L.srand(seed)
+        opt = L.pbo(D, True, S.MATERN, S.EI, 0, n_opt)
+        opt.set_hyperparams(*DEMO_HYPER)
+        rows = []
+        for it in range(iters):
+            options = opt.current_options()
+            best = int(np.argmax([LS.demo_objective(o) for o in options]))
+            opt.submit(best)
+            opt.determine_next_query()
+            rows.append(opt.current_options().copy())
+        opt.close()
+        logs.append(rows)
+    matched = 0
+    for a, b in zip(*logs):
+        if np.max(np.abs(a - b)) < 1e-4:
+            matched += 1
+        else:
+            break
+    print(f"\nPBO loop (D={D}, {n_opt} options): options agree to 1e-4 for {matched} of {iters} iterations")
+    assert matched >= 2
+    assert max(LS.demo_objective(o) for o in logs[1][-1]) > 0.8
