@@ -13,6 +13,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LOOP_PATH = os.path.join(ROOT, "oracle", "_ref", "libsls_ref_loop.so")
+REF_LOOP_FMA_PATH = os.path.join(ROOT, "oracle", "_ref", "libsls_ref_loop_fma.so")  # same sources, FMA contraction allowed
 HOST_PATH = os.path.join(ROOT, "sequential-line-search_b200", "lib", "libsls_b200_host.so")
 
 c_dp = C.POINTER(C.c_double)
@@ -34,15 +35,16 @@ def ref_loop_available() -> bool:
 
 
 class LoopLib:
-    """One side of the comparison. ``side`` is "ref" (CPU reference) or "b200" (GPU host layer)."""
+    """One side of the comparison. ``side`` is "ref" (CPU reference), "ref_fma" (the same reference sources compiled with FMA
+    contraction: the yardstick for the reference's own reproducibility) or "b200" (GPU host layer)."""
 
     _POINTER = ("sls_create", "pbo_create", "pref_fit", "pref_fit_regressor", "gpr_fit", "gpr_given", "gpr_fit_regressor")
     _DOUBLE = ("sls_query", "loop_acq_value", "loop_predict")
 
     def __init__(self, side: str):
-        assert side in ("ref", "b200")
-        self.side = side
-        self.lib = C.CDLL(REF_LOOP_PATH if side == "ref" else HOST_PATH)
+        assert side in ("ref", "ref_fma", "b200")
+        self.lib = C.CDLL({"ref": REF_LOOP_PATH, "ref_fma": REF_LOOP_FMA_PATH, "b200": HOST_PATH}[side])
+        self.side = side = "ref" if side == "ref_fma" else side
         for n in self._POINTER:
             self.fn(n).restype = C.c_void_p
         for n in self._DOUBLE:
