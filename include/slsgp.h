@@ -75,6 +75,10 @@ extern "C"
 
     /* Reference quirks that parity has to reproduce; all on by default. */
 #define SLSGP_COMPAT_SE_XGRAD_2X 1u /* mathtoolbox kernel-functions.cpp:92 returns -2 k (x_a-x_b)/l^2 */
+    /* Off by default: the reference's compile-time option SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION (CMakeLists.txt:28-33,
+     * src/preference-regressor.cpp:48-52,139,178-192,237): slsgp_map_objective_pref with use_map_hyperparams builds K = K_f (the
+     * noise entry of x is ignored, b = 0), drops the prior on b and returns d/db = 0. */
+#define SLSGP_COMPAT_NOISELESS 2u
 
     /* ---- context -------------------------------------------------------------------------------------------- */
     slsgp_status slsgp_ctx_create(int device, slsgp_ctx** ctx_out);
@@ -83,6 +87,7 @@ extern "C"
     const char*  slsgp_status_string(slsgp_status s);
     slsgp_status slsgp_set_compat_flags(slsgp_ctx* ctx, unsigned flags);
     slsgp_status slsgp_set_sweep_mode(slsgp_ctx* ctx, slsgp_sweep_mode mode);
+    slsgp_status slsgp_get_sweep_mode(const slsgp_ctx* ctx, slsgp_sweep_mode* mode_out);
     /* Use a caller-owned CUDA stream (a cudaStream_t passed as void*) instead of the context's own; NULL restores
      * the context's stream. Lets a host framework order libslsgp work with its own copies and events. */
     slsgp_status slsgp_set_stream(slsgp_ctx* ctx, void* cuda_stream);
@@ -92,6 +97,22 @@ extern "C"
      * Replaces the regressors' `m_X` copy (src/preference-regressor.cpp:273, gaussian-process-regressor.cpp:203).
      * Uploads X (D x N, column-major, host memory) and invalidates every derived quantity. */
     slsgp_status slsgp_set_data(slsgp_ctx* ctx, const double* X, int N, int D);
+
+    /* Frees the per-shard sweep workspaces of the context when they hold more than keep_bytes (they only ever grow with the
+     * largest batch seen); the fitted model stays. For hosts that pool contexts. */
+    slsgp_status slsgp_trim(slsgp_ctx* ctx, size_t keep_bytes);
+
+    /* ---- L1 arrays on request --------------------------------------------------------------------------------------
+     * The fused sweep and MAP kernels never materialise these; they are offered for callers of the reference's free functions.
+     * Both work on the context's X with the GIVEN theta and leave a fitted model untouched.
+     *   slsgp_small_k                CalcSmallK (src/regressor.cpp:45-59): k_out[i] = k(x, X_i), N values, and
+     *                                CalcSmallKSmallXDerivative (:91-108): dk_dx_out (D x N, column i = d k(x, X_i) / d x);
+     *                                either output may be NULL
+     *   slsgp_gram_theta_derivative  CalcLargeKYThetaDerivative (:110-134): out = D + 1 matrices of N x N, back to back
+     *                                (d K / d a, d K / d l_1, ...); CalcLargeKYNoiseLevelDerivative (:136-141) is the identity. */
+    slsgp_status slsgp_small_k(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, const double* x, double* k_out,
+                               double* dk_dx_out);
+    slsgp_status slsgp_gram_theta_derivative(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, double* out);
 
     /* ---- K1: Gram matrix --------------------------------------------------------------------------------------
      * K_y = K_f + noise * I: CalcLargeKY / CalcLargeKF (src/regressor.cpp:61-89) with the per-pair kernels

@@ -483,16 +483,17 @@ static void gp_hyper_gradient(int kt, int D, int N, const double* X, const doubl
     free(tensor);
 }
 
-/* objective() of PreferenceRegressor (src/preference-regressor.cpp:129-259) */
-double slsgp_oracle_map_objective_pref(int kt, int D, int N, const double* X, int P, const unsigned* offsets,
-                                       const unsigned* idx, int use_map, double default_a, double default_r,
-                                       double default_b, double prior_var, double btl_scale, const double* x,
-                                       double* grad)
+/* objective() of PreferenceRegressor (src/preference-regressor.cpp:129-259). noiseless != 0 restates the build with
+ * SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION (:48-52, :141, :180-188, :237): with use_map the kernel matrix is K_f (b = 0
+ * whatever x[N + 1] holds), b has no prior and d/db = 0; without use_map the option changes nothing (m_K keeps the default noise). */
+static double map_objective_pref(int kt, int D, int N, const double* X, int P, const unsigned* offsets, const unsigned* idx,
+                                 int use_map, double default_a, double default_r, double default_b, double prior_var,
+                                 double btl_scale, const double* x, double* grad, int noiseless)
 {
     const double* y     = x;
     double*       theta = (double*) malloc(sizeof(double) * (size_t) (D + 1));
     theta[0]            = use_map ? x[N + 0] : default_a;                       /* :139 */
-    const double b      = use_map ? x[N + 1] : default_b;                       /* :143 */
+    const double b      = use_map ? (noiseless ? 0.0 : x[N + 1]) : default_b;   /* :141-143 */
     for (int i = 0; i < D; ++i) theta[1 + i] = use_map ? x[N + 2 + i] : default_r; /* :145-147 */
 
     double obj = 0.0;
@@ -520,7 +521,7 @@ double slsgp_oracle_map_objective_pref(int kt, int D, int N, const double* X, in
     if (use_map)
     {
         obj += slsgp_oracle_log_lognormal(theta[0], log(default_a), prior_var);
-        obj += slsgp_oracle_log_lognormal(b, log(default_b), prior_var);
+        if (!noiseless) obj += slsgp_oracle_log_lognormal(b, log(default_b), prior_var); /* :184-186 */
         for (int i = 0; i < D; ++i) obj += slsgp_oracle_log_lognormal(theta[1 + i], log(default_r), prior_var);
     }
 
@@ -548,7 +549,7 @@ double slsgp_oracle_map_objective_pref(int kt, int D, int N, const double* X, in
             double  g_b;
             gp_hyper_gradient(kt, D, N, X, theta, Kinv, alpha, g_theta, &g_b);
             grad[N + 0] = g_theta[0] + slsgp_oracle_log_lognormal_derivative(theta[0], log(default_a), prior_var);
-            grad[N + 1] = g_b + slsgp_oracle_log_lognormal_derivative(b, log(default_b), prior_var);
+            grad[N + 1] = noiseless ? 0.0 : g_b + slsgp_oracle_log_lognormal_derivative(b, log(default_b), prior_var); /* :237 */
             for (int i = 0; i < D; ++i)
                 grad[N + 2 + i] =
                     g_theta[1 + i] + slsgp_oracle_log_lognormal_derivative(theta[1 + i], log(default_r), prior_var);
@@ -559,6 +560,22 @@ double slsgp_oracle_map_objective_pref(int kt, int D, int N, const double* X, in
     free(K);
     free(theta);
     return obj;
+}
+
+double slsgp_oracle_map_objective_pref(int kt, int D, int N, const double* X, int P, const unsigned* offsets,
+                                       const unsigned* idx, int use_map, double default_a, double default_r,
+                                       double default_b, double prior_var, double btl_scale, const double* x,
+                                       double* grad)
+{
+    return map_objective_pref(kt, D, N, X, P, offsets, idx, use_map, default_a, default_r, default_b, prior_var, btl_scale, x, grad, 0);
+}
+
+double slsgp_oracle_map_objective_pref_noiseless(int kt, int D, int N, const double* X, int P, const unsigned* offsets,
+                                                 const unsigned* idx, int use_map, double default_a, double default_r,
+                                                 double default_b, double prior_var, double btl_scale, const double* x,
+                                                 double* grad)
+{
+    return map_objective_pref(kt, D, N, X, P, offsets, idx, use_map, default_a, default_r, default_b, prior_var, btl_scale, x, grad, 1);
 }
 
 /* objective() of GaussianProcessRegressor (src/gaussian-process-regressor.cpp:141-193) with the hard-coded

@@ -100,6 +100,12 @@ extern "C"
                                            int use_map_hyperparams, double default_a, double default_r,
                                            double default_b, double prior_var, double btl_scale,
                                            const double* x, double* grad);
+    /* the same objective as the reference's SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION build evaluates it */
+    double slsgp_oracle_map_objective_pref_noiseless(int kernel_type, int D, int N, const double* X, int P,
+                                           const unsigned* offsets, const unsigned* idx,
+                                           int use_map_hyperparams, double default_a, double default_r,
+                                           double default_b, double prior_var, double btl_scale,
+                                           const double* x, double* grad);
     /* GaussianProcessRegressor objective (src/gaussian-process-regressor.cpp:141-193), x = (a, b, r_1..r_D). */
     double slsgp_oracle_map_objective_gpr(int kernel_type, int D, int N, const double* X, const double* y,
                                           const double* x, double* grad);

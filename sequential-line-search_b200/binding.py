@@ -19,7 +19,7 @@ OK, ERR_INVALID, ERR_STATE, ERR_NOT_SPD, ERR_NAN, ERR_CUDA, ERR_NOMEM = range(7)
 KERNEL_ARD_SQUARED_EXP, KERNEL_ARD_MATERN52 = 0, 1
 ACQ_EXPECTED_IMPROVEMENT, ACQ_GP_UCB = 0, 1
 SWEEP_FP64, SWEEP_TENSOR, SWEEP_TENSOR_X2, SWEEP_TENSOR_X1 = 0, 1, 2, 3
-COMPAT_SE_XGRAD_2X = 1
+COMPAT_SE_XGRAD_2X, COMPAT_NOISELESS = 1, 2
 
 # every symbol include/slsgp.h declares: (name, restype, argtypes)
 _API = [
@@ -29,6 +29,7 @@ _API = [
     ("slsgp_status_string", C.c_char_p, [C.c_int]),
     ("slsgp_set_compat_flags", C.c_int, [C.c_void_p, C.c_uint]),
     ("slsgp_set_sweep_mode", C.c_int, [C.c_void_p, C.c_int]),
+    ("slsgp_get_sweep_mode", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
     ("slsgp_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slsgp_synchronize", C.c_int, [C.c_void_p]),
     ("slsgp_set_data", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
@@ -54,6 +55,9 @@ _API = [
     ("slsgp_map_objective_pref_whitened", C.c_int, [C.c_void_p, c_dp, C.c_double, c_dp, c_dp, c_dp]),
     ("slsgp_whiten", C.c_int, [C.c_void_p, c_dp, c_dp]),
     ("slsgp_map_objective_gpr", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    ("slsgp_trim", C.c_int, [C.c_void_p, C.c_size_t]),
+    ("slsgp_small_k", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp, c_dp, c_dp]),
+    ("slsgp_gram_theta_derivative", C.c_int, [C.c_void_p, C.c_int, c_dp, c_dp]),
     ("slsgp_launch_count", C.c_uint64, [C.c_void_p]),
     ("slsgp_last_phase_ms", C.c_double, [C.c_void_p, C.c_char_p]),
     ("slsgp_profile_enable", C.c_int, [C.c_void_p, C.c_int]),
@@ -240,6 +244,24 @@ class Context:
         self._check(self.lib.slsgp_acq_maximize(self.h, acq_type, ucb_beta, seed, first, count, n_starts, n_iters, _p(x), C.byref(v),
                                                 _p(g), C.byref(vs)))
         return x, v.value, g, vs.value
+
+    def small_k(self, kernel_type, theta, x, want_derivative=True):
+        """CalcSmallK / CalcSmallKSmallXDerivative on the context's X: (k [N], dk/dx [D x N] or None)."""
+        theta, x = _f64(theta), _f64(x)
+        k = np.empty(self.N)
+        dk = np.empty((self.D, self.N), order="F") if want_derivative else None
+        self._check(self.lib.slsgp_small_k(self.h, kernel_type, _p(theta), _p(x), _p(k), _p(dk)))
+        return k, dk
+
+    def gram_theta_derivative(self, kernel_type, theta):
+        """CalcLargeKYThetaDerivative: array [D + 1, N, N]."""
+        theta = _f64(theta)
+        out = np.empty((self.D + 1, self.N * self.N))
+        self._check(self.lib.slsgp_gram_theta_derivative(self.h, kernel_type, _p(theta), _p(out)))
+        return out.reshape(self.D + 1, self.N, self.N).transpose(0, 2, 1)
+
+    def trim(self, keep_bytes=0):
+        self._check(self.lib.slsgp_trim(self.h, keep_bytes))
 
     def argmax_device(self, d_val, count, index0=0):
         val, idx = C.c_double(), C.c_int64()

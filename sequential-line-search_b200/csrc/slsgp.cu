@@ -19,6 +19,7 @@
 #include "small.cuh"
 #include "maximize.cuh"
 #include "tc_sweep.cuh"
+#include "l1.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -870,30 +871,24 @@ extern "C"
         }
         slsgp_ctx* ctx = new slsgp_ctx;
         ctx->device    = device;
-        if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess)
-        {
-            delete ctx;
-            return SLSGP_ERR_CUDA;
-        }
-        ctx->stream       = ctx->own_stream;
-        bool aux_ok = cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking) == cudaSuccess &&
-                      cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) == cudaSuccess &&
-                      cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
-        for (int b = 0; b < 2 && aux_ok; ++b)
-            aux_ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ctx->ev_main[b], cudaEventDisableTiming) == cudaSuccess &&
-                     cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
-        if (!aux_ok)
-        {
-            delete ctx;
-            return SLSGP_ERR_CUDA;
-        }
+        // every failure below goes through slsgp_ctx_destroy, which releases whatever had been created by then
+        bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+        ctx->stream = ctx->own_stream;
+        ok = ok && cudaStreamCreateWithFlags(&ctx->pre_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaStreamCreateWithFlags(&ctx->post_stream, cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming) == cudaSuccess;
+        for (int b = 0; b < 2 && ok; ++b)
+            ok = cudaEventCreateWithFlags(&ctx->ev_in[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_main[b], cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
         if (const char* e = std::getenv("SLSGP_TC_PAIR")) ctx->tc_ncta = std::atoi(e) ? 2 : 1;
         ctx->pinned_bytes = 1 << 16;
-        if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess)
+        ok                = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;
+        if (!ok)
         {
-            cudaStreamDestroy(ctx->own_stream);
-            delete ctx;
+            cudaGetLastError();
+            ctx->pinned = ok ? ctx->pinned : nullptr;
+            slsgp_ctx_destroy(ctx);
             return SLSGP_ERR_CUDA;
         }
         *ctx_out = ctx;
@@ -904,7 +899,7 @@ extern "C"
     {
         if (!ctx) return SLSGP_OK;
         cudaSetDevice(ctx->device);
-        cudaStreamSynchronize(ctx->stream);
+        if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         DevBuf* all[] = {&ctx->X, &ctx->Xpad, &ctx->XT1, &ctx->theta, &ctx->inv_l, &ctx->K, &ctx->L, &ctx->W,
                          &ctx->Kinv, &ctx->T, &ctx->y, &ctx->alpha, &ctx->Kalpha, &ctx->vec, &ctx->scalars,
                          &ctx->info, &ctx->fbest, &ctx->fbest_idx, &ctx->pref_off, &ctx->pref_idx, &ctx->slot_off,
@@ -925,15 +920,37 @@ extern "C"
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
         for (int b = 0; b < 2; ++b)
         {
-            cudaEventDestroy(ctx->ev_in[b]);
-            cudaEventDestroy(ctx->ev_main[b]);
-            cudaEventDestroy(ctx->ev_out[b]);
+            if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
+            if (ctx->ev_main[b]) cudaEventDestroy(ctx->ev_main[b]);
+            if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
         }
-        cudaEventDestroy(ctx->ev_start);
-        cudaStreamDestroy(ctx->pre_stream);
-        cudaStreamDestroy(ctx->post_stream);
-        cudaStreamDestroy(ctx->own_stream);
+        if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+        if (ctx->pre_stream) cudaStreamDestroy(ctx->pre_stream);
+        if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
         delete ctx;
+        return SLSGP_OK;
+    }
+
+    // Release the per-shard sweep workspaces (the buffers that only ever grow with the largest batch seen) when they hold more
+    // than keep_bytes; the model itself (X, K, L, W, K^-1, alpha) stays. They are re-allocated by the next sweep.
+    slsgp_status slsgp_trim(slsgp_ctx* ctx, size_t keep_bytes)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        DevBuf* scratch[] = {&ctx->Xq, &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu, &ctx->o_sigma, &ctx->o_dmu,
+                             &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->Ks, &ctx->comb, &ctx->tc_qx, &ctx->tc_P2x, &ctx->mx_best, &ctx->mx_X,
+                             &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
+        size_t  total     = 0;
+        for (DevBuf* b : scratch) total += b->bytes;
+        if (total <= keep_bytes) return SLSGP_OK;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (DevBuf* b : scratch)
+        {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr, b->bytes = 0;
+        }
+        ctx->Mcap = 0, ctx->tc_Mcap = 0;
         return SLSGP_OK;
     }
 
@@ -952,6 +969,13 @@ extern "C"
         if (mode != SLSGP_SWEEP_FP64 && !is_tensor_mode(mode)) return fail(ctx, SLSGP_ERR_INVALID, "unknown sweep mode");
         if (is_tensor_mode(mode) != is_tensor_mode(ctx->sweep_mode)) ctx->Mcap = 0; // the per-shard scratch differs between the two modes
         ctx->sweep_mode = mode;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_get_sweep_mode(const slsgp_ctx* ctx, slsgp_sweep_mode* mode_out)
+    {
+        if (!ctx || !mode_out) return SLSGP_ERR_INVALID;
+        *mode_out = (slsgp_sweep_mode) ctx->sweep_mode;
         return SLSGP_OK;
     }
 
@@ -1452,6 +1476,75 @@ extern "C"
     }
 
     // ---------------------------------------------------------------------------------------------------------
+    // L1 arrays on request (l1.cuh). theta / x go through the scratch buffer `comb`, so a fitted model is left untouched.
+    // ---------------------------------------------------------------------------------------------------------
+    static slsgp_status l1_upload(slsgp_ctx* ctx, const double* theta, const double* x, double** d_theta, double** d_inv_l, double** d_x)
+    {
+        const int D = ctx->D;
+        for (int i = 0; i <= D; ++i)
+            if (!std::isfinite(theta[i])) return fail(ctx, SLSGP_ERR_NAN, "non-finite kernel hyper-parameter");
+        TRY(ensure(ctx, ctx->comb, sizeof(double) * (size_t) (3 * D + 1)));
+        double* h = ctx->pinned;
+        for (int i = 0; i <= D; ++i) h[i] = theta[i];
+        for (int i = 0; i < D; ++i) h[D + 1 + i] = 1.0 / theta[1 + i];
+        for (int i = 0; i < D; ++i) h[2 * D + 1 + i] = x ? x[i] : 0.0;
+        CUDA_TRY(cudaMemcpyAsync(ctx->comb.p, h, sizeof(double) * (size_t) (3 * D + 1), cudaMemcpyHostToDevice, ctx->stream));
+        *d_theta = dp(ctx->comb), *d_inv_l = dp(ctx->comb) + D + 1, *d_x = dp(ctx->comb) + 2 * D + 1;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_small_k(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, const double* x, double* k_out,
+                               double* dk_dx_out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_small_k before slsgp_set_data");
+        if (!theta || !x || (kernel_type != 0 && kernel_type != 1)) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_small_k: bad arguments");
+        const int N = ctx->N, D = ctx->D;
+        for (int d = 0; d < D; ++d)
+            if (!std::isfinite(x[d])) return fail(ctx, SLSGP_ERR_NAN, "slsgp_small_k: non-finite x");
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        double *d_theta, *d_inv_l, *d_x;
+        TRY(l1_upload(ctx, theta, x, &d_theta, &d_inv_l, &d_x));
+        DevBuf out; // k (N) followed by dk/dx (D x N)
+        TRY(ensure(ctx, out, sizeof(double) * (size_t) (D + 1) * N));
+        double *d_k = dp(out), *d_dk = dp(out) + N;
+        small_k_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), N, D, d_x, d_theta, d_inv_l, (int) kernel_type,
+                                                                 (ctx->compat & SLSGP_COMPAT_SE_XGRAD_2X) ? 2.0 : 1.0, k_out ? d_k : nullptr,
+                                                                 dk_dx_out ? d_dk : nullptr);
+        ++ctx->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess && k_out) e = cudaMemcpyAsync(k_out, d_k, sizeof(double) * (size_t) N, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess && dk_dx_out) e = cudaMemcpyAsync(dk_dx_out, d_dk, sizeof(double) * (size_t) N * D, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(out.p);
+        if (e != cudaSuccess) return fail(ctx, SLSGP_ERR_CUDA, std::string("slsgp_small_k: ") + cudaGetErrorString(e));
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_gram_theta_derivative(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, double* out)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!ctx->has_data) return fail(ctx, SLSGP_ERR_STATE, "slsgp_gram_theta_derivative before slsgp_set_data");
+        if (!theta || !out || (kernel_type != 0 && kernel_type != 1)) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_gram_theta_derivative: bad arguments");
+        const int N = ctx->N, D = ctx->D;
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        double *d_theta, *d_inv_l, *d_x;
+        TRY(l1_upload(ctx, theta, nullptr, &d_theta, &d_inv_l, &d_x));
+        DevBuf       planes;
+        const size_t bytes = sizeof(double) * (size_t) (D + 1) * N * N;
+        TRY(ensure(ctx, planes, bytes));
+        gram_theta_derivative_kernel<<<dim3((N + 15) / 16, (N + 15) / 16), dim3(16, 16), 0, ctx->stream>>>(dp(ctx->X), N, D, d_theta, d_inv_l,
+                                                                                                          (int) kernel_type, dp(planes));
+        ++ctx->launches;
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out, planes.p, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        cudaFree(planes.p);
+        if (e != cudaSuccess) return fail(ctx, SLSGP_ERR_CUDA, std::string("slsgp_gram_theta_derivative: ") + cudaGetErrorString(e));
+        return SLSGP_OK;
+    }
+
+    // ---------------------------------------------------------------------------------------------------------
     // K5 / K6
     // ---------------------------------------------------------------------------------------------------------
     slsgp_status slsgp_set_preferences(slsgp_ctx* ctx, const uint32_t* offsets, const uint32_t* idx, int P)
@@ -1625,16 +1718,20 @@ extern "C"
         double              logdet = 0.0, gp = 0.0;
         std::vector<double> gh((size_t) D + 2);
         const bool          want_hyper = grad_out && use_map, small = use_map && small_model_applies(ctx);
+        // SLSGP_COMPAT_NOISELESS: the reference's SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION build (:48-52, 139, 178-192, 237):
+        // K = K_f (b fixed at 0 whatever x holds), no prior on b, d/db = 0
+        const bool   noiseless = use_map && (ctx->compat & SLSGP_COMPAT_NOISELESS);
+        const double b_used    = noiseless ? 0.0 : (use_map ? x[N + 1] : 0.0);
         if (use_map)
         {
             std::vector<double> theta((size_t) D + 1);
             theta[0] = x[N + 0];
             for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[N + 2 + i];
             if (small) // one launch: model, alpha, scalars and the length-scale gradient (small.cuh); read back with the BTL terms
-                TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), x[N + 1], x, want_hyper));
+                TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), b_used, x, want_hyper));
             else
             {
-                TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[N + 1]));
+                TRY(do_gram(ctx, (int) kernel_type, theta.data(), b_used));
                 TRY(do_factor(ctx, &logdet));
                 CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
                 TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
@@ -1678,12 +1775,12 @@ extern "C"
         {
             const double a = x[N], b = x[N + 1];
             obj += log_lognormal(a, std::log(default_a), prior_var);
-            obj += log_lognormal(b, std::log(default_b), prior_var);
+            if (!noiseless) obj += log_lognormal(b, std::log(default_b), prior_var);
             for (int i = 0; i < D; ++i) obj += log_lognormal(x[N + 2 + i], std::log(default_r), prior_var);
             if (grad_out)
             {
                 grad_out[N + 0] = gh[0] + log_lognormal_derivative(a, std::log(default_a), prior_var);
-                grad_out[N + 1] = gh[1] + log_lognormal_derivative(b, std::log(default_b), prior_var);
+                grad_out[N + 1] = noiseless ? 0.0 : gh[1] + log_lognormal_derivative(b, std::log(default_b), prior_var);
                 for (int i = 0; i < D; ++i)
                     grad_out[N + 2 + i] = gh[(size_t) 2 + i] + log_lognormal_derivative(x[N + 2 + i], std::log(default_r), prior_var);
             }

@@ -10,14 +10,17 @@
 // fallback: constructing a regressor without a usable CUDA device throws std::runtime_error.
 //
 // Deviations from the reference surface:
-//   * PreferenceRegressor::m_K_llt (an Eigen::LLT computed on the host) is replaced by m_L, the lower Cholesky factor
-//     read back from the device; define SLS_B200_HOST_LLT to also get the Eigen::LLT member (host O(N^3)).
-//   * CalcSmallK / CalcSmallKSmallXDerivative / CalcLargeKYThetaDerivative are never materialised by the device path
-//     (they are fused into the sweep and MAP kernels) and are not offered as free functions.
+//   * PreferenceRegressor::m_K_llt is an Eigen::LLT computed on the host (O(N^3)); it is built when the header is compiled
+//     against the real Eigen (not the bundled include/eigen-lite subset) or with SLS_B200_HOST_LLT defined, and omitted
+//     otherwise. m_L, the lower Cholesky factor read back from the device, is always there.
+//   * Copies of a device-backed regressor are deep: the copy refits its own device model on first use.
 #ifndef SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP
 #define SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP
 
 #include <Eigen/Core>
+#if !defined(SLS_B200_HOST_LLT) && !defined(EIGEN_LITE_CORE)
+#define SLS_B200_HOST_LLT 1 // the real Eigen is present: keep the reference's public member m_K_llt
+#endif
 #ifdef SLS_B200_HOST_LLT
 #include <Eigen/Cholesky>
 #endif
@@ -88,6 +91,13 @@ namespace sequential_line_search
     {
     public:
         explicit DeviceRegressor(const KernelType kernel_type);
+        // Value semantics as in the reference (it copy-assigns its temporary regressor, src/acquisition-function.cpp:294): a copy
+        // shares NOTHING with its source. The device model is not duplicated eagerly; the copy rebuilds it from its own host
+        // state (X, y, hyper-parameters) the first time it is asked for a prediction. Moves take the model along.
+        DeviceRegressor(const DeviceRegressor& other);
+        DeviceRegressor& operator=(const DeviceRegressor& other);
+        DeviceRegressor(DeviceRegressor&& other) noexcept            = default;
+        DeviceRegressor& operator=(DeviceRegressor&& other) noexcept = default;
 
         double          PredictMu(const Eigen::VectorXd& x) const override;
         double          PredictSigma(const Eigen::VectorXd& x) const override;
@@ -101,8 +111,8 @@ namespace sequential_line_search
                           Eigen::MatrixXd*       mu_derivative    = nullptr,
                           Eigen::MatrixXd*       sigma_derivative = nullptr) const;
 
-        bool       HasModel() const { return m_fitted; }
-        slsgp_ctx* Device() const { return m_device.get(); }
+        bool       HasModel() const { return m_fitted || m_refit_pending; }
+        slsgp_ctx* Device() const; // the context holding this regressor's model (rebuilt first if this is a fresh copy)
         std::mutex& DeviceMutex() const { return *m_mutex; } // calls on one context are serialised
 
     protected:
@@ -115,10 +125,13 @@ namespace sequential_line_search
                          Eigen::MatrixXd*       Kinv_out,
                          Eigen::MatrixXd*       L_out);
         void EnsureDevice();
+        // Rebuild the device model from the host state of the derived class (used by copies).
+        virtual void RefitOnDevice() = 0;
 
         std::shared_ptr<slsgp_ctx>  m_device;
         std::shared_ptr<std::mutex> m_mutex;
         bool                        m_fitted = false, m_data_on_device = false;
+        mutable bool                m_refit_pending = false; // a copy that has not rebuilt its model yet
     };
 
     class GaussianProcessRegressor : public DeviceRegressor
@@ -160,6 +173,7 @@ namespace sequential_line_search
 
     private:
         void PerformMapEstimation();
+        void RefitOnDevice() override;
 
         Eigen::MatrixXd m_X;
         Eigen::VectorXd m_y;
@@ -231,6 +245,7 @@ namespace sequential_line_search
         unsigned        m_num_map_evaluations = 0;
 
         void PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start);
+        void RefitOnDevice() override;
     };
 
     // K_y = K_f + noise I and K_f for one of the two library kernels, built by the device Gram kernel
@@ -240,6 +255,27 @@ namespace sequential_line_search
                                 const double           noise_level,
                                 const Kernel           kernel);
     Eigen::MatrixXd CalcLargeKF(const Eigen::MatrixXd& X, const Eigen::VectorXd& kernel_hyperparameters, const Kernel kernel);
+
+    // The remaining L1 free functions of the reference (regressor.hpp:42-70), for programs that call them directly; the
+    // regressors themselves never do (the sweep and MAP kernels fuse these arrays away). Device kernels for the library's two
+    // kernels, the reference's own per-pair loop for a foreign function pointer.
+    Eigen::VectorXd CalcSmallK(const Eigen::VectorXd& x,
+                               const Eigen::MatrixXd& X,
+                               const Eigen::VectorXd& kernel_hyperparameters,
+                               const Kernel           kernel);
+    Eigen::MatrixXd CalcSmallKSmallXDerivative(const Eigen::VectorXd&         x,
+                                               const Eigen::MatrixXd&         X,
+                                               const Eigen::VectorXd&         kernel_hyperparameters,
+                                               const KernelFirstArgDerivative kernel_first_arg_derivative);
+    std::vector<Eigen::MatrixXd> CalcLargeKYThetaDerivative(const Eigen::MatrixXd&      X,
+                                                            const Eigen::VectorXd&      kernel_hyperparameters,
+                                                            const KernelThetaDerivative kernel_theta_derivative);
+    Eigen::MatrixXd CalcLargeKYNoiseLevelDerivative(const Eigen::MatrixXd& X,
+                                                    const Eigen::VectorXd& kernel_hyperparameters,
+                                                    const double           noise_level);
+
+    // Frees the idle device contexts the library keeps for re-use by the next regressor (addition).
+    void ReleaseDeviceResources();
 } // namespace sequential_line_search
 
 #endif // SEQUENTIAL_LINE_SEARCH_B200_REGRESSORS_HPP

@@ -63,8 +63,9 @@ namespace sequential_line_search
 
         void device_acq(const DeviceRegressor& r, const double* Xq, long M, AcquisitionFuncType type, double beta, double* val, double* grad)
         {
+            slsgp_ctx* const            c = r.Device();
             std::lock_guard<std::mutex> lock(r.DeviceMutex());
-            check(r.Device(), slsgp_acq_batch(r.Device(), internal::to_abi(type), beta, Xq, M, val, grad), "slsgp_acq_batch");
+            check(c, slsgp_acq_batch(c, internal::to_abi(type), beta, Xq, M, val, grad), "slsgp_acq_batch");
         }
 
         // maximise `value_and_gradient` over [0, 1]^D from x0 within `max_evals` evaluations
@@ -97,6 +98,32 @@ namespace sequential_line_search
             const VectorXd x_global = internal::nlopt_solve(x_ini, upper, lower, objective, internal::NloptAlgorithm::GN_DIRECT, true, (int) n_global);
             return internal::nlopt_solve(x_global, upper, lower, objective, internal::NloptAlgorithm::LD_LBFGS, true, (int) n_local);
         }
+
+        // Sets the sweep arithmetic of a regressor's context for the lifetime of the guard and puts the previous mode back on
+        // every exit path (exceptions included), so a failed search never leaves a user's regressor answering in 1e-3-class
+        // arithmetic. The regressor must not serve other threads while a search runs on it.
+        class SweepModeGuard
+        {
+        public:
+            SweepModeGuard(const DeviceRegressor& r, slsgp_sweep_mode mode) : m_r(r), m_ctx(r.Device())
+            {
+                std::lock_guard<std::mutex> lock(m_r.DeviceMutex());
+                check(m_ctx, slsgp_get_sweep_mode(m_ctx, &m_previous), "slsgp_get_sweep_mode");
+                check(m_ctx, slsgp_set_sweep_mode(m_ctx, mode), "slsgp_set_sweep_mode");
+            }
+            ~SweepModeGuard()
+            {
+                std::lock_guard<std::mutex> lock(m_r.DeviceMutex());
+                slsgp_set_sweep_mode(m_ctx, m_previous);
+            }
+            SweepModeGuard(const SweepModeGuard&)            = delete;
+            SweepModeGuard& operator=(const SweepModeGuard&) = delete;
+
+        private:
+            const DeviceRegressor& m_r;
+            slsgp_ctx*             m_ctx;
+            slsgp_sweep_mode       m_previous = SLSGP_SWEEP_FP64;
+        };
 
         uint64_t search_seed(const Regressor& r) { return 0x9E3779B97F4A7C15ull ^ ((uint64_t) r.GetLargeX().cols() << 20) ^ (uint64_t) r.GetNumDims(); }
     } // namespace
@@ -169,18 +196,18 @@ namespace sequential_line_search
             VectorXd       x0    = VectorXd::Zero(D);
             if (const DeviceRegressor* d = device_of(regressor))
             {
-                std::lock_guard<std::mutex> lock(d->DeviceMutex());
-                slsgp_ctx*                  c = d->Device();
                 // the tensor-core sweep pays off for large candidate counts; the ascent and the polish are FP64
                 const bool tensor = count >= 32768 && D <= (regressor.GetKernelType() == KernelType::ArdSquaredExponentialKernel ? 67u : 66u);
-                check(c, slsgp_set_sweep_mode(c, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), "slsgp_set_sweep_mode");
+                const SweepModeGuard        mode(*d, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64);
+                slsgp_ctx* const            c = d->Device();
+                std::lock_guard<std::mutex> lock(d->DeviceMutex());
                 // global sweep + batched multi-start ascent, all on the device; the winner is polished below
-                double             v0 = 0.0;
-                const int          n_starts = (int) std::min<long>(1024, std::max<long>(1, count / 64));
-                const slsgp_status s = slsgp_acq_maximize(c, internal::to_abi(func_type), hyperparam, search_seed(regressor), 0, count, n_starts,
-                                                          (int) std::min(num_local_search_iters, 200u), x0.data(), &v0, nullptr, nullptr);
-                slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
-                check(c, s, "slsgp_acq_maximize");
+                double    v0       = 0.0;
+                const int n_starts = (int) std::min<long>(1024, std::max<long>(1, count / 64));
+                check(c,
+                      slsgp_acq_maximize(c, internal::to_abi(func_type), hyperparam, search_seed(regressor), 0, count, n_starts,
+                                         (int) std::min(num_local_search_iters, 200u), x0.data(), &v0, nullptr, nullptr),
+                      "slsgp_acq_maximize");
             }
             else
             {
@@ -218,6 +245,7 @@ namespace sequential_line_search
             if (num_points == 0) return points;
             const DeviceRegressor* orig = device_of(regressor);
             if (!orig) throw std::invalid_argument("FindNextPoints needs a device-backed regressor with data");
+            slsgp_ctx* const orig_ctx = orig->Device(); // (a fresh copy builds its device model here, outside any lock)
 
             const VectorXd theta = regressor.GetKernelHyperparams();
             const double   noise = regressor.GetNoiseHyperparam();
@@ -232,7 +260,7 @@ namespace sequential_line_search
             double f_best = 0.0;
             {
                 std::lock_guard<std::mutex> lock(orig->DeviceMutex());
-                check(orig->Device(), slsgp_get_f_best(orig->Device(), &f_best, nullptr), "slsgp_get_f_best");
+                check(orig_ctx, slsgp_get_f_best(orig_ctx, &f_best, nullptr), "slsgp_get_f_best");
             }
             // mu / dmu from the original model, sigma / dsigma from the temporary one, formulas on the device
             const auto pair_acq = [&](const MatrixXd& Xq, VectorXd& val, MatrixXd* grad) {
@@ -244,8 +272,8 @@ namespace sequential_line_search
                 val = VectorXd::Zero(M);
                 if (grad) *grad = MatrixXd::Zero(D, M);
                 std::lock_guard<std::mutex> lock(orig->DeviceMutex());
-                check(orig->Device(),
-                      slsgp_acq_from_posterior(orig->Device(), internal::to_abi(func_type), hyperparam, f_best, (int) D, M, mu.data(), sigma.data(),
+                check(orig_ctx,
+                      slsgp_acq_from_posterior(orig_ctx, internal::to_abi(func_type), hyperparam, f_best, (int) D, M, mu.data(), sigma.data(),
                                                grad ? dmu.data() : nullptr, grad ? dsigma.data() : nullptr, val.data(), grad ? grad->data() : nullptr),
                       "slsgp_acq_from_posterior");
             };
@@ -274,31 +302,28 @@ namespace sequential_line_search
             const long count = std::min<long>((long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter, 1L << 21);
             const long chunk = std::min<long>(count, 1L << 17);
             const bool tensor = count >= 32768 && D <= 66;
-            const auto set_mode = [&](const DeviceRegressor& r, slsgp_sweep_mode mode) {
-                std::lock_guard<std::mutex> lock(r.DeviceMutex());
-                check(r.Device(), slsgp_set_sweep_mode(r.Device(), mode), "slsgp_set_sweep_mode");
-            };
             MatrixXd cand = MatrixXd::Zero(D, chunk);
             for (unsigned i = 0; i < num_points; ++i)
             {
                 VectorXd x_best  = VectorXd::Constant(D, 0.5);
                 double   v_best  = -std::numeric_limits<double>::infinity();
                 const uint64_t seed = search_seed(regressor) + 0x51ED27ull * (i + 1);
-                if (tensor) set_mode(*orig, SLSGP_SWEEP_TENSOR), set_mode(*temp, SLSGP_SWEEP_TENSOR);
+                {
+                const SweepModeGuard mode_orig(*orig, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), mode_temp(*temp, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64);
                 for (long first = 0; first < count; first += chunk)
                 {
                     const long n = std::min(chunk, count - first);
                     if (n != cand.cols()) cand = MatrixXd::Zero(D, n);
                     {
                         std::lock_guard<std::mutex> lock(orig->DeviceMutex());
-                        check(orig->Device(), slsgp_candidates(orig->Device(), seed, first, n, cand.data()), "slsgp_candidates");
+                        check(orig_ctx, slsgp_candidates(orig_ctx, seed, first, n, cand.data()), "slsgp_candidates");
                     }
                     VectorXd val;
                     pair_acq(cand, val, nullptr);
                     for (long m = 0; m < n; ++m)
                         if (val(m) > v_best) v_best = val(m), x_best = cand.col(m); // NaN never wins, lowest index wins ties
                 }
-                if (tensor) set_mode(*orig, SLSGP_SWEEP_FP64), set_mode(*temp, SLSGP_SWEEP_FP64);
+                } // the sweep modes are restored here: the polish below is IEEE double
                 const VectorXd x_star = polish(
                     [&](const VectorXd& x, VectorXd& g) {
                         MatrixXd X1 = MatrixXd::Zero(D, 1), G;

@@ -89,7 +89,43 @@ extern "C"
             1);
     }
 
+    // same signatures as the reference-side test handles ref_calc_small_k / ref_calc_large_ky_theta_derivative
+    int b200_calc_small_k(int kt, int D, int N, const double* X, const double* theta, const double* x, double* k_out, double* dk_dx_out)
+    {
+        return guarded(
+            [&]() {
+                GaussianProcessRegressor probe(MatrixXd(), VectorXd(), VectorXd(), 0.0, kernel_type(kt));
+                const MatrixXd           Xm = matrix(X, D, N);
+                const VectorXd           th = vector(theta, D + 1), xv = vector(x, D);
+                store(CalcSmallK(xv, Xm, th, probe.GetKernel()), k_out);
+                if (dk_dx_out) store(CalcSmallKSmallXDerivative(xv, Xm, th, probe.GetKernelFirstArgDerivative()), dk_dx_out);
+                return 0;
+            },
+            1);
+    }
+    int b200_calc_large_ky_theta_derivative(int kt, int D, int N, const double* X, const double* theta, double* out)
+    {
+        return guarded(
+            [&]() {
+                GaussianProcessRegressor probe(MatrixXd(), VectorXd(), VectorXd(), 0.0, kernel_type(kt));
+                const auto tensor = CalcLargeKYThetaDerivative(matrix(X, D, N), vector(theta, D + 1), probe.GetKernelThetaDerivative());
+                for (size_t i = 0; i < tensor.size(); ++i) store(tensor[i], out + i * (size_t) N * (size_t) N);
+                const MatrixXd I = CalcLargeKYNoiseLevelDerivative(matrix(X, D, N), vector(theta, D + 1), 0.0);
+                for (int r = 0; r < N; ++r)
+                    for (int c = 0; c < N; ++c)
+                        if (I(r, c) != (r == c ? 1.0 : 0.0)) throw std::logic_error("CalcLargeKYNoiseLevelDerivative is not the identity");
+                return 0;
+            },
+            1);
+    }
+    void b200_release_device_resources() { ReleaseDeviceResources(); }
+
     // ---- GaussianProcessRegressor ---------------------------------------------------------------------------------
+    void* b200_gpr_copy(void* h) // the copy constructor: a regressor of its own (deep copy)
+    {
+        return guarded([&]() -> void* { return new GaussianProcessRegressor(*static_cast<GaussianProcessRegressor*>(h)); }, nullptr);
+    }
+    int b200_gpr_num_points(void* h) { return (int) static_cast<GaussianProcessRegressor*>(h)->GetLargeX().cols(); }
     void* b200_gpr_create(int kt, int D, int N, const double* X, const double* y, const double* theta, double b)
     {
         return guarded([&]() -> void* { return new GaussianProcessRegressor(matrix(X, D, N), vector(y, N), vector(theta, D + 1), b, kernel_type(kt)); },

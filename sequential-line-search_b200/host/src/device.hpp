@@ -26,6 +26,7 @@ namespace sequential_line_search
 
         // New context on the device named by SLS_B200_DEVICE (default 0). Throws when there is no usable GPU.
         std::shared_ptr<slsgp_ctx> make_device();
+        void                       drain_device_pool(); // destroy the idle pooled contexts
 
         inline slsgp_kernel_type to_abi(KernelType t)
         {

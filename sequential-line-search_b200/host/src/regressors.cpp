@@ -24,17 +24,31 @@ namespace sequential_line_search
         // invalidates everything the previous owner left behind.
         namespace
         {
-            std::mutex                           g_pool_mutex;
-            std::vector<std::pair<int, slsgp_ctx*>> g_pool; // (device, idle context)
-            struct PoolDrain                     // destroy what is still pooled at process exit
+            // The pool is a leaked function-local singleton: regressors with static storage duration may be released after any
+            // static destructor of this library has run, and the CUDA runtime may already be torn down by then, so nothing is
+            // destroyed at process exit (the driver reclaims device memory with the process). ReleaseDeviceResources() below
+            // empties it on request.
+            struct Pool
             {
-                ~PoolDrain()
-                {
-                    for (auto& e : g_pool) slsgp_ctx_destroy(e.second);
-                    g_pool.clear();
-                }
-            } g_pool_drain;
+                std::mutex                              mutex;
+                std::vector<std::pair<int, slsgp_ctx*>> idle; // (device, idle context)
+            };
+            Pool& pool()
+            {
+                static Pool* p = new Pool;
+                return *p;
+            }
         } // namespace
+
+        void drain_device_pool()
+        {
+            std::vector<std::pair<int, slsgp_ctx*>> idle;
+            {
+                std::lock_guard<std::mutex> lock(pool().mutex);
+                idle.swap(pool().idle);
+            }
+            for (auto& e : idle) slsgp_ctx_destroy(e.second);
+        }
 
         std::shared_ptr<slsgp_ctx> make_device()
         {
@@ -42,12 +56,13 @@ namespace sequential_line_search
             const int   device = env ? std::atoi(env) : 0;
             slsgp_ctx*  raw    = nullptr;
             {
-                std::lock_guard<std::mutex> lock(g_pool_mutex);
-                for (size_t i = 0; i < g_pool.size(); ++i)
-                    if (g_pool[i].first == device)
+                std::lock_guard<std::mutex> lock(pool().mutex);
+                auto&                       idle = pool().idle;
+                for (size_t i = 0; i < idle.size(); ++i)
+                    if (idle[i].first == device)
                     {
-                        raw = g_pool[i].second;
-                        g_pool.erase(g_pool.begin() + (long) i);
+                        raw = idle[i].second;
+                        idle.erase(idle.begin() + (long) i);
                         break;
                     }
             }
@@ -60,9 +75,10 @@ namespace sequential_line_search
             }
             return std::shared_ptr<slsgp_ctx>(raw, [device](slsgp_ctx* c) {
                 slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
-                std::lock_guard<std::mutex> lock(g_pool_mutex);
-                if (g_pool.size() < 4)
-                    g_pool.emplace_back(device, c);
+                slsgp_trim(c, (size_t) 64 << 20); // a pooled context keeps at most 64 MiB of grown device buffers
+                std::lock_guard<std::mutex> lock(pool().mutex);
+                if (pool().idle.size() < 4)
+                    pool().idle.emplace_back(device, c);
                 else
                     slsgp_ctx_destroy(c);
             });
@@ -89,9 +105,10 @@ namespace sequential_line_search
         {
             if (dev->HasModel())
             {
+                slsgp_ctx* const            c = dev->Device();
                 std::lock_guard<std::mutex> lock(dev->DeviceMutex());
                 int                         index = 0;
-                check(dev->Device(), slsgp_get_f_best(dev->Device(), nullptr, &index), "slsgp_get_f_best");
+                check(c, slsgp_get_f_best(c, nullptr, &index), "slsgp_get_f_best");
                 return X.col(index);
             }
         }
@@ -110,6 +127,36 @@ namespace sequential_line_search
     // DeviceRegressor
     // ------------------------------------------------------------------------------------------------------------
     DeviceRegressor::DeviceRegressor(const KernelType kernel_type) : Regressor(kernel_type), m_mutex(std::make_shared<std::mutex>()) {}
+
+    // A copy starts without a device model and rebuilds it on first use from the host state the derived class copies.
+    DeviceRegressor::DeviceRegressor(const DeviceRegressor& other)
+        : Regressor(other), m_device(nullptr), m_mutex(std::make_shared<std::mutex>()), m_fitted(false), m_data_on_device(false),
+          m_refit_pending(other.m_fitted || other.m_refit_pending)
+    {
+    }
+    DeviceRegressor& DeviceRegressor::operator=(const DeviceRegressor& other)
+    {
+        if (this == &other) return *this;
+        Regressor::operator=(other);
+        m_device.reset();
+        m_mutex          = std::make_shared<std::mutex>();
+        m_fitted         = false;
+        m_data_on_device = false;
+        m_refit_pending  = other.m_fitted || other.m_refit_pending;
+        return *this;
+    }
+
+    slsgp_ctx* DeviceRegressor::Device() const
+    {
+        if (m_refit_pending)
+        {
+            // logically const: the observable state (X, y, hyper-parameters) does not change, only where the model lives
+            auto* self            = const_cast<DeviceRegressor*>(this);
+            self->m_refit_pending = false;
+            self->RefitOnDevice();
+        }
+        return m_device.get();
+    }
 
     void DeviceRegressor::EnsureDevice()
     {
@@ -139,16 +186,17 @@ namespace sequential_line_search
 
     void DeviceRegressor::PredictBatch(const MatrixXd& Xq, VectorXd* mu, VectorXd* sigma, MatrixXd* dmu, MatrixXd* dsigma) const
     {
-        if (!m_fitted) throw std::logic_error("the regressor holds no data");
-        const long M = Xq.cols(), D = Xq.rows();
+        if (!HasModel()) throw std::logic_error("the regressor holds no data");
+        slsgp_ctx* const c = Device();
+        const long       M = Xq.cols(), D = Xq.rows();
         if (D != (long) GetLargeX().rows()) throw std::invalid_argument("query points must have the dimension of the data");
         if (mu) *mu = VectorXd::Zero(M);
         if (sigma) *sigma = VectorXd::Zero(M);
         if (dmu) *dmu = MatrixXd::Zero(D, M);
         if (dsigma) *dsigma = MatrixXd::Zero(D, M);
         std::lock_guard<std::mutex> lock(*m_mutex);
-        check(m_device.get(),
-              slsgp_posterior_batch(m_device.get(), Xq.data(), M, mu ? mu->data() : nullptr, sigma ? sigma->data() : nullptr,
+        check(c,
+              slsgp_posterior_batch(c, Xq.data(), M, mu ? mu->data() : nullptr, sigma ? sigma->data() : nullptr,
                                     dmu ? dmu->data() : nullptr, dsigma ? dsigma->data() : nullptr),
               "slsgp_posterior_batch");
     }
@@ -160,8 +208,9 @@ namespace sequential_line_search
         {
             if (!r.HasModel()) throw std::logic_error("the regressor holds no data");
             if (x.size() != (long) r.GetLargeX().rows()) throw std::invalid_argument("x must have the dimension of the data");
+            slsgp_ctx* const            c = r.Device();
             std::lock_guard<std::mutex> lock(r.DeviceMutex());
-            check(r.Device(), slsgp_posterior_batch(r.Device(), x.data(), 1, mu, sigma, dmu, dsigma), "slsgp_posterior_batch");
+            check(c, slsgp_posterior_batch(c, x.data(), 1, mu, sigma, dmu, dsigma), "slsgp_posterior_batch");
         }
     } // namespace
 
@@ -217,9 +266,12 @@ namespace sequential_line_search
         FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, nullptr, nullptr, nullptr);
     }
 
+    void GaussianProcessRegressor::RefitOnDevice() { FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, nullptr, nullptr, nullptr); }
+
     void GaussianProcessRegressor::AppendPoint(const VectorXd& x, double y)
     {
-        if (!m_fitted) throw std::logic_error("AppendPoint needs a fitted regressor");
+        if (!HasModel()) throw std::logic_error("AppendPoint needs a fitted regressor");
+        Device(); // a fresh copy builds its own model first: the update never touches the source's
         const long D = m_X.rows(), N = m_X.cols();
         if (x.size() != D) throw std::invalid_argument("the new point must have the dimension of the data");
         const bool mirror = m_K_y.rows() == N && m_K_y_inv.rows() == N; // false for DeviceOnly regressors
@@ -363,9 +415,37 @@ namespace sequential_line_search
 #endif
     }
 
+    namespace
+    {
+        void tuples_to_csr(const std::vector<Preference>& D, unsigned N, std::vector<uint32_t>& offsets, std::vector<uint32_t>& indices)
+        {
+            offsets.assign(1, 0);
+            indices.clear();
+            for (const Preference& p : D)
+            {
+                for (unsigned i : p)
+                {
+                    if (i >= N) throw std::invalid_argument("preference index out of range");
+                    indices.push_back(i);
+                }
+                offsets.push_back((uint32_t) indices.size());
+            }
+        }
+    } // namespace
+
+    void PreferenceRegressor::RefitOnDevice()
+    {
+        FitOnDevice(m_X, m_y, m_kernel_hyperparams, m_noise_hyperparam, nullptr, nullptr, nullptr);
+        std::vector<uint32_t> offsets, indices;
+        tuples_to_csr(m_D, (unsigned) m_X.cols(), offsets, indices);
+        std::lock_guard<std::mutex> lock(*m_mutex);
+        check(m_device.get(), slsgp_set_preferences(m_device.get(), offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
+    }
+
     double PreferenceRegressor::EvaluateMapObjective(const VectorXd& x, VectorXd* gradient) const
     {
-        if (!m_device) throw std::logic_error("the regressor holds no data");
+        if (!HasModel()) throw std::logic_error("the regressor holds no data");
+        Device();
         const int N = (int) m_X.cols(), D = (int) m_X.rows(), n = m_use_map_hyperparams ? N + 2 + D : N;
         if ((int) x.size() != n) throw std::invalid_argument("MAP objective: x has the wrong length");
         if (gradient) *gradient = VectorXd::Zero(n);
@@ -400,7 +480,9 @@ namespace sequential_line_search
     //   * the hyper-parameters are an outer problem over w = log(a, b, r) on  G(w) = max_y F(y, w)  whose gradient is
     //     dF/dw at the inner maximiser (envelope theorem), read from slsgp_map_objective_pref; each outer evaluation
     //     rebuilds K_y once and warm-starts the inner solve from the previous y.
-    // `num_iters` bounds the OUTER evaluations (>= 60 are always allowed); the inner solves run to convergence.
+    // `num_iters` is the total evaluation budget (inner whitened evaluations and outer full evaluations alike), as NLopt's maxeval is
+    // in the reference; the best point found within it is returned. This is the SearchDriver::Native path; with NLopt available the
+    // fit is the reference's own LD_TNEWTON run (branch below).
     void PreferenceRegressor::PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start)
     {
         EnsureDevice();
@@ -408,20 +490,18 @@ namespace sequential_line_search
         slsgp_ctx* c = m_device.get();
         const slsgp_kernel_type kt = internal::to_abi(m_kernel_type);
 
-        std::vector<uint32_t> offsets(1, 0), indices;
-        for (const Preference& p : m_D)
-        {
-            for (unsigned i : p)
-            {
-                if (i >= (unsigned) N) throw std::invalid_argument("preference index out of range");
-                indices.push_back(i);
-            }
-            offsets.push_back((uint32_t) indices.size());
-        }
+        std::vector<uint32_t> offsets, indices;
+        tuples_to_csr(m_D, (unsigned) N, offsets, indices);
         std::lock_guard<std::mutex> lock(*m_mutex);
         check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
         m_data_on_device = true;
         check(c, slsgp_set_preferences(c, offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
+#ifdef SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION
+        // the reference's compile-time option (CMakeLists.txt:28-33): K = K(X, X) without the noise term, b fixed at 0
+        check(c, slsgp_set_compat_flags(c, SLSGP_COMPAT_SE_XGRAD_2X | SLSGP_COMPAT_NOISELESS), "slsgp_set_compat_flags");
+#else
+        check(c, slsgp_set_compat_flags(c, SLSGP_COMPAT_SE_XGRAD_2X), "slsgp_set_compat_flags"); // a pooled context may carry another flag set
+#endif
 
         if (internal::use_nlopt_for_map())
         {
@@ -433,7 +513,11 @@ namespace sequential_line_search
             {
                 for (int i = 0; i < 2 + D; ++i) lower(N + i) = 1e-08;
                 x_ini(N + 0) = m_default_kernel_signal_var;
+#ifdef SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION
+                x_ini(N + 1) = 0.5 * (upper(N + 1) + lower(N + 1));
+#else
                 x_ini(N + 1) = m_default_noise_level;
+#endif
                 for (int i = 0; i < D; ++i) x_ini(N + 2 + i) = m_default_kernel_length_scale;
                 for (int i = 0; i < opt_dim; ++i) x_ini(i) = std::min(std::max(x_ini(i), lower(i)), upper(i));
             }
@@ -470,7 +554,11 @@ namespace sequential_line_search
             {
                 m_kernel_hyperparams(0) = x_opt(N + 0);
                 for (int i = 0; i < D; ++i) m_kernel_hyperparams(i + 1) = x_opt(N + 2 + i);
+#ifdef SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION
+                m_noise_hyperparam = 0.0;
+#else
                 m_noise_hyperparam = x_opt(N + 1);
+#endif
             }
             return;
         }
@@ -500,7 +588,8 @@ namespace sequential_line_search
             }
         }
 
-        unsigned evals = 0;
+        unsigned       evals  = 0;
+        const unsigned budget = std::max(1u, num_iters); // the caller's evaluation budget, as in the reference (maxeval of NLopt)
         // ---- inner problem: y for the hyper-parameters whose factor is current on the device. Returns F at the maximiser.
         std::vector<double> y_cur = y_start, z((size_t) N), gz((size_t) N);
         const auto solve_y = [&](bool from_y_cur) -> double {
@@ -517,7 +606,8 @@ namespace sequential_line_search
                 return -f;
             };
             const std::vector<double>      lo((size_t) N, -1e3), hi((size_t) N, 1e3);
-            const internal::MinimizeResult r = internal::minimize_bounded(neg, z0, lo, hi, 600, 1e-9);
+            const unsigned                 left = evals < budget ? budget - evals : 0; // inner and outer evaluations share `num_iters`
+            const internal::MinimizeResult r = internal::minimize_bounded(neg, z0, lo, hi, std::max(2u, left), 1e-9);
             if (!std::isfinite(r.f)) return -std::numeric_limits<double>::infinity();
             double f = 0.0;
             check(c, slsgp_map_objective_pref_whitened(c, r.x.data(), m_btl_scale, &f, nullptr, y_cur.data()), "slsgp_map_objective_pref_whitened");
@@ -552,6 +642,10 @@ namespace sequential_line_search
             // after `num_iters` evaluations). The signal variance and the noise level are therefore kept above their prior
             // mean minus four prior standard deviations (a factor exp(-4 sqrt(var)), 1/7.4 for the default variance 0.25);
             // the length scales and all upper bounds stay at the reference's box.
+            // Opt-in (SLS_B200_MAP_HYPER_FLOOR=1); the default is the reference's box [1e-8, 10], where the evaluation budget is what
+            // keeps the fit away from that corner, exactly as in the reference.
+            static const bool floor_enabled = std::getenv("SLS_B200_MAP_HYPER_FLOOR") && std::atoi(std::getenv("SLS_B200_MAP_HYPER_FLOOR")) != 0;
+            if (floor_enabled)
             {
                 const double span = 4.0 * std::sqrt(m_kernel_hyperparams_prior_var);
                 lo[0] = std::max(lo[0], std::log(m_default_kernel_signal_var) - span);
@@ -561,6 +655,7 @@ namespace sequential_line_search
             double              f_best = -std::numeric_limits<double>::infinity();
             bool                first  = true;
             const internal::Objective outer = [&](const std::vector<double>& w, std::vector<double>& g) {
+                if (evals >= budget && std::isfinite(f_best)) return std::numeric_limits<double>::infinity(); // budget spent: the driver backs off and stops
                 if (!build_model(w)) return std::numeric_limits<double>::infinity();
                 const bool   from_cur = first ? have_start : true;
                 first                 = false;
@@ -580,7 +675,7 @@ namespace sequential_line_search
                 return -f;
             };
             for (int i = 0; i < nh; ++i) w0[(size_t) i] = std::min(std::max(w0[(size_t) i], lo[(size_t) i]), hi[(size_t) i]);
-            const internal::MinimizeResult r = internal::minimize_bounded(outer, w0, lo, hi, std::max(60u, num_iters), 1e-7, 1e-13);
+            const internal::MinimizeResult r = internal::minimize_bounded(outer, w0, lo, hi, budget, 1e-7, 1e-13);
             if (!std::isfinite(f_best)) throw std::runtime_error("PreferenceRegressor: the MAP objective could not be evaluated at the initial point");
             (void) r;
             y_cur = y_at_best;
@@ -647,4 +742,85 @@ namespace sequential_line_search
     {
         return CalcLargeKY(X, kernel_hyperparameters, 0.0, kernel);
     }
+
+    namespace
+    {
+        // which of the library's kernels a function pointer of any of the three families belongs to
+        bool library_kernel_type(Kernel k, KernelThetaDerivative kt, KernelFirstArgDerivative kx, KernelType* out)
+        {
+            for (KernelType t : {KernelType::ArdSquaredExponentialKernel, KernelType::ArdMatern52Kernel})
+                if ((k && k == internal::kernel_of(t)) || (kt && kt == internal::kernel_theta_derivative_of(t)) ||
+                    (kx && kx == internal::kernel_first_arg_derivative_of(t)))
+                    return *out = t, true;
+            return false;
+        }
+        std::shared_ptr<slsgp_ctx> device_with_data(const MatrixXd& X)
+        {
+            std::shared_ptr<slsgp_ctx> dev = internal::make_device();
+            check(dev.get(), slsgp_set_data(dev.get(), X.data(), (int) X.cols(), (int) X.rows()), "slsgp_set_data");
+            return dev;
+        }
+    } // namespace
+
+    VectorXd CalcSmallK(const VectorXd& x, const MatrixXd& X, const VectorXd& kernel_hyperparameters, const Kernel kernel)
+    {
+        const int N = (int) X.cols();
+        VectorXd  k = VectorXd::Zero(N);
+        if (N == 0) return k;
+        KernelType type;
+        if (!library_kernel_type(kernel, nullptr, nullptr, &type)) // a foreign kernel: the reference's loop (src/regressor.cpp:45-59)
+        {
+            for (int i = 0; i < N; ++i) k(i) = kernel(x, X.col(i), kernel_hyperparameters);
+            return k;
+        }
+        std::shared_ptr<slsgp_ctx> dev = device_with_data(X);
+        check(dev.get(), slsgp_small_k(dev.get(), internal::to_abi(type), kernel_hyperparameters.data(), x.data(), k.data(), nullptr), "slsgp_small_k");
+        return k;
+    }
+
+    MatrixXd CalcSmallKSmallXDerivative(const VectorXd& x, const MatrixXd& X, const VectorXd& kernel_hyperparameters,
+                                        const KernelFirstArgDerivative kernel_first_arg_derivative)
+    {
+        const int N = (int) X.cols(), D = (int) X.rows();
+        MatrixXd  J = MatrixXd::Zero(D, N);
+        if (N == 0) return J;
+        KernelType type;
+        if (!library_kernel_type(nullptr, nullptr, kernel_first_arg_derivative, &type)) // :91-108
+        {
+            for (int i = 0; i < N; ++i) J.col(i) = kernel_first_arg_derivative(x, X.col(i), kernel_hyperparameters);
+            return J;
+        }
+        std::shared_ptr<slsgp_ctx> dev = device_with_data(X);
+        check(dev.get(), slsgp_small_k(dev.get(), internal::to_abi(type), kernel_hyperparameters.data(), x.data(), nullptr, J.data()), "slsgp_small_k");
+        return J;
+    }
+
+    std::vector<MatrixXd> CalcLargeKYThetaDerivative(const MatrixXd& X, const VectorXd& kernel_hyperparameters,
+                                                     const KernelThetaDerivative kernel_theta_derivative)
+    {
+        const int             N = (int) X.cols(), n_theta = (int) kernel_hyperparameters.size();
+        std::vector<MatrixXd> tensor((size_t) n_theta, MatrixXd::Zero(N, N));
+        if (N == 0) return tensor;
+        KernelType type;
+        if (!library_kernel_type(nullptr, kernel_theta_derivative, nullptr, &type)) // :110-134
+        {
+            for (int i = 0; i < N; ++i)
+                for (int j = i; j < N; ++j)
+                {
+                    const VectorXd grad = kernel_theta_derivative(X.col(i), X.col(j), kernel_hyperparameters);
+                    for (int k = 0; k < n_theta; ++k) tensor[(size_t) k](i, j) = grad(k), tensor[(size_t) k](j, i) = grad(k);
+                }
+            return tensor;
+        }
+        std::shared_ptr<slsgp_ctx> dev = device_with_data(X);
+        std::vector<double>        planes((size_t) n_theta * N * N);
+        check(dev.get(), slsgp_gram_theta_derivative(dev.get(), internal::to_abi(type), kernel_hyperparameters.data(), planes.data()),
+              "slsgp_gram_theta_derivative");
+        for (int k = 0; k < n_theta; ++k) std::copy(planes.begin() + (size_t) k * N * N, planes.begin() + (size_t) (k + 1) * N * N, tensor[(size_t) k].data());
+        return tensor;
+    }
+
+    MatrixXd CalcLargeKYNoiseLevelDerivative(const MatrixXd& X, const VectorXd&, const double) { return MatrixXd::Identity(X.cols(), X.cols()); } // :136-141
+
+    void ReleaseDeviceResources() { internal::drain_device_pool(); }
 } // namespace sequential_line_search

@@ -16,7 +16,7 @@ c_up = C.POINTER(C.c_uint)
 _lib = None
 
 _DOUBLE = ("b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value", "b200_utils_btl")
-_POINTER = ("b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
+_POINTER = ("b200_gpr_copy", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
 HOST_SYMBOLS = [
     "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy", "b200_gpr_append_point",
     "b200_gpr_regressor", "b200_gpr_get_state", "b200_pref_create", "b200_pref_create_warm", "b200_pref_destroy", "b200_pref_regressor",
@@ -25,7 +25,8 @@ HOST_SYMBOLS = [
     "b200_predict_sigma_derivative", "b200_predict_maximum_point_from_data", "b200_predict_batch", "b200_acq_value",
     "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
     "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
-    "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver",
+    "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver", "b200_calc_small_k", "b200_calc_large_ky_theta_derivative",
+    "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points",
 ] + ["b200_" + n for n in (
     # host/src/loop_capi.inl: optimiser front-ends and driver-dependent entry points (bound by tests/loop_support.py)
     "srand sls_create sls_destroy sls_set_hyperparams sls_set_ucb_hyperparam sls_submit sls_get_slider_ends sls_get_maximizer sls_calc_point "
@@ -106,6 +107,30 @@ class Host:
         K = np.empty((N, N), order="F")
         self._ok(self.lib.b200_calc_large_ky(kt, D, N, _p(X), _p(theta), C.c_double(b), _p(K)) == 0)
         return K
+
+    def small_k(self, kt, X, theta, x):
+        """CalcSmallK and CalcSmallKSmallXDerivative (the reference's L1 free functions)."""
+        X, theta, x = _f64(X), _f64(theta), _f64(x)
+        D, N = X.shape
+        k, J = np.empty(N), np.empty((D, N), order="F")
+        self._ok(self.lib.b200_calc_small_k(kt, D, N, _p(X), _p(theta), _p(x), _p(k), _p(J)) == 0)
+        return k, J
+
+    def large_ky_theta_derivative(self, kt, X, theta):
+        """CalcLargeKYThetaDerivative: [D + 1, N, N] (also checks CalcLargeKYNoiseLevelDerivative == I)."""
+        X, theta = _f64(X), _f64(theta)
+        D, N = X.shape
+        out = np.empty((D + 1, N * N))
+        self._ok(self.lib.b200_calc_large_ky_theta_derivative(kt, D, N, _p(X), _p(theta), _p(out)) == 0)
+        return out.reshape(D + 1, N, N).transpose(0, 2, 1)
+
+    def gpr_copy(self, h):
+        c = self.lib.b200_gpr_copy(h)
+        self._ok(c)
+        return C.c_void_p(c)
+
+    def gpr_num_points(self, h):
+        return self.lib.b200_gpr_num_points(h)
 
     # GaussianProcessRegressor
     def gpr_create(self, kt, X, y, theta=None, b=None):

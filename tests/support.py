@@ -188,6 +188,16 @@ class Oracle:
                                                      C.c_double(prior_var), C.c_double(btl_scale), _p(x), _p(g))
         return f, g
 
+    def map_objective_pref_noiseless(self, kt, X, offsets, idx, use_map, a, r, b, prior_var, btl_scale, x, want_grad=True):
+        """The objective of the reference's SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION build."""
+        X, x = f64(X), f64(x)
+        D, N = X.shape
+        g = np.empty(len(x)) if want_grad else None
+        self.lib.slsgp_oracle_map_objective_pref_noiseless.restype = C.c_double
+        f = self.lib.slsgp_oracle_map_objective_pref_noiseless(kt, D, N, _p(X), len(offsets) - 1, _u(offsets), _u(idx), int(use_map), C.c_double(a),
+                                                               C.c_double(r), C.c_double(b), C.c_double(prior_var), C.c_double(btl_scale), _p(x), _p(g))
+        return f, g
+
     def map_objective_gpr(self, kt, X, y, x, want_grad=True):
         X, y, x = f64(X), f64(y), f64(x)
         D, N = X.shape
@@ -206,9 +216,12 @@ def ref_available():
     return os.path.exists(REF_PATH)
 
 
+REF_NOISELESS_PATH = os.path.join(ORACLE_DIR, "_ref", "libsls_ref_probe_noiseless.so")  # built with SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION
+
+
 class Ref:
-    def __init__(self):
-        self.lib = lib = C.CDLL(REF_PATH)
+    def __init__(self, path=None):
+        self.lib = lib = C.CDLL(path or REF_PATH)
         for name in ("ref_pref_create", "ref_pref_regressor", "ref_gpr_create", "ref_gpr_regressor"):
             getattr(lib, name).restype = C.c_void_p
         for name in ("ref_pref_objective", "ref_predict_mu", "ref_predict_sigma", "ref_acq_value", "ref_btl"):

@@ -187,3 +187,34 @@ def test_closed_form_known_answers(oracle):
     assert abs(sg - np.sqrt(a - k * k / (a + b))) < 1e-15
     v, _ = oracle.acq(m, S.EI, 1.0, mu, x)  # f_best := mu(x)  ->  Z = 0
     assert abs(v - sg / np.sqrt(2 * np.pi)) < 1e-15
+
+
+@pytest.mark.parametrize("kt,D,N", [(S.SE, 4, 17), (S.MATERN, 6, 30)])
+def test_noiseless_formulation_objective(oracle, kt, D, N):
+    """SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION (CMakeLists.txt:28-33; src/preference-regressor.cpp:48-52,141,180-188,237):
+    the oracle's restatement against the reference compiled with that option (oracle/_ref/libsls_ref_probe_noiseless.so)."""
+    import os
+    if not os.path.exists(S.REF_NOISELESS_PATH):
+        pytest.skip("oracle/_ref/libsls_ref_probe_noiseless.so not built")
+    ref_nl = S.Ref(S.REF_NOISELESS_PATH)
+    X = S.make_X(N, D, "uniform")  # K_f alone must be positive definite: well-separated points
+    offsets, idx = S.make_tuples(X)
+    a, r, b, var, btl = 0.5, 0.5, 0.005, 0.25, 0.01
+    rng = np.random.default_rng(8)
+    y = 0.05 * rng.standard_normal(N)
+    theta = S.make_theta(D, "perturbed")
+    sol = np.concatenate([y, [theta[0], 0.0123], 0.3 * theta[1:]])
+    h = ref_nl.pref_create(kt, X, offsets, idx, True, a, r, b, var, btl, sol)
+    try:
+        assert ref_nl.pref_state(h, N, D)["b"] == 0.0  # m_noise_hyperparam = b_fixed (:389)
+        for x in (sol, sol * 1.05 + 0.002):
+            f, g = ref_nl.pref_objective(h, x)
+            of, og = oracle.map_objective_pref_noiseless(kt, X, offsets, idx, True, a, r, b, var, btl, x)
+            assert np.isfinite(f) and abs(of - f) <= 1e-9 * abs(f)
+            np.testing.assert_allclose(og, g, rtol=1e-6, atol=1e-7)
+            assert og[N + 1] == 0.0 and g[N + 1] == 0.0
+            # and it is NOT the standard objective
+            sf, _ = oracle.map_objective_pref(kt, X, offsets, idx, True, a, r, b, var, btl, x)
+            assert abs(sf - f) > 1e-6 * abs(f)
+    finally:
+        ref_nl.pref_destroy(h)
