@@ -5,6 +5,7 @@
 // oracle/nlopt_probe/nlopt.hpp. Output: oracle/_ref/libsls_ref_probe.so. Only tests/, the golden-vector generator
 // and bench.py's reference/cpu_baseline legs load it. It contains no arithmetic of its own: every number that
 // comes out of it is computed by the reference's code (with eigen-lite's LLT / LU standing in for Eigen's).
+#include <chrono>
 #include <cstring>
 #include <memory>
 #include <nlopt.hpp>
@@ -96,6 +97,25 @@ extern "C"
         KernelProbe    p(to_kernel_type(kt));
         const MatrixXd K = CalcLargeKY(to_matrix(X, D, N), to_vector(theta, D + 1), b, p.GetKernel());
         std::memcpy(K_out, K.data(), sizeof(double) * size_t(N) * size_t(N));
+    }
+
+    // CalcLargeKY + Eigen::LLT exactly as PreferenceRegressor's constructor runs them (src/preference-regressor.cpp:289-290);
+    // returns the wall time of the two statements in seconds (bench.py: the reference side of "Gram + Chol ms").
+    double ref_gram_chol_seconds(int kt, int D, int N, const double* X, const double* theta, double b, double* L_out /* N x N or null */)
+    {
+        KernelProbe    p(to_kernel_type(kt));
+        const MatrixXd Xm = to_matrix(X, D, N);
+        const VectorXd th = to_vector(theta, D + 1);
+        const auto     t0 = std::chrono::steady_clock::now();
+        const MatrixXd             K = CalcLargeKY(Xm, th, b, p.GetKernel());
+        const Eigen::LLT<MatrixXd> llt(K);
+        const double               dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        if (L_out)
+        {
+            const MatrixXd L = llt.matrixL().toDenseMatrix();
+            std::memcpy(L_out, L.data(), sizeof(double) * size_t(N) * size_t(N));
+        }
+        return dt;
     }
 
     void ref_calc_small_k(int kt, int D, int N, const double* X, const double* theta, const double* x,

@@ -341,6 +341,21 @@ extern "C"
             1);
     }
 
+    // Arithmetic of the candidate sweep behind this regressor's batched calls (slsgp_sweep_mode: 0 IEEE double, 1..3 tensor-core modes)
+    int b200_regressor_set_sweep_mode(const void* r, int mode)
+    {
+        return guarded(
+            [&]() {
+                const auto* d = dynamic_cast<const DeviceRegressor*>(static_cast<const Regressor*>(r));
+                if (!d || !d->HasModel()) throw std::invalid_argument("not a device-backed regressor with a model");
+                slsgp_ctx* const            c = d->Device();
+                std::lock_guard<std::mutex> lock(d->DeviceMutex());
+                internal::check(c, slsgp_set_sweep_mode(c, (slsgp_sweep_mode) mode), "slsgp_set_sweep_mode");
+                return 0;
+            },
+            1);
+    }
+
     // ---- acquisition_func --------------------------------------------------------------------------------------------------
     double b200_acq_value(const void* r, int D, int acq, double ucb_beta, const double* x)
     {

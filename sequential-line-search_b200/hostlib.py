@@ -26,7 +26,7 @@ HOST_SYMBOLS = [
     "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
     "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
     "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver", "b200_calc_small_k", "b200_calc_large_ky_theta_derivative",
-    "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points",
+    "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points", "b200_regressor_set_sweep_mode",
 ] + ["b200_" + n for n in (
     # host/src/loop_capi.inl: optimiser front-ends and driver-dependent entry points (bound by tests/loop_support.py)
     "srand sls_create sls_destroy sls_set_hyperparams sls_set_ucb_hyperparam sls_submit sls_get_slider_ends sls_get_maximizer sls_calc_point "
@@ -123,6 +123,9 @@ class Host:
         out = np.empty((D + 1, N * N))
         self._ok(self.lib.b200_calc_large_ky_theta_derivative(kt, D, N, _p(X), _p(theta), _p(out)) == 0)
         return out.reshape(D + 1, N, N).transpose(0, 2, 1)
+
+    def regressor_set_sweep_mode(self, reg, mode):
+        self._ok(self.lib.b200_regressor_set_sweep_mode(reg, int(mode)) == 0)
 
     def gpr_copy(self, h):
         c = self.lib.b200_gpr_copy(h)

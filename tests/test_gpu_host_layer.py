@@ -2,8 +2,9 @@
 libslsgp) against the reference's own classes (oracle/_ref, compiled from the unmodified sources), call for call.
 
 Tolerance: 1e-5 relative (north_star FP64), measured as max |err| / max |ref| per quantity.
-The MAP fits cannot be compared step by step (the reference drives them with NLopt, which is not built here); they are
-checked where it matters: the point our optimiser returns must be a maximiser of the REFERENCE's objective."""
+The MAP fits and searches of the Native driver are checked as what they claim to be: maximisers of the REFERENCE's objective
+(given an evaluation budget that lets them converge). Parity with what the reference's own NLopt runs return is the subject of
+tests/test_gpu_step_parity.py."""
 import importlib
 import os
 
@@ -20,6 +21,17 @@ RT = 1e-5
 @pytest.fixture(scope="module")
 def host():
     return pkg.hostlib.Host()
+
+
+@pytest.fixture(autouse=True)
+def native_driver():
+    """This file exercises the host layer's OWN search drivers (SearchDriver::Native: the whitened quasi-Newton MAP fit, the
+    device-resident acquisition maximiser). The NLopt-driven reference-faithful path is compared with the real reference in
+    tests/test_gpu_step_parity.py."""
+    previous = pkg.hostlib.get_search_driver()
+    pkg.hostlib.set_search_driver(pkg.hostlib.NATIVE)
+    yield
+    pkg.hostlib.set_search_driver(previous)
 
 
 CASES = [(S.SE, 6, 40, "uniform", "default"), (S.MATERN, 6, 40, "sls", "perturbed"), (S.SE, 16, 130, "sls", "perturbed"),
@@ -111,7 +123,7 @@ def test_preference_regressor_map_is_a_maximiser_of_the_reference_objective(host
     X = S.make_X(N, D, "sls")
     offsets, idx = S.make_tuples(X)
     a, r, b, pv, btl = 0.5, 0.5, 0.005, 0.25, 0.01
-    h = host.pref_create(kt, X, offsets, idx, use_map, a, r, b, pv, btl)
+    h = host.pref_create(kt, X, offsets, idx, use_map, a, r, b, pv, btl, num_iters=6000)  # a budget that lets the fit converge
     try:
         st = host.pref_state(h, N, D)
         sol = np.concatenate([st["y"], [st["theta"][0], st["b"]], st["theta"][1:]]) if use_map else st["y"]
@@ -127,9 +139,7 @@ def test_preference_regressor_map_is_a_maximiser_of_the_reference_objective(host
             away = sol * (1.0 + 0.05 * np.random.default_rng(9).standard_normal(len(sol)))
             assert S.rel_err(host.pref_objective(h, away)[1], ref.pref_objective(hr, away)[1]) < 1e-6
             # first-order optimality of the reference objective at our solution, bounds respected
-            # (signal variance and noise level are held above exp(-4 sqrt(prior_var)) x their prior mean: DESIGN.md 4.4)
-            floor = np.exp(-4.0 * np.sqrt(pv))
-            lo = np.concatenate([np.full(N, -10.0), [a * floor, b * floor], np.full(D, 1e-8)]) if use_map else np.full(N, -10.0)
+            lo = np.concatenate([np.full(N, -10.0), np.full(D + 2, 1e-8)]) if use_map else np.full(N, -10.0)  # the reference's box
             hi = np.full(len(sol), 10.0)
             pg = np.where(((sol <= lo * (1 + 1e-9)) & (g_r < 0)) | ((sol >= hi) & (g_r > 0)), 0.0, g_r)
             if use_map:   # hyper-parameters live on a log scale (b ~ 5e-3): d F / d log x = x dF/dx
@@ -155,7 +165,7 @@ def test_preference_regressor_map_is_a_maximiser_of_the_reference_objective(host
             np.testing.assert_array_equal(host.pref_find_arg_max(h, D), X[:, int(np.argmax(st["y"]))])
         finally:
             ref.pref_destroy(hr)
-        assert 1 < host.pref_num_map_evaluations(h) <= 2100
+        assert 1 < host.pref_num_map_evaluations(h) <= 6000 + 700  # the budget, plus at most one inner solve started below it
     finally:
         host.pref_destroy(h)
 
@@ -238,7 +248,7 @@ def test_warm_started_map_reaches_the_same_optimum_in_fewer_evaluations(host):
     kt, D = S.SE, 5
     X = S.make_X(33, D, "sls")
     offsets, idx = S.make_tuples(X)
-    args = (False, 0.5, 0.5, 0.005, 0.25, 0.01)
+    args = (False, 0.5, 0.5, 0.005, 0.25, 0.01, 1000)
     prev = host.pref_create(kt, X[:, :30], offsets[:11], idx[:offsets[10]], *args)         # iteration t: 10 tuples
     cold = host.pref_create(kt, X, offsets, idx, *args)                                    # iteration t+1, cold start
     warm = host.pref_create(kt, X, offsets, idx, *args, warm_from=prev)                    # iteration t+1, warm start
