@@ -269,9 +269,14 @@ namespace
         TRY(phase_begin(ctx, "gram"));
         const int nt = ctx->ld / TILE;
         ProfScope prof_scope(ctx, "gram");
-        gram_tile_kernel<0><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld,
-                                                                         dp(ctx->theta), dp(ctx->inv_l), noise,
-                                                                         kernel_type, dp(ctx->K), nullptr, nullptr);
+        static const bool first_layout = std::getenv("SLSGP_GRAM_V1") && std::atoi(std::getenv("SLSGP_GRAM_V1")) != 0; // A/B switch
+        if (first_layout)
+            gram_tile_kernel<0><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld, dp(ctx->theta), dp(ctx->inv_l), noise,
+                                                                             kernel_type, dp(ctx->K), nullptr, nullptr);
+        else if (kernel_type == 0)
+            gram_sym_kernel<0><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld, dp(ctx->theta), dp(ctx->inv_l), noise, dp(ctx->K));
+        else
+            gram_sym_kernel<1><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ctx->ld, dp(ctx->theta), dp(ctx->inv_l), noise, dp(ctx->K));
         LAUNCH_CHECK();
         TRY(phase_end(ctx, "gram"));
         ctx->has_gram = true;
