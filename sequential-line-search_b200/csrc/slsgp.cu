@@ -594,8 +594,9 @@ namespace
         return SLSGP_OK;
     }
 
-    // k* operand of one shard into shard buffer `buf`, on `st` (the pipeline's `pre` stream).
-    slsgp_status tensor_kstar(slsgp_ctx* ctx, int buf, const double* d_Xq, long long Mc, cudaStream_t st)
+    // k* operand of one shard into shard buffer `buf`, on `st`. under_gemm: the launch shares the SMs with the persistent
+    // contraction kernel of the previous shard (one CTA per SM, see kstar16_strip_kernel); else it has the GPU to itself.
+    slsgp_status tensor_kstar(slsgp_ctx* ctx, int buf, const double* d_Xq, long long Mc, cudaStream_t st, bool under_gemm)
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
@@ -604,17 +605,41 @@ namespace
         __half*         Gs    = Ks + (size_t) 2 * ctx->tc_Mcap * ldt; // Matern only
         __half*         Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
         ProfScope       ps(ctx, "tc_kstar", st);
-        const size_t    smem = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + D * 128);
-        static bool     kstar_attr_dev[64] = {};
-        bool&           kstar_attr = kstar_attr_dev[ctx->device & 63];
+        static const bool tiled = std::getenv("SLSGP_KSTAR_V1") && std::atoi(std::getenv("SLSGP_KSTAR_V1")) != 0; // A/B: the first generator
+        static bool       kstar_attr_dev[64] = {};
+        bool&             kstar_attr = kstar_attr_dev[ctx->device & 63];
         if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
         {
-            CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int) (sizeof(float) * (64 * 68 + 67 * 128))));
+            const int big = (int) (sizeof(float) * (64 * 68 + 67 * 128));
+            CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CUDA_TRY(cudaFuncSetAttribute(kstar16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CUDA_TRY(cudaFuncSetAttribute(kstar16_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+            CUDA_TRY(cudaFuncSetAttribute(kstar16_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             kstar_attr = true;
         }
-        kstar16_kernel<<<dim3(ldt / 128, (unsigned) (Mpad / 64)), 256, smem, st>>>(
-            d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo, ctx->kernel_type, Gs, Gs_lo);
+        if (tiled)
+        {
+            const size_t smem = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + D * 128);
+            const dim3   grid(ldt / 128, (unsigned) (Mpad / 64));
+            if (ctx->kernel_type == 0)
+                kstar16_kernel<0><<<grid, 256, smem, st>>>(d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo, Gs, Gs_lo);
+            else
+                kstar16_kernel<1><<<grid, 256, smem, st>>>(d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks, Ks_lo, Gs, Gs_lo);
+        }
+        else
+        {
+            int n_sm = 0;
+            CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+            const size_t smem     = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + 2 * D * 64);
+            const int    n_strips = (int) (Mpad / 64);
+            const int    grid     = std::min(n_strips, (under_gemm ? 1 : 4) * n_sm);
+            if (ctx->kernel_type == 0)
+                kstar16_strip_kernel<0><<<grid, 256, smem, st>>>(d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks,
+                                                                  Ks_lo, Gs, Gs_lo, n_strips);
+            else
+                kstar16_strip_kernel<1><<<grid, 256, smem, st>>>(d_Xq, Mc, D, ctx->N, ldt, ptr<float>(ctx->Xs32), dp(ctx->inv_l), ptr<TcScales>(ctx->tcs), Ks,
+                                                                  Ks_lo, Gs, Gs_lo, n_strips);
+        }
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -741,7 +766,8 @@ namespace
         const long long cap = ctx->Mcap, n_shards = (job.M + cap - 1) / cap;
         if (n_shards == 0) return SLSGP_OK;
         static const bool overlap = !(std::getenv("SLSGP_PIPELINE") && std::atoi(std::getenv("SLSGP_PIPELINE")) == 0);
-        static const bool kstar_overlap = std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) != 0;
+        // k* of shard s + 1 on `pre`, under the contraction of shard s (see kstar16_kernel); SLSGP_KSTAR_OVERLAP=0 puts it back in front
+        static const bool kstar_overlap = !(std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) == 0);
         // a single shard has nothing to overlap with: keep it on one stream (one-candidate calls are latency-bound)
         const bool   multi = overlap && n_shards > 1;
         cudaStream_t main = ctx->stream, pre = multi ? ctx->pre_stream : main, post = multi ? ctx->post_stream : main;
@@ -767,9 +793,8 @@ namespace
                 candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, pre>>>(job.seed, job.first + m0, Mc, D, xq);
                 LAUNCH_CHECK();
             }
-            // The k* generator can ride on `pre` too (SLSGP_KSTAR_OVERLAP=1). Default off: under the tensor load the chip is
-            // power-capped, the two kernels share one budget, and the measured step is shorter when they run back to back.
-            if (tensor && kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre));
+            // the k* generator rides on `pre` too: it co-resides with the persistent contraction CTAs (64 registers per thread)
+            if (tensor && kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre, multi && s > 0));
             if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
             return SLSGP_OK;
         };
@@ -801,7 +826,7 @@ namespace
             if ((job.argmax || job.slice_len > 0) && !o.val) o.val = dp(ctx->o_val) + (size_t) b * cap;
             if (tensor)
             {
-                if (!kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, main));
+                if (!kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, main, false));
                 TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
             }
             else

@@ -141,12 +141,18 @@ namespace slsgp
     // pipe (FADD2 + FFMA2: two observations per issue slot); Xs32 holds the NEGATED observation coordinates.
     // Tile: 64 candidates x 128 observations per CTA. grid: (ldt / 128, Mpad / 64); dynamic smem: (64 * DQ + D * 128) floats,
     // DQ = round_up(D, 4).
-    __global__ void __launch_bounds__(256)
+    // Register budget: 64 per thread (4 CTAs per SM by __launch_bounds__). The contraction kernel below keeps one persistent
+    // 256-thread CTA of 188 registers on every SM, which leaves 16384 registers = exactly one 64-register CTA of this kernel
+    // (and ~14 KB of shared memory): with that the generator of shard s + 1 runs UNDER the contraction of shard s instead of
+    // in front of it (run_sweep puts it on the `pre` stream). At 71 registers it could not co-reside and the overlap was void.
+    template <int KT>
+    __global__ void __launch_bounds__(256, 4)
         kstar16_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt,
                        const float* __restrict__ Xs32, const double* __restrict__ inv_l,
-                       const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo, int kernel_type,
+                       const TcScales* __restrict__ sc, __half* __restrict__ Ks, __half* __restrict__ Ks_lo,
                        __half* __restrict__ Gs, __half* __restrict__ Gs_lo)
     {
+        constexpr int kernel_type = KT;
         extern __shared__ __align__(16) float ksm[];
         const int               DQ = (D + 3) & ~3; // row stride of sq: 16-byte aligned rows
         float*                  sq = ksm;          // [64][DQ]
@@ -256,6 +262,146 @@ namespace slsgp
                     *reinterpret_cast<uint2*>(Gs_lo + off)      = *reinterpret_cast<const uint2*>(&gl[0]);
                     *reinterpret_cast<uint2*>(Gs_lo + off + 64) = *reinterpret_cast<const uint2*>(&gl[2]);
                 }
+            }
+        }
+    }
+
+    // ---- k* generator, persistent form ---------------------------------------------------------------------------------
+    // Same arithmetic and output as kstar16_kernel. A CTA takes whole strips of 64 candidates x ALL observations and walks them
+    // in 64-observation chunks whose length-scaled coordinates (Xs32 rows) arrive through a double-buffered cp.async pipeline,
+    // so one resident CTA per SM keeps its eight warps busy: global latency is paid once per strip, not once per 8192 values.
+    // That is the form that can live UNDER the contraction kernel of the previous shard: the contraction keeps one persistent
+    // 188-register CTA and ~213 KB of shared memory on every SM, which leaves room for exactly one 256-thread CTA of <= 64
+    // registers and <= 13 KB; launched with one CTA per SM both kernels are fully resident whatever order the block scheduler
+    // places them in. Shared memory: sq [64][DQ] + sx [2][D][64] floats (12 KB at D = 16).
+    // thread = 4 candidates (tm = tid >> 4) x 4 consecutive observations (tj = tid & 15) per chunk.
+    __device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gmem_src)
+    {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(tc::smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+    }
+    __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+    template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+    template <int KT>
+    __global__ void __launch_bounds__(256, 4)
+        kstar16_strip_kernel(const double* __restrict__ Xq, long long Mc, int D, int N, int ldt, const float* __restrict__ Xs32,
+                             const double* __restrict__ inv_l, const TcScales* __restrict__ sc, __half* __restrict__ Ks,
+                             __half* __restrict__ Ks_lo, __half* __restrict__ Gs, __half* __restrict__ Gs_lo, int n_strips)
+    {
+        extern __shared__ __align__(16) float ksm[];
+        const int DQ = (D + 3) & ~3;
+        float*    sq = ksm;           // [64][DQ]
+        float*    sx = ksm + 64 * DQ; // [2][D][64], negated observation coordinates
+        const int tid = threadIdx.x, tj = tid & 15, tm = tid >> 4, n_chunks = ldt / 64;
+        const float c1 = -0.72134752044448170368f; // -0.5 * log2(e)
+        const float c0 = sc->c0;
+
+        auto prefetch = [&](int chunk, int buf) {
+            // D rows of 64 floats = 16 sixteen-byte pieces per row
+            for (int e = tid; e < D * 16; e += 256)
+                cp_async_16(sx + buf * D * 64 + (e >> 4) * 64 + (e & 15) * 4, Xs32 + (size_t) (e >> 4) * ldt + chunk * 64 + (e & 15) * 4);
+            cp_async_commit();
+        };
+
+        for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x)
+        {
+            const long long m_base = (long long) strip * 64;
+            __syncthreads(); // the previous strip's readers of sq / sx are done
+            prefetch(0, 0);
+            for (int e = tid; e < 64 * DQ; e += 256)
+            {
+                const int       p = e / DQ, d = e - p * DQ;
+                const long long m = m_base + p;
+                sq[p * DQ + d]  = (m < Mc && d < D) ? (float) ((Xq[(size_t) d + (size_t) m * D] - 0.5) * inv_l[d]) : 0.f;
+            }
+            for (int chunk = 0; chunk < n_chunks; ++chunk)
+            {
+                const int buf = chunk & 1, j_base = chunk * 64;
+                if (chunk + 1 < n_chunks)
+                {
+                    prefetch(chunk + 1, buf ^ 1);
+                    cp_async_wait<1>();
+                }
+                else
+                    cp_async_wait<0>();
+                __syncthreads();
+                const float* sxb = sx + buf * D * 64;
+                float2       r2[4][2];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) r2[i][0] = r2[i][1] = make_float2(0.f, 0.f);
+                for (int d0 = 0; d0 < DQ; d0 += 4)
+                {
+                    float4 qv[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) qv[i] = *reinterpret_cast<const float4*>(&sq[(tm * 4 + i) * DQ + d0]);
+#pragma unroll
+                    for (int dd = 0; dd < 4; ++dd)
+                    {
+                        if (d0 + dd < D)
+                        {
+                            const float4 xa    = *reinterpret_cast<const float4*>(&sxb[(d0 + dd) * 64 + tj * 4]);
+                            const float2 x2[2] = {make_float2(xa.x, xa.y), make_float2(xa.z, xa.w)};
+#pragma unroll
+                            for (int i = 0; i < 4; ++i)
+                            {
+                                const float  q  = dd == 0 ? qv[i].x : (dd == 1 ? qv[i].y : (dd == 2 ? qv[i].z : qv[i].w));
+                                const float2 q2 = make_float2(q, q);
+#pragma unroll
+                                for (int jj = 0; jj < 2; ++jj)
+                                {
+                                    const float2 df = tc::fadd2(q2, x2[jj]); // q - x
+                                    r2[i][jj]       = tc::ffma2(df, df, r2[i][jj]);
+                                }
+                            }
+                        }
+                    }
+                }
+                const bool interior = m_base + 64 <= Mc && j_base + 64 <= N;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                {
+                    const long long m = m_base + tm * 4 + i;
+                    __half2         h[2], hl[2], gh[2], gl[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj)
+                    {
+                        const int j = j_base + tj * 4 + jj * 2;
+                        float     v0, v1, g0 = 0.f, g1 = 0.f;
+                        if (KT == 0)
+                            v0 = tc::ex2_approx(fmaf(r2[i][jj].x, c1, c0)), v1 = tc::ex2_approx(fmaf(r2[i][jj].y, c1, c0));
+                        else
+                        {
+                            const float s0 = sqrtf(5.f * r2[i][jj].x), s1 = sqrtf(5.f * r2[i][jj].y);
+                            const float e0 = tc::ex2_approx(fmaf(s0, -1.44269504088896340736f, c0));
+                            const float e1 = tc::ex2_approx(fmaf(s1, -1.44269504088896340736f, c0));
+                            v0 = e0 * fmaf(s0, fmaf(s0, 0.33333333333333333f, 1.f), 1.f), v1 = e1 * fmaf(s1, fmaf(s1, 0.33333333333333333f, 1.f), 1.f);
+                            g0 = -1.66666666666666667f * e0 * (1.f + s0), g1 = -1.66666666666666667f * e1 * (1.f + s1);
+                        }
+                        if (!interior)
+                        {
+                            if (!(m < Mc && j < N)) v0 = 0.f, g0 = 0.f;
+                            if (!(m < Mc && j + 1 < N)) v1 = 0.f, g1 = 0.f;
+                        }
+                        h[jj]          = __floats2half2_rn(v0, v1);
+                        const float2 b = __half22float2(h[jj]);
+                        hl[jj]         = __floats2half2_rn(v0 - b.x, v1 - b.y);
+                        if (KT != 0)
+                        {
+                            gh[jj]         = __floats2half2_rn(g0, g1);
+                            const float2 c = __half22float2(gh[jj]);
+                            gl[jj]         = __floats2half2_rn(g0 - c.x, g1 - c.y);
+                        }
+                    }
+                    const size_t off = (size_t) m * ldt + j_base + tj * 4;
+                    *reinterpret_cast<uint2*>(Ks + off) = *reinterpret_cast<const uint2*>(&h[0]);
+                    if (Ks_lo) *reinterpret_cast<uint2*>(Ks_lo + off) = *reinterpret_cast<const uint2*>(&hl[0]);
+                    if (KT != 0)
+                    {
+                        *reinterpret_cast<uint2*>(Gs + off) = *reinterpret_cast<const uint2*>(&gh[0]);
+                        if (Gs_lo) *reinterpret_cast<uint2*>(Gs_lo + off) = *reinterpret_cast<const uint2*>(&gl[0]);
+                    }
+                }
+                __syncthreads(); // buffer `buf` is refilled by the prefetch of the iteration after next
             }
         }
     }
