@@ -88,6 +88,12 @@ extern "C"
     slsgp_status slsgp_set_compat_flags(slsgp_ctx* ctx, unsigned flags);
     slsgp_status slsgp_set_sweep_mode(slsgp_ctx* ctx, slsgp_sweep_mode mode);
     slsgp_status slsgp_get_sweep_mode(const slsgp_ctx* ctx, slsgp_sweep_mode* mode_out);
+    /* Two-tier precision of the tensor modes: after a sweep that returns per-candidate arrays, the candidates whose posterior
+     * variance came out below tau * a (a = signal variance; these sit next to data points, where sigma^2 = a - k K^-1 k and the
+     * sums behind grad sigma cancel and the fp16 / fp32 round-off is amplified by a / sigma^2) are re-evaluated through the
+     * IEEE-double sweep and overwritten. tau in [0, 1]; 0 switches the second tier off; default 0.1 (environment variable
+     * SLSGP_REFINE_TAU). Costs one host synchronisation per call and nothing else when no candidate qualifies. */
+    slsgp_status slsgp_set_refine_threshold(slsgp_ctx* ctx, double tau);
     /* Use a caller-owned CUDA stream (a cudaStream_t passed as void*) instead of the context's own; NULL restores
      * the context's stream. Lets a host framework order libslsgp work with its own copies and events. */
     slsgp_status slsgp_set_stream(slsgp_ctx* ctx, void* cuda_stream);

@@ -30,6 +30,7 @@ _API = [
     ("slsgp_set_compat_flags", C.c_int, [C.c_void_p, C.c_uint]),
     ("slsgp_set_sweep_mode", C.c_int, [C.c_void_p, C.c_int]),
     ("slsgp_get_sweep_mode", C.c_int, [C.c_void_p, C.POINTER(C.c_int)]),
+    ("slsgp_set_refine_threshold", C.c_int, [C.c_void_p, C.c_double]),
     ("slsgp_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slsgp_synchronize", C.c_int, [C.c_void_p]),
     ("slsgp_set_data", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
@@ -259,6 +260,9 @@ class Context:
         out = np.empty((self.D + 1, self.N * self.N))
         self._check(self.lib.slsgp_gram_theta_derivative(self.h, kernel_type, _p(theta), _p(out)))
         return out.reshape(self.D + 1, self.N, self.N).transpose(0, 2, 1)
+
+    def set_refine_threshold(self, tau):
+        self._check(self.lib.slsgp_set_refine_threshold(self.h, float(tau)))
 
     def trim(self, keep_bytes=0):
         self._check(self.lib.slsgp_trim(self.h, keep_bytes))

@@ -73,6 +73,8 @@ struct slsgp_ctx
     DevBuf pref_off, pref_idx, slot_off, slot_list, loglik, contrib, grad_y, Ymat, g_l;
     int    P = 0, pref_total = 0;
     DevBuf Xq, Kstar, Gstar, Beta, P1, P2, stats, o_mu, o_sigma, o_dmu, o_dsigma, o_val, o_grad, am_part, am_acc;
+    DevBuf rf_count, rf_index, rf_X, rf_out; // two-tier precision of the tensor sweep (RefineList)
+    double refine_tau = 0.1;                // candidates with sigma^2 < tau * a are re-evaluated in IEEE double; 0 = off
     long long Mcap = 0;
 
     // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
@@ -584,12 +586,12 @@ namespace
     }
 
     slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
-                              int n_parts = 0, double x_shift = 0.0, int ldp = 0)
+                              int n_parts = 0, double x_shift = 0.0, int ldp = 0, RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
     {
         ProfScope ps(ctx, "sweep_finish");
         sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
             d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ldp ? ldp : ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
-            acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x), x_shift);
+            acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x), x_shift, refine);
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -645,7 +647,8 @@ namespace
     }
 
     // contraction + fused epilogue + acquisition formulas of one shard whose k* operand sits in shard buffer `buf`
-    slsgp_status tensor_main(slsgp_ctx* ctx, int buf, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out)
+    slsgp_status tensor_main(slsgp_ctx* ctx, int buf, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
+                             RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
@@ -683,7 +686,7 @@ namespace
                 default: return fail(ctx, SLSGP_ERR_INVALID, "tensor sweep: unsupported D");
             }
         }
-        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1, 0.5, D);
+        return sweep_finish(ctx, acq_type, ucb_beta, d_Xq, Mc, out, split - 1, 0.5, D, refine);
     }
 
     slsgp_status sweep_shard(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc,
@@ -759,6 +762,85 @@ namespace
         ArgMax*       slice_best = nullptr;
     };
 
+    // Second tier of the tensor sweep: the candidates sweep_finish_kernel listed (sigma^2 < tau * a) go through the IEEE-double
+    // sweep in chunks and their results replace the tensor-path ones. One host synchronisation (the count); nothing to do in the
+    // common case of candidates away from the data.
+    slsgp_status refine_listed(slsgp_ctx* ctx, const SweepJob& job, long long cap)
+    {
+        cudaStream_t main = ctx->stream;
+        const int    D = ctx->D;
+        int          count = 0;
+        CUDA_TRY(cudaMemcpyAsync(&count, ctx->rf_count.p, sizeof(int), cudaMemcpyDeviceToHost, main));
+        CUDA_TRY(cudaStreamSynchronize(main)); // main has already waited for the last result copies of a host-buffer job
+        const int R = (int) std::min<long long>(count, cap);
+        if (R <= 0) return SLSGP_OK;
+        const int Rc = (int) std::min<long long>(2048, ctx->Mcap); // P1 / P2 / stats hold Mcap candidates
+        const size_t col = sizeof(double) * (size_t) ctx->ld;
+        TRY(ensure(ctx, ctx->Kstar, col * Rc));
+        TRY(ensure(ctx, ctx->Gstar, col * Rc));
+        TRY(ensure(ctx, ctx->Beta, col * Rc));
+        TRY(ensure(ctx, ctx->rf_X, sizeof(double) * (size_t) D * Rc));
+        TRY(ensure(ctx, ctx->rf_out, sizeof(double) * (size_t) (3 + 3 * D) * Rc));
+        std::vector<long long> index;
+        std::vector<double>    hx, hout;
+        if (job.h_Xq || job.host_out)
+        {
+            index.resize((size_t) R);
+            CUDA_TRY(cudaMemcpyAsync(index.data(), ctx->rf_index.p, sizeof(long long) * (size_t) R, cudaMemcpyDeviceToHost, main));
+            CUDA_TRY(cudaStreamSynchronize(main));
+        }
+        double*  base = dp(ctx->rf_out);
+        SweepOut ro;
+        ro.mu = base, ro.sigma = base + Rc, ro.val = base + 2 * (size_t) Rc;
+        ro.dmu = base + 3 * (size_t) Rc, ro.dsigma = ro.dmu + (size_t) D * Rc, ro.grad = ro.dsigma + (size_t) D * Rc;
+        const bool want_grad = job.dmu || job.dsigma || job.grad;
+        if (!want_grad) ro.dmu = ro.dsigma = ro.grad = nullptr;
+        for (int r0 = 0; r0 < R; r0 += Rc)
+        {
+            const int        Rn  = std::min(Rc, R - r0);
+            const long long* idx = ptr<long long>(ctx->rf_index) + r0;
+            if (job.h_Xq)
+            {
+                hx.resize((size_t) Rn * D);
+                for (int r = 0; r < Rn; ++r) std::memcpy(&hx[(size_t) r * D], job.h_Xq + (size_t) index[(size_t) r0 + r] * D, sizeof(double) * D);
+                CUDA_TRY(cudaMemcpyAsync(ctx->rf_X.p, hx.data(), sizeof(double) * hx.size(), cudaMemcpyHostToDevice, main));
+                CUDA_TRY(cudaStreamSynchronize(main)); // hx is pageable and reused by the next chunk
+            }
+            else
+            {
+                refine_gather_kernel<<<(Rn * D + 255) / 256, 256, 0, main>>>(idx, Rn, D, job.d_Xq, job.generate ? 1 : 0, job.seed, job.first, dp(ctx->rf_X));
+                LAUNCH_CHECK();
+            }
+            TRY(sweep_shard(ctx, job.acq_type, job.ucb_beta, dp(ctx->rf_X), Rn, ro));
+            if (job.host_out)
+            {
+                hout.resize((size_t) (3 + 3 * D) * Rc);
+                CUDA_TRY(cudaMemcpyAsync(hout.data(), base, sizeof(double) * hout.size(), cudaMemcpyDeviceToHost, main));
+                CUDA_TRY(cudaStreamSynchronize(main));
+                const double *h_mu = hout.data(), *h_sigma = h_mu + Rc, *h_val = h_mu + 2 * (size_t) Rc, *h_dmu = h_mu + 3 * (size_t) Rc,
+                             *h_dsigma = h_dmu + (size_t) D * Rc, *h_grad = h_dsigma + (size_t) D * Rc;
+                for (int r = 0; r < Rn; ++r)
+                {
+                    const size_t m = (size_t) index[(size_t) r0 + r];
+                    if (job.mu) job.mu[m] = h_mu[r];
+                    if (job.sigma) job.sigma[m] = h_sigma[r];
+                    if (job.val) job.val[m] = h_val[r];
+                    if (job.dmu) std::memcpy(job.dmu + m * D, h_dmu + (size_t) r * D, sizeof(double) * D);
+                    if (job.dsigma) std::memcpy(job.dsigma + m * D, h_dsigma + (size_t) r * D, sizeof(double) * D);
+                    if (job.grad) std::memcpy(job.grad + m * D, h_grad + (size_t) r * D, sizeof(double) * D);
+                }
+            }
+            else
+            {
+                SweepOut dst;
+                dst.mu = job.mu, dst.sigma = job.sigma, dst.val = job.val, dst.dmu = job.dmu, dst.dsigma = job.dsigma, dst.grad = job.grad;
+                refine_scatter_kernel<<<(Rn * (D + 1) + 255) / 256, 256, 0, main>>>(idx, Rn, D, ro, dst);
+                LAUNCH_CHECK();
+            }
+        }
+        return SLSGP_OK;
+    }
+
     slsgp_status run_sweep(slsgp_ctx* ctx, const SweepJob& job)
     {
         const bool      tensor = is_tensor_mode(ctx->sweep_mode);
@@ -799,6 +881,18 @@ namespace
             return SLSGP_OK;
         };
 
+        // Two-tier precision (tensor modes, jobs that return per-candidate arrays): sweep_finish_kernel lists the candidates with
+        // sigma^2 < tau * a; they are re-evaluated in IEEE double after the last shard (refine_listed below).
+        const bool      refine_on  = tensor && ctx->refine_tau > 0.0 && !job.argmax && job.slice_len == 0 &&
+                                (job.mu || job.sigma || job.val || job.dmu || job.dsigma || job.grad);
+        const long long refine_cap = std::min<long long>(job.M, 1LL << 21);
+        if (refine_on)
+        {
+            TRY(ensure(ctx, ctx->rf_count, sizeof(int)));
+            TRY(ensure(ctx, ctx->rf_index, sizeof(long long) * (size_t) refine_cap));
+            CUDA_TRY(cudaMemsetAsync(ctx->rf_count.p, 0, sizeof(int), main));
+        }
+
         TRY(stage_in(0));
         for (long long s = 0; s < n_shards; ++s)
         {
@@ -827,7 +921,9 @@ namespace
             if (tensor)
             {
                 if (!kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, main, false));
-                TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
+                RefineList rl{nullptr, nullptr, 0, 0, 0.0};
+                if (refine_on) rl = RefineList{ptr<int>(ctx->rf_count), ptr<long long>(ctx->rf_index), refine_cap, m0, ctx->refine_tau};
+                TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o, rl));
             }
             else
                 TRY(sweep_shard(ctx, job.acq_type, job.ucb_beta, xq_of(s), Mc, o));
@@ -865,6 +961,7 @@ namespace
         if (job.host_out && multi)
             for (long long s = std::max<long long>(0, n_shards - 2); s < n_shards; ++s)
                 CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[s & 1], 0));
+        if (refine_on) TRY(refine_listed(ctx, job, refine_cap));
         return SLSGP_OK;
     }
 } // namespace
@@ -912,6 +1009,7 @@ extern "C"
                  cudaEventCreateWithFlags(&ctx->ev_main[b], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
         if (const char* e = std::getenv("SLSGP_TC_PAIR")) ctx->tc_ncta = std::atoi(e) ? 2 : 1;
+        if (const char* e = std::getenv("SLSGP_REFINE_TAU")) ctx->refine_tau = std::min(1.0, std::max(0.0, std::atof(e)));
         ctx->pinned_bytes = 1 << 16;
         ok                = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;
         if (!ok)
@@ -936,7 +1034,7 @@ extern "C"
                          &ctx->slot_list, &ctx->loglik, &ctx->contrib, &ctx->grad_y, &ctx->Ymat, &ctx->g_l, &ctx->Xq,
                          &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu,
                          &ctx->o_sigma, &ctx->o_dmu, &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->am_part,
-                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb, &ctx->tc_qx, &ctx->tc_P2x, &ctx->mx_best, &ctx->mx_X, &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
+                         &ctx->am_acc, &ctx->chol_flags, &ctx->Bmat, &ctx->Xt, &ctx->Xs32, &ctx->tcs, &ctx->Ks, &ctx->tc_err, &ctx->comb, &ctx->tc_qx, &ctx->tc_P2x, &ctx->mx_best, &ctx->mx_X, &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad, &ctx->rf_count, &ctx->rf_index, &ctx->rf_X, &ctx->rf_out};
         for (DevBuf* b : all)
             if (b->p) cudaFree(b->p);
         for (auto& kv : ctx->phases)
@@ -969,7 +1067,7 @@ extern "C"
         if (!ctx) return SLSGP_ERR_INVALID;
         DevBuf* scratch[] = {&ctx->Xq, &ctx->Kstar, &ctx->Gstar, &ctx->Beta, &ctx->P1, &ctx->P2, &ctx->stats, &ctx->o_mu, &ctx->o_sigma, &ctx->o_dmu,
                              &ctx->o_dsigma, &ctx->o_val, &ctx->o_grad, &ctx->Ks, &ctx->comb, &ctx->tc_qx, &ctx->tc_P2x, &ctx->mx_best, &ctx->mx_X,
-                             &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad};
+                             &ctx->mx_Xbest, &ctx->mx_Gbest, &ctx->mx_state, &ctx->mx_val, &ctx->mx_grad, &ctx->rf_index, &ctx->rf_X, &ctx->rf_out};
         size_t  total     = 0;
         for (DevBuf* b : scratch) total += b->bytes;
         if (total <= keep_bytes) return SLSGP_OK;
@@ -999,6 +1097,14 @@ extern "C"
         if (mode != SLSGP_SWEEP_FP64 && !is_tensor_mode(mode)) return fail(ctx, SLSGP_ERR_INVALID, "unknown sweep mode");
         if (is_tensor_mode(mode) != is_tensor_mode(ctx->sweep_mode)) ctx->Mcap = 0; // the per-shard scratch differs between the two modes
         ctx->sweep_mode = mode;
+        return SLSGP_OK;
+    }
+
+    slsgp_status slsgp_set_refine_threshold(slsgp_ctx* ctx, double tau)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!(tau >= 0.0) || tau > 1.0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_set_refine_threshold: tau must lie in [0, 1]");
+        ctx->refine_tau = tau;
         return SLSGP_OK;
     }
 

@@ -89,6 +89,19 @@ namespace slsgp
         double *mu, *sigma, *dmu, *dsigma, *val, *grad; // any may be null; dmu / dsigma / grad are D x M
     };
 
+    // Two-tier precision of the tensor-core sweep: sweep_finish_kernel lists the candidates whose posterior variance is small
+    // against the signal variance (sigma^2 < tau * a: the candidates next to data points, where sigma^2 = a - k.A.k and the
+    // difference x_d gb - P2_d behind grad sigma cancel and fp16 / fp32 round-off is amplified by a / sigma^2), and run_sweep
+    // re-evaluates exactly those in IEEE double afterwards.
+    struct RefineList
+    {
+        int*       count;     // number of listed candidates (may exceed cap: only the first cap are kept); null = off
+        long long* index;     // their positions in the job's candidate sequence
+        long long  cap;
+        long long  first;     // position of this shard's candidate 0
+        double     threshold; // tau
+    };
+
     // One thread per candidate: finish grad mu / grad sigma and apply the acquisition formulas.
     // P1, P2: ldp x Mc (rows 0..D-1 used). has_data == 0 reproduces the "regressor has no data" early return
     // (src/acquisition-function.cpp:176-179, 206-209).
@@ -97,7 +110,8 @@ namespace slsgp
                             const double* __restrict__ P1, const double* __restrict__ P2, int ldp,
                             const double* __restrict__ theta, const double* __restrict__ f_best_ptr, int acq_type,
                             double ucb_beta, SweepOut o, int n_parts = 0, long long part_stride = 0,
-                            const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr, double x_shift = 0.0)
+                            const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr, double x_shift = 0.0,
+                            RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
     {
         const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (m >= Mc) return;
@@ -112,6 +126,11 @@ namespace slsgp
         const double  sig2   = a - s.y;
         const double  sigma  = sig2 < 0 ? 0.0 : sqrt(sig2); // src/preference-regressor.cpp:311-312
         const double  f_best = *f_best_ptr;
+        if (refine.count && !(sig2 >= refine.threshold * a)) // also catches NaN
+        {
+            const int slot = atomicAdd(refine.count, 1);
+            if (slot < refine.cap) refine.index[slot] = refine.first + m;
+        }
         if (o.mu) o.mu[m] = mu;
         if (o.sigma) o.sigma[m] = sigma;
 
@@ -200,6 +219,38 @@ namespace slsgp
         }
         if (acq_type == 0 && (sigma < 1e-16 || has_nan))
             for (int d = 0; d < D; ++d) grad[(size_t) d + (size_t) m * D] = 0.0;
+    }
+
+    // Refinement plumbing: candidates listed by RefineList are gathered into a compact D x R block (from a device array or from
+    // the counter-based generator), swept in IEEE double, and the compact results are scattered back to their positions.
+    __global__ void refine_gather_kernel(const long long* __restrict__ index, int R, int D, const double* __restrict__ Xq_all,
+                                         int generate, uint64_t seed, long long first, double* __restrict__ Xr)
+    {
+        const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= R * D) return;
+        const int       r = e / D, d = e - r * D;
+        const long long m = index[r];
+        Xr[e]             = generate ? candidate_coord(seed, first + m, d) : Xq_all[(size_t) d + (size_t) m * D];
+    }
+    // src: compact results (SweepOut over R candidates), dst: the job's outputs (device pointers, any may be null)
+    __global__ void refine_scatter_kernel(const long long* __restrict__ index, int R, int D, SweepOut src, SweepOut dst)
+    {
+        const int e = blockIdx.x * blockDim.x + threadIdx.x;
+        if (e >= R * (D + 1)) return;
+        const int       r = e / (D + 1), c = e - r * (D + 1);
+        const long long m = index[r];
+        if (c == D)
+        {
+            if (dst.mu) dst.mu[m] = src.mu[r];
+            if (dst.sigma) dst.sigma[m] = src.sigma[r];
+            if (dst.val) dst.val[m] = src.val[r];
+        }
+        else
+        {
+            if (dst.dmu) dst.dmu[(size_t) c + (size_t) m * D] = src.dmu[(size_t) c + (size_t) r * D];
+            if (dst.dsigma) dst.dsigma[(size_t) c + (size_t) m * D] = src.dsigma[(size_t) c + (size_t) r * D];
+            if (dst.grad) dst.grad[(size_t) c + (size_t) m * D] = src.grad[(size_t) c + (size_t) r * D];
+        }
     }
 
     // Counter-based candidates: Xq[d + i*D] = candidate_coord(seed, first + i, d)
