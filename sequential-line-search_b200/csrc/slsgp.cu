@@ -586,7 +586,7 @@ namespace
     }
 
     slsgp_status sweep_finish(slsgp_ctx* ctx, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
-                              int n_parts = 0, double x_shift = 0.0, int ldp = 0, RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
+                              int n_parts = 0, double x_shift = 0.0, int ldp = 0, RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0, 0})
     {
         ProfScope ps(ctx, "sweep_finish");
         sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
@@ -648,7 +648,7 @@ namespace
 
     // contraction + fused epilogue + acquisition formulas of one shard whose k* operand sits in shard buffer `buf`
     slsgp_status tensor_main(slsgp_ctx* ctx, int buf, int acq_type, double ucb_beta, const double* d_Xq, long long Mc, SweepOut out,
-                             RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
+                             RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0, 0})
     {
         const int       D = ctx->D, ldt = ctx->ldt, passes = tensor_passes(ctx->sweep_mode);
         const long long Mpad = round_up64(Mc, TC_BM * ctx->tc_ncta);
@@ -812,6 +812,11 @@ namespace
                 LAUNCH_CHECK();
             }
             TRY(sweep_shard(ctx, job.acq_type, job.ucb_beta, dp(ctx->rf_X), Rn, ro));
+            if (job.argmax)
+            {
+                argmax_indexed_kernel<<<1, 256, 0, main>>>(ro.val, idx, Rn, job.first, ptr<ArgMax>(ctx->am_acc));
+                LAUNCH_CHECK();
+            }
             if (job.host_out)
             {
                 hout.resize((size_t) (3 + 3 * D) * Rc);
@@ -883,8 +888,10 @@ namespace
 
         // Two-tier precision (tensor modes, jobs that return per-candidate arrays): sweep_finish_kernel lists the candidates with
         // sigma^2 < tau * a; they are re-evaluated in IEEE double after the last shard (refine_listed below).
-        const bool      refine_on  = tensor && ctx->refine_tau > 0.0 && !job.argmax && job.slice_len == 0 &&
-                                (job.mu || job.sigma || job.val || job.dmu || job.dsigma || job.grad);
+        // (arg-max jobs defer the listed candidates: they cannot win until their IEEE-double value is folded in; the slice
+        // winners of slsgp_acq_maximize are only starting points and are left alone)
+        const bool      refine_on  = tensor && ctx->refine_tau > 0.0 && job.slice_len == 0 &&
+                                (job.argmax || job.mu || job.sigma || job.val || job.dmu || job.dsigma || job.grad);
         const long long refine_cap = std::min<long long>(job.M, 1LL << 21);
         if (refine_on)
         {
@@ -921,8 +928,8 @@ namespace
             if (tensor)
             {
                 if (!kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, main, false));
-                RefineList rl{nullptr, nullptr, 0, 0, 0.0};
-                if (refine_on) rl = RefineList{ptr<int>(ctx->rf_count), ptr<long long>(ctx->rf_index), refine_cap, m0, ctx->refine_tau};
+                RefineList rl{nullptr, nullptr, 0, 0, 0.0, 0};
+                if (refine_on) rl = RefineList{ptr<int>(ctx->rf_count), ptr<long long>(ctx->rf_index), refine_cap, m0, ctx->refine_tau, job.argmax ? 1 : 0};
                 TRY(tensor_main(ctx, b, job.acq_type, job.ucb_beta, xq_of(s), Mc, o, rl));
             }
             else

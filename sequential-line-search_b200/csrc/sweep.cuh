@@ -100,6 +100,7 @@ namespace slsgp
         long long  cap;
         long long  first;     // position of this shard's candidate 0
         double     threshold; // tau
+        int        defer;     // arg-max jobs: listed candidates get val = NaN (never wins) until the second tier folds their value in
     };
 
     // One thread per candidate: finish grad mu / grad sigma and apply the acquisition formulas.
@@ -111,7 +112,7 @@ namespace slsgp
                             const double* __restrict__ theta, const double* __restrict__ f_best_ptr, int acq_type,
                             double ucb_beta, SweepOut o, int n_parts = 0, long long part_stride = 0,
                             const double2* __restrict__ qx = nullptr, const double* __restrict__ P2x = nullptr, double x_shift = 0.0,
-                            RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0})
+                            RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0, 0})
     {
         const long long m = (long long) blockIdx.x * blockDim.x + threadIdx.x;
         if (m >= Mc) return;
@@ -126,10 +127,11 @@ namespace slsgp
         const double  sig2   = a - s.y;
         const double  sigma  = sig2 < 0 ? 0.0 : sqrt(sig2); // src/preference-regressor.cpp:311-312
         const double  f_best = *f_best_ptr;
+        bool deferred = false;
         if (refine.count && !(sig2 >= refine.threshold * a)) // also catches NaN
         {
             const int slot = atomicAdd(refine.count, 1);
-            if (slot < refine.cap) refine.index[slot] = refine.first + m;
+            if (slot < refine.cap) refine.index[slot] = refine.first + m, deferred = refine.defer != 0;
         }
         if (o.mu) o.mu[m] = mu;
         if (o.sigma) o.sigma[m] = sigma;
@@ -148,7 +150,7 @@ namespace slsgp
                 const double EI = diff * Phi + sigma * phi;
                 v               = (sigma < 1e-16 || isnan(EI)) ? 0.0 : EI;
             }
-            o.val[m] = v;
+            o.val[m] = deferred ? nan("") : v;
         }
         if (!(o.dmu || o.dsigma || o.grad)) return;
 
@@ -302,6 +304,34 @@ namespace slsgp
         }
         if (threadIdx.x == 0) part[blockIdx.x] = sm[0];
     }
+    // Second tier of an arg-max job: fold the re-evaluated values of the listed candidates (val[r] belongs to candidate
+    // index0 + index[r]) into the running best. Single block.
+    __global__ void __launch_bounds__(256)
+        argmax_indexed_kernel(const double* __restrict__ val, const long long* __restrict__ index, int R, long long index0, ArgMax* acc)
+    {
+        __shared__ ArgMax sm[256];
+        ArgMax            best;
+        best.v = 0.0, best.i = -1;
+        for (int e = threadIdx.x; e < R; e += 256)
+        {
+            const double v = val[e];
+            if (!isnan(v))
+            {
+                ArgMax c;
+                c.v = v, c.i = index0 + index[e];
+                best = argmax_combine(best, c);
+            }
+        }
+        sm[threadIdx.x] = best;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1)
+        {
+            if (threadIdx.x < o) sm[threadIdx.x] = argmax_combine(sm[threadIdx.x], sm[threadIdx.x + o]);
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) acc[0] = argmax_combine(acc[0], sm[0]);
+    }
+
     // Folds the partials of this shard into the running best (acc[0]); single block.
     __global__ void __launch_bounds__(256) argmax_final_kernel(const ArgMax* __restrict__ part, int n, ArgMax* acc)
     {
