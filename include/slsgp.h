@@ -82,6 +82,15 @@ extern "C"
 
     /* ---- context -------------------------------------------------------------------------------------------- */
     slsgp_status slsgp_ctx_create(int device, slsgp_ctx** ctx_out);
+    /* A context that spans several GPUs of one node (device_ids[0] is the primary). Used exactly like a single-device context:
+     * the model is built on the primary (Gram, Cholesky, inverse and the MAP objectives are "replicas only"); the
+     * first sweep after a model change copies X, K^-1, alpha, f_best and the hyper-parameters to the other devices peer to peer
+     * (NVLink / NVSwitch); slsgp_acq_argmax, slsgp_acq_maximize (candidate ranges >= 2^16) and slsgp_posterior_batch /
+     * slsgp_acq_batch (batches >= 2^16) then split their candidates over the devices, one host thread each, and reduce the
+     * per-device winners (value, index, point) on the host - highest value, lowest candidate index on ties, so the answer of
+     * slsgp_acq_argmax does not depend on the number of devices. slsgp_ctx_destroy releases the whole group. */
+    slsgp_status slsgp_ctx_create_multi(const int* device_ids, int n_devices, slsgp_ctx** ctx_out);
+    int          slsgp_ctx_device_count(const slsgp_ctx* ctx);
     slsgp_status slsgp_ctx_destroy(slsgp_ctx* ctx);
     const char*  slsgp_last_error(const slsgp_ctx* ctx);
     const char*  slsgp_status_string(slsgp_status s);

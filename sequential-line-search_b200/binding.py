@@ -24,6 +24,8 @@ COMPAT_SE_XGRAD_2X, COMPAT_NOISELESS = 1, 2
 # every symbol include/slsgp.h declares: (name, restype, argtypes)
 _API = [
     ("slsgp_ctx_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("slsgp_ctx_create_multi", C.c_int, [C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_void_p)]),
+    ("slsgp_ctx_device_count", C.c_int, [C.c_void_p]),
     ("slsgp_ctx_destroy", C.c_int, [C.c_void_p]),
     ("slsgp_last_error", C.c_char_p, [C.c_void_p]),
     ("slsgp_status_string", C.c_char_p, [C.c_int]),
@@ -104,14 +106,22 @@ def _p(a):
 class Context:
     """One libslsgp device context. Mirrors the C ABI one to one; see include/slsgp.h for semantics."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device=0):
+        """device: one device index, or a list of indices for a multi-GPU group (slsgp_ctx_create_multi; the first is the primary)."""
         self.lib = load_library()
         h = C.c_void_p()
-        st = self.lib.slsgp_ctx_create(device, C.byref(h))
+        if isinstance(device, (list, tuple)):
+            ids = (C.c_int * len(device))(*device)
+            st = self.lib.slsgp_ctx_create_multi(ids, len(device), C.byref(h))
+        else:
+            st = self.lib.slsgp_ctx_create(device, C.byref(h))
         if st != OK:
             raise SlsgpError(st, "slsgp_ctx_create failed: no usable CUDA device (libslsgp has no CPU fallback)")
         self.h = h
         self.N = self.D = 0
+
+    def device_count(self):
+        return int(self.lib.slsgp_ctx_device_count(self.h))
 
     def close(self):
         if getattr(self, "h", None):

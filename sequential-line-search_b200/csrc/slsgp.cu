@@ -28,6 +28,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace slsgp;
@@ -85,6 +86,13 @@ struct slsgp_ctx
     bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
     long long   tc_Mcap = 0;      // rows of Ks (multiple of 128 * tc_ncta)
     int         tc_ncta = 2;      // CTAs per UMMA (1: cta_group::1, 2: CTA pair); SLSGP_TC_PAIR=0 selects 1
+
+    // multi-GPU group (slsgp_ctx_create_multi): contexts on the other devices, owned by this one. The candidate range of
+    // slsgp_acq_argmax / slsgp_acq_maximize and the batches of slsgp_posterior_batch / slsgp_acq_batch are split over the group.
+    std::vector<slsgp_ctx*> peers;
+    uint64_t                model_version = 0;   // bumped whenever (X, hyper-parameters, K^-1, alpha) change
+    uint64_t                replica_of    = 0;   // peers: the primary's model_version this replica holds
+    bool                    peer_access_tried = false;
 
     double* pinned       = nullptr; // small host staging area
     size_t  pinned_bytes = 0;
@@ -257,6 +265,36 @@ namespace
         }
     }
 
+    // device buffers of a model of ctx->N points in ctx->D dimensions (ctx->ld, Dp, ldx already set)
+    slsgp_status ensure_model_buffers(slsgp_ctx* ctx)
+    {
+        const int    D = ctx->D;
+        const size_t ld = ctx->ld, mat = sizeof(double) * ld * ld;
+        TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) ctx->ld * D)); // room for slsgp_append_point up to ld points
+
+        TRY(ensure(ctx, ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld));
+        TRY(ensure(ctx, ctx->XT1, sizeof(double) * ld * ctx->ldx));
+        TRY(ensure(ctx, ctx->theta, sizeof(double) * (D + 1)));
+        TRY(ensure(ctx, ctx->inv_l, sizeof(double) * D));
+        TRY(ensure(ctx, ctx->K, mat));
+        TRY(ensure(ctx, ctx->L, mat));
+        TRY(ensure(ctx, ctx->W, mat));
+        TRY(ensure(ctx, ctx->Kinv, mat));
+        TRY(ensure(ctx, ctx->T, mat));
+        TRY(ensure(ctx, ctx->y, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->alpha, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->Kalpha, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->vec, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->grad_y, sizeof(double) * ld));
+        TRY(ensure(ctx, ctx->Ymat, sizeof(double) * ld * ctx->ldx));
+        TRY(ensure(ctx, ctx->g_l, sizeof(double) * D));
+        TRY(ensure(ctx, ctx->scalars, sizeof(double) * 32));
+        TRY(ensure(ctx, ctx->info, sizeof(int)));
+        TRY(ensure(ctx, ctx->fbest, sizeof(double)));
+        TRY(ensure(ctx, ctx->fbest_idx, sizeof(int)));
+        return SLSGP_OK;
+    }
+
     // ---------------------------------------------------------------------------------------------------------
     // K1 / K2 / K3 on the context's current data
     // ---------------------------------------------------------------------------------------------------------
@@ -400,6 +438,7 @@ namespace
         LAUNCH_CHECK();
         TRY(phase_end(ctx, "alpha"));
         ctx->has_alpha = true;
+        ++ctx->model_version;
         return SLSGP_OK;
     }
 
@@ -971,6 +1010,105 @@ namespace
         if (refine_on) TRY(refine_listed(ctx, job, refine_cap));
         return SLSGP_OK;
     }
+    // ---------------------------------------------------------------------------------------------------------
+    // Multi-GPU group: the fitted model of the primary context is replicated onto the peers by peer-to-peer copies
+    // (NVLink / NVSwitch: X, K^-1, alpha, f_best, hyper-parameters: N^2 doubles dominate, 33.5 MB at N = 2048), once per
+    // model version; candidate ranges are then split over the group, one host thread per device, and the per-device winners
+    // (value, index, point: 8 (2 + D) bytes each) are reduced on the host: highest value, lowest candidate index on ties, so
+    // the result does not depend on the number of devices. Gram, Cholesky, inverse and the MAP objectives stay on the primary
+    // (replicas only).
+    // ---------------------------------------------------------------------------------------------------------
+    void adopt_sweep_mode(slsgp_ctx* c, int mode)
+    {
+        if (is_tensor_mode(mode) != is_tensor_mode(c->sweep_mode)) c->Mcap = 0; // the per-shard scratch differs between the two families
+        c->sweep_mode = mode;
+    }
+
+    slsgp_status replicate_model(slsgp_ctx* ctx /* primary */, slsgp_ctx* dst)
+    {
+        if (dst->replica_of == ctx->model_version && dst->has_alpha) return SLSGP_OK;
+        if (!ctx->has_alpha) return fail(ctx, SLSGP_ERR_STATE, "multi-GPU sweep needs a fitted model on the primary context");
+        CUDA_TRY(cudaSetDevice(dst->device));
+        if (!dst->peer_access_tried)
+        {
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dst->device, ctx->device) == cudaSuccess && can)
+                if (cudaDeviceEnablePeerAccess(ctx->device, 0) != cudaSuccess) cudaGetLastError(); // already enabled is fine
+            dst->peer_access_tried = true;
+        }
+        const bool same_shape = dst->has_data && dst->N == ctx->N && dst->D == ctx->D;
+        if (!same_shape)
+        {
+            dst->N = ctx->N, dst->D = ctx->D, dst->ld = ctx->ld, dst->Dp = ctx->Dp, dst->ldx = ctx->ldx;
+            dst->Mcap = 0, dst->tc_Mcap = 0;
+            dst->P = 0, dst->pref_total = 0;
+            const slsgp_status st = ensure_model_buffers(dst);
+            if (st != SLSGP_OK) return fail(ctx, st, "replica on device " + std::to_string(dst->device) + ": " + dst->err);
+        }
+        dst->tc_ready = false;
+        dst->kernel_type = ctx->kernel_type, dst->noise = ctx->noise, dst->theta_host = ctx->theta_host, dst->logdet_host = ctx->logdet_host;
+        dst->compat = ctx->compat, dst->refine_tau = ctx->refine_tau;
+        adopt_sweep_mode(dst, ctx->sweep_mode);
+        const size_t ld = ctx->ld, D = ctx->D, mat = sizeof(double) * ld * ld;
+        struct Piece
+        {
+            DevBuf *to, *from;
+            size_t  bytes;
+        } pieces[] = {{&dst->X, &ctx->X, sizeof(double) * ld * D},      {&dst->Xpad, &ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld},
+                      {&dst->XT1, &ctx->XT1, sizeof(double) * ld * ctx->ldx}, {&dst->theta, &ctx->theta, sizeof(double) * (D + 1)},
+                      {&dst->inv_l, &ctx->inv_l, sizeof(double) * D},   {&dst->Kinv, &ctx->Kinv, mat},
+                      {&dst->alpha, &ctx->alpha, sizeof(double) * ld},   {&dst->y, &ctx->y, sizeof(double) * ld},
+                      {&dst->fbest, &ctx->fbest, sizeof(double)},        {&dst->fbest_idx, &ctx->fbest_idx, sizeof(int)}};
+        for (const Piece& pc : pieces)
+            CUDA_TRY(cudaMemcpyPeerAsync(pc.to->p, dst->device, pc.from->p, ctx->device, pc.bytes, dst->stream));
+        CUDA_TRY(cudaStreamSynchronize(dst->stream));
+        // a replica serves sweeps only: no factor to update, no Gram matrix to read back
+        dst->has_data = true, dst->has_gram = false, dst->has_factor = false, dst->has_W = false, dst->has_inverse = true, dst->has_alpha = true;
+        dst->replica_of = ctx->model_version;
+        return SLSGP_OK;
+    }
+
+    // every member of the group with its share [first_g, first_g + count_g) of [first, first + count)
+    struct GroupShare
+    {
+        slsgp_ctx* ctx;
+        long long  first, count;
+    };
+    std::vector<GroupShare> split_over_group(slsgp_ctx* ctx, long long first, long long count)
+    {
+        const long long n = 1 + (long long) ctx->peers.size(), base = count / n, rem = count % n;
+        std::vector<GroupShare> out;
+        long long               at = first;
+        for (long long g = 0; g < n; ++g)
+        {
+            const long long c = base + (g < rem ? 1 : 0);
+            if (c > 0) out.push_back({g == 0 ? ctx : ctx->peers[(size_t) g - 1], at, c});
+            at += c;
+        }
+        return out;
+    }
+    // ranges smaller than this stay on the primary: a replica costs a peer copy of K^-1 and a thread hand-off
+    long long group_min_count() { return 1LL << 16; }
+
+    template <typename F> slsgp_status run_on_group(slsgp_ctx* ctx, const std::vector<GroupShare>& shares, F&& body)
+    {
+        for (const GroupShare& sh : shares)
+            if (sh.ctx != ctx)
+            {
+                adopt_sweep_mode(sh.ctx, ctx->sweep_mode);
+                sh.ctx->refine_tau = ctx->refine_tau, sh.ctx->compat = ctx->compat;
+                TRY(replicate_model(ctx, sh.ctx));
+            }
+        std::vector<slsgp_status> st(shares.size(), SLSGP_OK);
+        std::vector<std::thread>  workers;
+        for (size_t g = 1; g < shares.size(); ++g) workers.emplace_back([&, g]() { st[g] = body(shares[g], g); });
+        st[0] = body(shares[0], 0);
+        for (auto& w : workers) w.join();
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        for (size_t g = 0; g < shares.size(); ++g)
+            if (st[g] != SLSGP_OK) return fail(ctx, st[g], "device " + std::to_string(shares[g].ctx->device) + ": " + shares[g].ctx->err);
+        return SLSGP_OK;
+    }
 } // namespace
 
 // =============================================================================================================
@@ -1030,9 +1168,40 @@ extern "C"
         return SLSGP_OK;
     }
 
+    slsgp_status slsgp_ctx_create_multi(const int* device_ids, int n_devices, slsgp_ctx** ctx_out)
+    {
+        if (!ctx_out) return SLSGP_ERR_INVALID;
+        *ctx_out = nullptr;
+        if (!device_ids || n_devices <= 0) return SLSGP_ERR_INVALID;
+        for (int i = 0; i < n_devices; ++i)
+            for (int j = 0; j < i; ++j)
+                if (device_ids[i] == device_ids[j]) return SLSGP_ERR_INVALID; // one context per device
+        slsgp_ctx*   primary = nullptr;
+        slsgp_status st      = slsgp_ctx_create(device_ids[0], &primary);
+        if (st != SLSGP_OK) return st;
+        for (int i = 1; i < n_devices; ++i)
+        {
+            slsgp_ctx* peer = nullptr;
+            st              = slsgp_ctx_create(device_ids[i], &peer);
+            if (st != SLSGP_OK)
+            {
+                slsgp_ctx_destroy(primary);
+                return st;
+            }
+            primary->peers.push_back(peer);
+        }
+        cudaSetDevice(device_ids[0]);
+        *ctx_out = primary;
+        return SLSGP_OK;
+    }
+
+    int slsgp_ctx_device_count(const slsgp_ctx* ctx) { return ctx ? 1 + (int) ctx->peers.size() : 0; }
+
     slsgp_status slsgp_ctx_destroy(slsgp_ctx* ctx)
     {
         if (!ctx) return SLSGP_OK;
+        for (slsgp_ctx* peer : ctx->peers) slsgp_ctx_destroy(peer);
+        ctx->peers.clear();
         cudaSetDevice(ctx->device);
         if (ctx->stream) cudaStreamSynchronize(ctx->stream);
         DevBuf* all[] = {&ctx->X, &ctx->Xpad, &ctx->XT1, &ctx->theta, &ctx->inv_l, &ctx->K, &ctx->L, &ctx->W,
@@ -1195,28 +1364,8 @@ extern "C"
         ctx->has_data = ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
         ctx->Mcap = 0; // sweep workspace depends on ld
         ctx->tc_Mcap = 0, ctx->tc_ready = false;
-        const size_t ld = ctx->ld, mat = sizeof(double) * ld * ld;
-        TRY(ensure(ctx, ctx->X, sizeof(double) * (size_t) ctx->ld * D)); // room for slsgp_append_point up to ld points
-        TRY(ensure(ctx, ctx->Xpad, sizeof(double) * (size_t) ctx->Dp * ld));
-        TRY(ensure(ctx, ctx->XT1, sizeof(double) * ld * ctx->ldx));
-        TRY(ensure(ctx, ctx->theta, sizeof(double) * (D + 1)));
-        TRY(ensure(ctx, ctx->inv_l, sizeof(double) * D));
-        TRY(ensure(ctx, ctx->K, mat));
-        TRY(ensure(ctx, ctx->L, mat));
-        TRY(ensure(ctx, ctx->W, mat));
-        TRY(ensure(ctx, ctx->Kinv, mat));
-        TRY(ensure(ctx, ctx->T, mat));
-        TRY(ensure(ctx, ctx->y, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->alpha, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->Kalpha, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->vec, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->grad_y, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->Ymat, sizeof(double) * ld * ctx->ldx));
-        TRY(ensure(ctx, ctx->g_l, sizeof(double) * D));
-        TRY(ensure(ctx, ctx->scalars, sizeof(double) * 32));
-        TRY(ensure(ctx, ctx->info, sizeof(int)));
-        TRY(ensure(ctx, ctx->fbest, sizeof(double)));
-        TRY(ensure(ctx, ctx->fbest_idx, sizeof(int)));
+        TRY(ensure_model_buffers(ctx));
+        const size_t ld = ctx->ld;
         CUDA_TRY(cudaMemcpyAsync(ctx->X.p, X, sizeof(double) * (size_t) N * D, cudaMemcpyHostToDevice, ctx->stream));
         CUDA_TRY(cudaMemsetAsync(ctx->y.p, 0, sizeof(double) * ld, ctx->stream));
         pack_x_kernel<<<(ctx->ld + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), N, D, ctx->ld, ctx->Dp, ctx->ldx,
@@ -1401,6 +1550,23 @@ extern "C"
             return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
         TRY(require_model(ctx));
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (!ctx->peers.empty() && M >= group_min_count())
+        {
+            // the group: contiguous parts of the host batch, each through the host-buffer path of its own device
+            const std::vector<GroupShare> shares = split_over_group(ctx, 0, M);
+            const size_t                  D = (size_t) ctx->D;
+            return run_on_group(ctx, shares, [&](const GroupShare& sh, size_t) {
+                slsgp_ctx* c = sh.ctx;
+                std::vector<slsgp_ctx*> none;
+                none.swap(c->peers);
+                const size_t       o  = (size_t) sh.first;
+                const slsgp_status st = host_sweep(c, acq_type, ucb_beta, Xq + o * D, sh.count, mu ? mu + o : nullptr, sigma ? sigma + o : nullptr,
+                                                   dmu ? dmu + o * D : nullptr, dsigma ? dsigma + o * D : nullptr, val ? val + o : nullptr,
+                                                   grad ? grad + o * D : nullptr);
+                none.swap(c->peers);
+                return st;
+            });
+        }
         TRY(ensure_sweep_workspace(ctx, M));
         TRY(phase_begin(ctx, "sweep"));
         SweepJob job;
@@ -1503,6 +1669,30 @@ extern "C"
             return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
         TRY(require_model(ctx));
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (!ctx->peers.empty() && count >= group_min_count())
+        {
+            // the group: every device takes a contiguous part of the candidate range; winners reduced on the host
+            const std::vector<GroupShare> shares = split_over_group(ctx, first, count);
+            const int                     D      = ctx->D;
+            std::vector<double>           val(shares.size(), 0.0), xs(shares.size() * (size_t) D, 0.0);
+            std::vector<int64_t>          idx(shares.size(), -1);
+            TRY(run_on_group(ctx, shares, [&](const GroupShare& sh, size_t g) {
+                slsgp_ctx* c = sh.ctx;
+                std::vector<slsgp_ctx*> none;
+                none.swap(c->peers); // the member runs the single-device path
+                const slsgp_status st = slsgp_acq_argmax(c, acq_type, ucb_beta, seed, sh.first, sh.count, &xs[g * (size_t) D], &val[g], &idx[g], nullptr);
+                none.swap(c->peers);
+                return st;
+            }));
+            size_t best = 0;
+            for (size_t g = 1; g < shares.size(); ++g)
+                if (val[g] > val[best] || (val[g] == val[best] && idx[g] < idx[best])) best = g;
+            if (x_best_out) std::memcpy(x_best_out, &xs[best * (size_t) D], sizeof(double) * (size_t) D);
+            if (val_best_out) *val_best_out = val[best];
+            if (index_best_out) *index_best_out = idx[best];
+            if (grad_best_out) TRY(slsgp_acq_batch(ctx, acq_type, ucb_beta, &xs[best * (size_t) D], 1, nullptr, grad_best_out));
+            return SLSGP_OK;
+        }
         TRY(ensure_sweep_workspace(ctx, count));
         const int D = ctx->D;
         ArgMax    init;
@@ -1539,6 +1729,35 @@ extern "C"
             return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
         TRY(require_model(ctx));
         CUDA_TRY(cudaSetDevice(ctx->device));
+        if (!ctx->peers.empty() && count >= group_min_count())
+        {
+            // every device maximises over its own part of the candidate range with its share of the starts; best value wins
+            const std::vector<GroupShare> shares = split_over_group(ctx, first, count);
+            const int                     D = ctx->D, ng = (int) shares.size();
+            std::vector<double>           val(shares.size(), 0.0), vs(shares.size(), 0.0), xs(shares.size() * (size_t) D, 0.0), gs(shares.size() * (size_t) D, 0.0);
+            TRY(run_on_group(ctx, shares, [&](const GroupShare& sh, size_t g) {
+                slsgp_ctx* c = sh.ctx;
+                std::vector<slsgp_ctx*> none;
+                none.swap(c->peers);
+                const int          starts = std::max(1, n_starts / ng + ((int) g < n_starts % ng ? 1 : 0));
+                const slsgp_status st     = slsgp_acq_maximize(c, acq_type, ucb_beta, seed, sh.first, sh.count, starts, n_iters, &xs[g * (size_t) D], &val[g],
+                                                               &gs[g * (size_t) D], &vs[g]);
+                none.swap(c->peers);
+                return st;
+            }));
+            size_t best = 0;
+            double sweep_best = vs[0];
+            for (size_t g = 1; g < shares.size(); ++g)
+            {
+                if (val[g] > val[best]) best = g; // ties: the lower part of the range wins
+                sweep_best = std::max(sweep_best, vs[g]);
+            }
+            if (x_best_out) std::memcpy(x_best_out, &xs[best * (size_t) D], sizeof(double) * (size_t) D);
+            if (grad_best_out) std::memcpy(grad_best_out, &gs[best * (size_t) D], sizeof(double) * (size_t) D);
+            if (val_best_out) *val_best_out = val[best];
+            if (val_sweep_best_out) *val_sweep_best_out = sweep_best;
+            return SLSGP_OK;
+        }
         const int       D         = ctx->D;
         const long long slice_len = (count + std::min<long long>(std::min<long long>(n_starts, 16384), count) - 1) /
                                     std::min<long long>(std::min<long long>(n_starts, 16384), count);
@@ -1840,6 +2059,7 @@ extern "C"
                         "Cholesky: non-positive pivot at index " + std::to_string((int) r[4] - 1) + " (K_y is not SPD)");
         ctx->logdet_host = r[3];
         ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = true;
+        ++ctx->model_version;
         if (logdet_out) *logdet_out = r[3];
         gp_term_host(ctx, r[3], r, r + 5, want_hyper, value, g_hyper);
         return SLSGP_OK;

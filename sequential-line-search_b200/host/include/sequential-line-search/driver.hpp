@@ -18,6 +18,8 @@
 #ifndef SEQUENTIAL_LINE_SEARCH_B200_DRIVER_HPP
 #define SEQUENTIAL_LINE_SEARCH_B200_DRIVER_HPP
 
+#include <vector>
+
 namespace sequential_line_search
 {
     enum class SearchDriver
@@ -26,6 +28,13 @@ namespace sequential_line_search
         Hybrid,
         Reference,
     };
+
+    // The GPUs new regressors are built on (addition). With more than one index every regressor owns a multi-GPU group
+    // (slsgp_ctx_create_multi): the model is fitted on the first device and acquisition_func::FindNextPoint(s) / the batched
+    // queries split their candidates over all of them. Initial value: the environment variable SLS_B200_DEVICES ("0,1,2,3"),
+    // else SLS_B200_DEVICE (one index), else device 0.
+    void             SetDevices(const std::vector<int>& device_ids);
+    std::vector<int> GetDevices();
 
     bool         IsNloptAvailable();                // was the library built with NLopt?
     void         SetSearchDriver(SearchDriver mode); // throws std::runtime_error for Hybrid / Reference without NLopt

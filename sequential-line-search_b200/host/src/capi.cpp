@@ -302,6 +302,12 @@ extern "C"
         return guarded([&]() { return SetSearchDriver(mode == 0 ? SearchDriver::Native : mode == 1 ? SearchDriver::Hybrid : SearchDriver::Reference), 0; }, 1);
     }
 
+    int b200_set_devices(const int* ids, int n)
+    {
+        return guarded([&]() { return SetDevices(std::vector<int>(ids, ids + n)), 0; }, 1);
+    }
+    int b200_get_device_count() { return (int) GetDevices().size(); }
+
     // ---- Regressor virtual interface ------------------------------------------------------------------------------------
     double b200_predict_mu(const void* r, int D, const double* x)
     {

@@ -9,6 +9,7 @@
 #include <sequential-line-search/regressors.hpp>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace sequential_line_search
 {
@@ -27,6 +28,8 @@ namespace sequential_line_search
         // New context on the device named by SLS_B200_DEVICE (default 0). Throws when there is no usable GPU.
         std::shared_ptr<slsgp_ctx> make_device();
         void                       drain_device_pool(); // destroy the idle pooled contexts
+        void                       set_device_list(const std::vector<int>& ids);
+        std::vector<int>           get_device_list();
 
         inline slsgp_kernel_type to_abi(KernelType t)
         {

@@ -40,6 +40,18 @@ namespace sequential_line_search
             }
         } // namespace
 
+        std::vector<int>& device_list();
+        void              set_device_list(const std::vector<int>& ids)
+        {
+            std::lock_guard<std::mutex> lock(pool().mutex);
+            device_list() = ids;
+        }
+        std::vector<int> get_device_list()
+        {
+            std::lock_guard<std::mutex> lock(pool().mutex);
+            return device_list();
+        }
+
         void drain_device_pool()
         {
             std::vector<std::pair<int, slsgp_ctx*>> idle;
@@ -50,10 +62,47 @@ namespace sequential_line_search
             for (auto& e : idle) slsgp_ctx_destroy(e.second);
         }
 
+        // The devices new regressors are built on: SetDevices(), else SLS_B200_DEVICES="0,1,2,3" (a multi-GPU group whose
+        // first entry is the primary), else SLS_B200_DEVICE (one index, default 0).
+        std::vector<int>& device_list()
+        {
+            static std::vector<int>* ids = [] {
+                auto* v = new std::vector<int>;
+                if (const char* env = std::getenv("SLS_B200_DEVICES"))
+                {
+                    int  cur = 0;
+                    bool any = false;
+                    for (const char* c = env;; ++c)
+                    {
+                        if (*c >= '0' && *c <= '9')
+                            cur = cur * 10 + (*c - '0'), any = true;
+                        else
+                        {
+                            if (any) v->push_back(cur);
+                            cur = 0, any = false;
+                            if (!*c) break;
+                        }
+                    }
+                }
+                if (v->empty())
+                {
+                    const char* env = std::getenv("SLS_B200_DEVICE");
+                    v->push_back(env ? std::atoi(env) : 0);
+                }
+                return v;
+            }();
+            return *ids;
+        }
+
         std::shared_ptr<slsgp_ctx> make_device()
         {
-            const char* env    = std::getenv("SLS_B200_DEVICE");
-            const int   device = env ? std::atoi(env) : 0;
+            std::vector<int> ids;
+            {
+                std::lock_guard<std::mutex> lock(pool().mutex);
+                ids = device_list();
+            }
+            // pooled contexts are keyed by their primary device and their group size
+            const int   device = ids[0] + 1000 * (int) ids.size();
             slsgp_ctx*  raw    = nullptr;
             {
                 std::lock_guard<std::mutex> lock(pool().mutex);
@@ -68,7 +117,7 @@ namespace sequential_line_search
             }
             if (!raw)
             {
-                const slsgp_status s = slsgp_ctx_create(device, &raw);
+                const slsgp_status s = ids.size() > 1 ? slsgp_ctx_create_multi(ids.data(), (int) ids.size(), &raw) : slsgp_ctx_create(ids[0], &raw);
                 if (s != SLSGP_OK || !raw)
                     throw std::runtime_error(std::string("libslsgp: no usable CUDA device (") + slsgp_status_string(s) +
                                              "); this library has no CPU path");
@@ -823,4 +872,11 @@ namespace sequential_line_search
     MatrixXd CalcLargeKYNoiseLevelDerivative(const MatrixXd& X, const VectorXd&, const double) { return MatrixXd::Identity(X.cols(), X.cols()); } // :136-141
 
     void ReleaseDeviceResources() { internal::drain_device_pool(); }
+
+    void SetDevices(const std::vector<int>& device_ids)
+    {
+        if (device_ids.empty()) throw std::invalid_argument("SetDevices: at least one device index");
+        internal::set_device_list(device_ids);
+    }
+    std::vector<int> GetDevices() { return internal::get_device_list(); }
 } // namespace sequential_line_search

@@ -26,7 +26,7 @@ HOST_SYMBOLS = [
     "b200_acq_derivative", "b200_acq_values", "b200_find_next_point", "b200_find_next_points", "b200_data_manager_run", "b200_slider", "b200_test_minimize",
     "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
     "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver", "b200_calc_small_k", "b200_calc_large_ky_theta_derivative",
-    "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points", "b200_regressor_set_sweep_mode",
+    "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points", "b200_regressor_set_sweep_mode", "b200_set_devices", "b200_get_device_count",
 ] + ["b200_" + n for n in (
     # host/src/loop_capi.inl: optimiser front-ends and driver-dependent entry points (bound by tests/loop_support.py)
     "srand sls_create sls_destroy sls_set_hyperparams sls_set_ucb_hyperparam sls_submit sls_get_slider_ends sls_get_maximizer sls_calc_point "
@@ -44,6 +44,13 @@ def nlopt_available() -> bool:
 
 def set_search_driver(mode: int) -> None:
     if load_host_library().b200_set_search_driver(mode) != 0:
+        raise RuntimeError(load_host_library().b200_last_error().decode())
+
+
+def set_devices(ids) -> None:
+    """The GPUs new regressors are built on (sequential_line_search::SetDevices); more than one = a multi-GPU group."""
+    arr = (C.c_int * len(ids))(*ids)
+    if load_host_library().b200_set_devices(arr, len(ids)) != 0:
         raise RuntimeError(load_host_library().b200_last_error().decode())
 
 
