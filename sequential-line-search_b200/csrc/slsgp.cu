@@ -2012,7 +2012,8 @@ extern "C"
     constexpr int kSmallOutOffset = 1024; // doubles into the pinned staging area: results of the small-model kernel
 
     // Enqueue: ONE host-to-device copy of [theta | 1 / l | y], the kernel, ONE device-to-host copy of its results.
-    static slsgp_status small_model_launch(slsgp_ctx* ctx, int kernel_type, const double* theta, double noise, const double* y_host, bool want_hyper)
+    static slsgp_status small_model_launch(slsgp_ctx* ctx, int kernel_type, const double* theta, double noise, const double* y_host, bool want_hyper,
+                                           int btl_P = -1, double btl_scale = 1.0, bool btl_grad = false)
     {
         const int N = ctx->N, D = ctx->D;
         if (kernel_type != 0 && kernel_type != 1) return fail(ctx, SLSGP_ERR_INVALID, "unknown kernel_type");
@@ -2041,12 +2042,16 @@ extern "C"
         a.theta = dp(ctx->theta), a.inv_l = dp(ctx->inv_l), a.y = dp(ctx->y);
         a.K = dp(ctx->K), a.L = dp(ctx->L), a.W = dp(ctx->W), a.Kinv = dp(ctx->Kinv), a.alpha = dp(ctx->alpha), a.Kalpha = dp(ctx->Kalpha);
         a.out = out_dev, a.fbest = dp(ctx->fbest), a.fbest_idx = ptr<int>(ctx->fbest_idx), a.info = ptr<int>(ctx->info);
+        a.btl_P = btl_P, a.btl_grad = btl_grad ? 1 : 0, a.btl_scale = btl_scale;
+        a.pref_off = ptr<uint32_t>(ctx->pref_off), a.pref_idx = ptr<uint32_t>(ctx->pref_idx), a.slot_off = ptr<uint32_t>(ctx->slot_off);
+        a.slot_list = ptr<uint32_t>(ctx->slot_list), a.contrib = dp(ctx->contrib);
         {
             ProfScope ps(ctx, "small_model");
             small_model_kernel<<<1, 256, SMALL_SMEM_BYTES, ctx->stream>>>(a);
             LAUNCH_CHECK();
         }
-        CUDA_TRY(cudaMemcpyAsync(ctx->pinned + kSmallOutOffset, out_dev, sizeof(double) * (size_t) (5 + D), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaMemcpyAsync(ctx->pinned + kSmallOutOffset, out_dev, sizeof(double) * (size_t) (5 + D + (btl_P >= 0 ? 1 + N : 0)), cudaMemcpyDeviceToHost,
+                                 ctx->stream));
         return SLSGP_OK;
     }
 
@@ -2090,8 +2095,8 @@ extern "C"
             std::vector<double> theta((size_t) D + 1);
             theta[0] = x[N + 0];
             for (int i = 0; i < D; ++i) theta[(size_t) 1 + i] = x[N + 2 + i];
-            if (small) // one launch: model, alpha, scalars and the length-scale gradient (small.cuh); read back with the BTL terms
-                TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), b_used, x, want_hyper));
+            if (small) // ONE launch and two copies: model, alpha, GP scalars, length-scale gradient AND the BTL terms (small.cuh)
+                TRY(small_model_launch(ctx, (int) kernel_type, theta.data(), b_used, x, want_hyper, ctx->P, btl_scale, grad_out != nullptr));
             else
             {
                 TRY(do_gram(ctx, (int) kernel_type, theta.data(), b_used));
@@ -2109,9 +2114,9 @@ extern "C"
             TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
         }
 
-        // BTL likelihood of the tuples
+        // BTL likelihood of the tuples (the small-model launch above already holds them)
         double loglik = 0.0;
-        if (ctx->P > 0)
+        if (ctx->P > 0 && !small)
         {
             btl_tuple_kernel<<<(ctx->P + 127) / 128, 128, 0, ctx->stream>>>(
                 dp(ctx->y), ptr<uint32_t>(ctx->pref_off), ptr<uint32_t>(ctx->pref_idx), ctx->P, btl_scale,
@@ -2121,7 +2126,7 @@ extern "C"
             LAUNCH_CHECK();
             CUDA_TRY(cudaMemcpyAsync(&loglik, dp(ctx->scalars) + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
-        if (grad_out)
+        if (grad_out && !small)
         {
             btl_gather_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(
                 dp(ctx->contrib), ptr<uint32_t>(ctx->slot_off), ptr<uint32_t>(ctx->slot_list), dp(ctx->alpha), N,
@@ -2131,7 +2136,13 @@ extern "C"
         }
         TRY(phase_end(ctx, "map"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
-        if (small) TRY(small_model_collect(ctx, want_hyper, &logdet, &gp, gh.data()));
+        if (small)
+        {
+            TRY(small_model_collect(ctx, want_hyper, &logdet, &gp, gh.data()));
+            const double* r = ctx->pinned + kSmallOutOffset + 5 + D;
+            loglik          = r[0];
+            if (grad_out) std::memcpy(grad_out, r + 1, sizeof(double) * (size_t) N);
+        }
 
         double obj = loglik + gp;
         if (use_map) // log-normal hyper-priors centred on the defaults (:175-192) and their derivatives (:103-112, :69-73)

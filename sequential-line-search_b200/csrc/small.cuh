@@ -26,6 +26,13 @@ namespace slsgp
                                                          // [5 .. 5 + D) length-scale gradient: one device-to-host copy
         double *      fbest;
         int *         fbest_idx, *info;
+        // Bradley-Terry-Luce part of the preference MAP objective, fused (btl_P < 0: not wanted). Tuples in CSR form and its
+        // transpose as slsgp_set_preferences stores them; results: out[5 + D] = sum_t log BTL_t, out[6 + D + i] = d/dy_i of the
+        // whole objective = gathered BTL terms - alpha_i (btl_grad != 0), so ONE device-to-host copy returns everything.
+        int             btl_P, btl_grad;
+        double          btl_scale;
+        const uint32_t *pref_off, *pref_idx, *slot_off, *slot_list;
+        double*         contrib;
     };
 
     __global__ void __launch_bounds__(256) small_model_kernel(const SmallModelArgs a)
@@ -264,7 +271,46 @@ namespace slsgp
             a.out[3] = 2.0 * (part[3] + part[11]), a.out[4] = 0.0;
             a.fbest[0] = best.v, a.fbest_idx[0] = (int) best.i;
         }
-        __syncthreads(); // `part` is reused by the gradient reduction below
+        __syncthreads(); // `part` is reused by the reductions below
+        if (a.btl_P >= 0)
+        {
+            // same arithmetic as btl_tuple_kernel / btl_gather_kernel (map.cuh), on the y and alpha already in shared memory
+            double ll = 0.0;
+            for (int t = tid; t < a.btl_P; t += 256)
+            {
+                const uint32_t b = a.pref_off[t], e = a.pref_off[t + 1];
+                const double   f0 = ys[a.pref_idx[b]];
+                double         sum = 0.0;
+                for (uint32_t i = b; i < e; ++i) sum += exp((1.0 / a.btl_scale) * ys[a.pref_idx[i]]);
+                const double btl = exp((1.0 / a.btl_scale) * f0) / sum;
+                ll += log(btl);
+                if (a.btl_grad)
+                {
+                    const double tmp = -btl * btl / a.btl_scale;
+                    double       s2  = 0.0;
+                    for (uint32_t i = b + 1; i < e; ++i) s2 += exp((ys[a.pref_idx[i]] - f0) / a.btl_scale);
+                    a.contrib[b] = (tmp * (-s2)) / btl;
+                    for (uint32_t i = b + 1; i < e; ++i) a.contrib[i] = (tmp * exp((ys[a.pref_idx[i]] - f0) / a.btl_scale)) / btl;
+                }
+            }
+            ll = warp_sum(ll);
+            if (lane == 0) part[warp] = ll;
+            __syncthreads(); // also orders the contrib[] writes (global) before the gather below
+            if (tid == 0)
+            {
+                double sum = 0.0;
+                for (int w = 0; w < 8; ++w) sum += part[w];
+                a.out[5 + D] = sum;
+            }
+            if (a.btl_grad && tid < N)
+            {
+                double g = 0.0;
+                if (a.btl_P > 0)
+                    for (uint32_t q = a.slot_off[tid]; q < a.slot_off[tid + 1]; ++q) g += a.contrib[a.slot_list[q]];
+                a.out[6 + D + tid] = g + -al[tid];
+            }
+            __syncthreads();
+        }
         if (!a.want_hyper) return;
 
         // ---- length-scale gradient: G_t = 1 / (2 l_t) sum_ij (alpha_i alpha_j - Kinv_ij) kl(r2_ij) ((x_it - x_jt) / l_t)^2 ----
