@@ -893,7 +893,10 @@ namespace
         if (n_shards == 0) return SLSGP_OK;
         static const bool overlap = !(std::getenv("SLSGP_PIPELINE") && std::atoi(std::getenv("SLSGP_PIPELINE")) == 0);
         // k* of shard s + 1 on `pre`, under the contraction of shard s (see kstar16_kernel); SLSGP_KSTAR_OVERLAP=0 puts it back in front
-        static const bool kstar_overlap = !(std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) == 0);
+        // (only when the contraction is long enough to hide it: below ~1000 observations a shard is launch-latency bound and the
+        // one-CTA-per-SM generator would be the slower of the two; measured on the D = 64 optimiser loop, N <= 120: 74 vs 88 ms)
+        static const bool kstar_overlap_env = !(std::getenv("SLSGP_KSTAR_OVERLAP") && std::atoi(std::getenv("SLSGP_KSTAR_OVERLAP")) == 0);
+        const bool        kstar_overlap     = kstar_overlap_env && tensor && ctx->ldt >= 1024;
         // a single shard has nothing to overlap with: keep it on one stream (one-candidate calls are latency-bound)
         const bool   multi = overlap && n_shards > 1;
         cudaStream_t main = ctx->stream, pre = multi ? ctx->pre_stream : main, post = multi ? ctx->post_stream : main;

@@ -124,7 +124,9 @@ namespace sequential_line_search
             }
             return std::shared_ptr<slsgp_ctx>(raw, [device](slsgp_ctx* c) {
                 slsgp_set_sweep_mode(c, SLSGP_SWEEP_FP64);
-                slsgp_trim(c, (size_t) 64 << 20); // a pooled context keeps at most 64 MiB of grown device buffers
+                // a pooled context keeps its sweep workspaces (re-allocating ~150 MB per SubmitFeedbackData costs milliseconds)
+                // unless they have grown beyond 2 GiB (sweeps against thousands of observations)
+                slsgp_trim(c, (size_t) 2 << 30);
                 std::lock_guard<std::mutex> lock(pool().mutex);
                 if (pool().idle.size() < 4)
                     pool().idle.emplace_back(device, c);
