@@ -193,6 +193,13 @@ extern "C"
                                           int64_t M, const double* mu, const double* sigma, const double* dmu,
                                           const double* dsigma, double* val_out, double* grad_out);
 
+    /* The global stage of FindNextPoints (src/acquisition-function.cpp:264-276 over objective_for_multiple_points :63-110) as one
+     * device-resident arg-max: candidate i of [first, first + count) from the generator of slsgp_candidates, mu from `ctx`, sigma
+     * from `ctx_sigma` (same device, same D), EI / UCB with f_best of `ctx`, lowest index wins ties; only the winner is copied out. */
+    slsgp_status slsgp_pair_acq_argmax(slsgp_ctx* ctx, slsgp_ctx* ctx_sigma, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
+                                       int64_t first, int64_t count, double* x_best_out, double* val_best_out,
+                                       int64_t* index_best_out);
+
     /* Same sweep with every buffer already resident on the context's device (device pointers): no copies.
      * Any output may be NULL. Asynchronous on the context's stream. */
     slsgp_status slsgp_acq_batch_device(slsgp_ctx* ctx, slsgp_acq_type acq_type, double ucb_beta,

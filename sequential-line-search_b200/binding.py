@@ -50,6 +50,7 @@ _API = [
                                    C.POINTER(C.c_int64), c_dp]),
     ("slsgp_acq_maximize", C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, C.c_int, C.c_int, c_dp, c_dp,
                                      c_dp, c_dp]),
+    ("slsgp_pair_acq_argmax", C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_uint64, C.c_int64, C.c_int64, c_dp, c_dp, C.POINTER(C.c_int64)]),
     ("slsgp_argmax_device", C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, c_dp, C.POINTER(C.c_int64)]),
     ("slsgp_candidates", C.c_int, [C.c_void_p, C.c_uint64, C.c_int64, C.c_int64, c_dp]),
     ("slsgp_set_preferences", C.c_int, [C.c_void_p, c_u32p, c_u32p, C.c_int]),
@@ -276,6 +277,13 @@ class Context:
 
     def trim(self, keep_bytes=0):
         self._check(self.lib.slsgp_trim(self.h, keep_bytes))
+
+    def pair_acq_argmax(self, sigma_ctx, acq_type, ucb_beta, seed, first, count):
+        """mu from this context, sigma from `sigma_ctx` (same device): (x, value, index) of the best candidate."""
+        x = np.empty(self.D)
+        val, idx = C.c_double(), C.c_int64()
+        self._check(self.lib.slsgp_pair_acq_argmax(self.h, sigma_ctx.h, acq_type, ucb_beta, seed, first, count, _p(x), C.byref(val), C.byref(idx)))
+        return x, val.value, idx.value
 
     def argmax_device(self, d_val, count, index0=0):
         val, idx = C.c_double(), C.c_int64()

@@ -1630,6 +1630,69 @@ extern "C"
         return SLSGP_OK;
     }
 
+    // Schonlau's batch criterion as one device-resident arg-max: candidate i of [first, first + count) from the counter-based
+    // generator, mu from `ctx` (the original model), sigma from `ctx_sigma` (the model that already holds the pending points),
+    // the acquisition formula, a running arg-max; nothing but the winner leaves the device. Chunks of 2^17 candidates.
+    slsgp_status slsgp_pair_acq_argmax(slsgp_ctx* ctx, slsgp_ctx* ctx_sigma, slsgp_acq_type acq_type, double ucb_beta, uint64_t seed,
+                                       int64_t first, int64_t count, double* x_best_out, double* val_best_out, int64_t* index_best_out)
+    {
+        if (!ctx || !ctx_sigma) return SLSGP_ERR_INVALID;
+        if (count <= 0 || first < 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_pair_acq_argmax: empty candidate range");
+        if (acq_type != SLSGP_ACQ_EXPECTED_IMPROVEMENT && acq_type != SLSGP_ACQ_GP_UCB) return fail(ctx, SLSGP_ERR_INVALID, "unknown acq_type");
+        if (ctx->device != ctx_sigma->device) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_pair_acq_argmax: both models must live on one device");
+        if (ctx->D != ctx_sigma->D) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_pair_acq_argmax: the two models differ in dimension");
+        TRY(require_model(ctx));
+        {
+            const slsgp_status st = require_model(ctx_sigma);
+            if (st != SLSGP_OK) return fail(ctx, st, "slsgp_pair_acq_argmax: " + ctx_sigma->err);
+        }
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        const int       D = ctx->D;
+        const long long chunk = std::min<long long>(count, 1LL << 17);
+        // scratch in the first context: candidates (D x chunk) | mu | sigma | val
+        TRY(ensure(ctx, ctx->comb, sizeof(double) * (size_t) (D + 3) * chunk));
+        double *d_Xq = dp(ctx->comb), *d_mu = d_Xq + (size_t) D * chunk, *d_sigma = d_mu + chunk, *d_val = d_sigma + chunk;
+        TRY(ensure(ctx, ctx->am_part, sizeof(ArgMax) * 1024));
+        TRY(ensure(ctx, ctx->am_acc, sizeof(ArgMax)));
+        ArgMax init;
+        init.v = 0.0, init.i = -1;
+        std::memcpy(ctx->pinned, &init, sizeof(init));
+        CUDA_TRY(cudaMemcpyAsync(ctx->am_acc.p, ctx->pinned, sizeof(ArgMax), cudaMemcpyHostToDevice, ctx->stream));
+        double f_best = 0.0;
+        CUDA_TRY(cudaMemcpyAsync(&f_best, ctx->fbest.p, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        for (long long m0 = 0; m0 < count; m0 += chunk)
+        {
+            const long long Mc = std::min(chunk, count - m0);
+            candidates_kernel<<<(unsigned) ((Mc * D + 255) / 256), 256, 0, ctx->stream>>>(seed, first + m0, Mc, D, d_Xq);
+            LAUNCH_CHECK();
+            TRY(slsgp_acq_batch_device(ctx, acq_type, ucb_beta, d_Xq, Mc, d_mu, nullptr, nullptr, nullptr, nullptr, nullptr));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream)); // the candidates are complete before the second context reads them
+            {
+                const slsgp_status st = slsgp_acq_batch_device(ctx_sigma, acq_type, ucb_beta, d_Xq, Mc, nullptr, d_sigma, nullptr, nullptr, nullptr, nullptr);
+                if (st != SLSGP_OK) return fail(ctx, st, "slsgp_pair_acq_argmax: " + ctx_sigma->err);
+                CUDA_TRY(cudaStreamSynchronize(ctx_sigma->stream));
+            }
+            acq_combine_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(d_mu, d_sigma, nullptr, nullptr, D, Mc, f_best, (int) acq_type, ucb_beta,
+                                                                                    d_val, nullptr);
+            LAUNCH_CHECK();
+            const int nblk = (int) std::min<long long>(1024, (Mc + 255) / 256);
+            argmax_partial_kernel<<<nblk, 256, 0, ctx->stream>>>(d_val, Mc, first + m0, ptr<ArgMax>(ctx->am_part));
+            LAUNCH_CHECK();
+            argmax_final_kernel<<<1, 256, 0, ctx->stream>>>(ptr<ArgMax>(ctx->am_part), nblk, ptr<ArgMax>(ctx->am_acc));
+            LAUNCH_CHECK();
+        }
+        ArgMax best;
+        CUDA_TRY(cudaMemcpyAsync(&best, ctx->am_acc.p, sizeof(ArgMax), cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (best.i < 0) return fail(ctx, SLSGP_ERR_NAN, "slsgp_pair_acq_argmax: every candidate evaluated to NaN");
+        if (x_best_out)
+            for (int d = 0; d < D; ++d) x_best_out[d] = candidate_coord(seed, best.i, d);
+        if (val_best_out) *val_best_out = best.v;
+        if (index_best_out) *index_best_out = best.i;
+        return SLSGP_OK;
+    }
+
     slsgp_status slsgp_argmax_device(slsgp_ctx* ctx, const double* d_val, int64_t count, int64_t index0,
                                      double* val_best_out, int64_t* index_best_out)
     {

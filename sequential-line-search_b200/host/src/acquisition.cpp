@@ -298,31 +298,22 @@ namespace sequential_line_search
                 return points;
             }
 
-            // global stage: the counter-based candidate sequence in chunks (bounded host memory), tensor sweep for large counts
-            const long count = std::min<long>((long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter, 1L << 21);
-            const long chunk = std::min<long>(count, 1L << 17);
+            // global stage: the counter-based candidate sequence, mu from the original model and sigma from the temporary one, all
+            // on the device (slsgp_pair_acq_argmax); tensor sweep for large counts
+            const long count  = std::min<long>((long) std::max(1u, num_global_search_iters) * kCandidatesPerGlobalIter, 1L << 21);
             const bool tensor = count >= 32768 && D <= 66;
-            MatrixXd cand = MatrixXd::Zero(D, chunk);
             for (unsigned i = 0; i < num_points; ++i)
             {
-                VectorXd x_best  = VectorXd::Constant(D, 0.5);
-                double   v_best  = -std::numeric_limits<double>::infinity();
-                const uint64_t seed = search_seed(regressor) + 0x51ED27ull * (i + 1);
+                VectorXd       x_best = VectorXd::Constant(D, 0.5);
+                const uint64_t seed   = search_seed(regressor) + 0x51ED27ull * (i + 1);
                 {
-                const SweepModeGuard mode_orig(*orig, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), mode_temp(*temp, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64);
-                for (long first = 0; first < count; first += chunk)
-                {
-                    const long n = std::min(chunk, count - first);
-                    if (n != cand.cols()) cand = MatrixXd::Zero(D, n);
-                    {
-                        std::lock_guard<std::mutex> lock(orig->DeviceMutex());
-                        check(orig_ctx, slsgp_candidates(orig_ctx, seed, first, n, cand.data()), "slsgp_candidates");
-                    }
-                    VectorXd val;
-                    pair_acq(cand, val, nullptr);
-                    for (long m = 0; m < n; ++m)
-                        if (val(m) > v_best) v_best = val(m), x_best = cand.col(m); // NaN never wins, lowest index wins ties
-                }
+                    const SweepModeGuard mode_orig(*orig, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64), mode_temp(*temp, tensor ? SLSGP_SWEEP_TENSOR : SLSGP_SWEEP_FP64);
+                    slsgp_ctx* const     temp_ctx = temp->Device();
+                    std::lock_guard<std::mutex> lock_orig(orig->DeviceMutex());
+                    std::lock_guard<std::mutex> lock_temp(temp->DeviceMutex());
+                    double v_best = 0.0;
+                    check(orig_ctx, slsgp_pair_acq_argmax(orig_ctx, temp_ctx, internal::to_abi(func_type), hyperparam, seed, 0, count, x_best.data(), &v_best, nullptr),
+                          "slsgp_pair_acq_argmax");
                 } // the sweep modes are restored here: the polish below is IEEE double
                 const VectorXd x_star = polish(
                     [&](const VectorXd& x, VectorXd& g) {

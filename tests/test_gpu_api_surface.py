@@ -116,3 +116,31 @@ def test_trim_releases_the_sweep_workspace_and_keeps_the_model(oracle):
     np.testing.assert_array_equal(g0, g1)
     ctx.close()
     pkg.hostlib.load_host_library().b200_release_device_resources()
+
+
+@pytest.mark.parametrize("acq,beta,mode", [(S.EI, 1.0, "fp64"), (S.UCB, 2.0, "fp64"), (S.EI, 1.0, "tensor")])
+def test_pair_acq_argmax_equals_the_explicit_pipeline(acq, beta, mode):
+    """slsgp_pair_acq_argmax (device-resident global stage of FindNextPoints: mu from one model, sigma from another) against the
+    same steps done one by one through host buffers: slsgp_candidates, two slsgp_posterior_batch calls, slsgp_acq_from_posterior."""
+    kt, D, N = S.MATERN, 5, 40
+    X, theta = S.make_X(N + 3, D, "sls"), S.make_theta(D, "perturbed")
+    y = S.make_y(X)
+    a, b = pkg.Context(0), pkg.Context(0)
+    try:
+        a.fit(X[:, :N], kt, theta, 0.005, y[:N])
+        b.fit(X, kt, theta, 0.005, y)          # the model that already holds three pending points
+        sweep = pkg.SWEEP_TENSOR if mode == "tensor" else pkg.SWEEP_FP64
+        a.set_sweep_mode(sweep)
+        b.set_sweep_mode(sweep)
+        seed, first, count = 42, 17, 150000     # two chunks of 2^17
+        x, v, idx = a.pair_acq_argmax(b, acq, beta, seed, first, count)
+        Q = a.candidates(seed, first, count)
+        mu, _, _, _ = a.posterior_batch(Q, grads=False)
+        _, sigma, _, _ = b.posterior_batch(Q, grads=False)
+        f_best, _ = a.f_best()
+        val, _ = a.acq_from_posterior(acq, beta, f_best, mu, sigma)
+        assert idx == first + int(np.argmax(val)) and v == val.max()
+        np.testing.assert_array_equal(x, Q[:, idx - first])
+    finally:
+        a.close()
+        b.close()
