@@ -94,6 +94,10 @@ struct slsgp_ctx
     uint64_t                replica_of    = 0;   // peers: the primary's model_version this replica holds
     bool                    peer_access_tried = false;
 
+    // pinned staging ring of the host-buffer entry points for PAGEABLE caller memory (run_sweep): two shard-sized slots each way
+    double *pin_in = nullptr, *pin_out = nullptr;
+    size_t  pin_in_bytes = 0, pin_out_bytes = 0;
+
     double* pinned       = nullptr; // small host staging area
     size_t  pinned_bytes = 0;
 
@@ -801,6 +805,31 @@ namespace
         ArgMax*       slice_best = nullptr;
     };
 
+    bool is_pageable(const void* p)
+    {
+        if (!p) return false;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, p) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return true;
+        }
+        return at.type == cudaMemoryTypeUnregistered;
+    }
+    slsgp_status ensure_pinned(slsgp_ctx* ctx, double** buf, size_t* have, size_t bytes)
+    {
+        if (*have >= bytes) return SLSGP_OK;
+        if (*buf) cudaFreeHost(*buf);
+        *buf = nullptr, *have = 0;
+        if (cudaMallocHost(buf, bytes) != cudaSuccess)
+        {
+            cudaGetLastError();
+            return fail(ctx, SLSGP_ERR_NOMEM, "cudaMallocHost of " + std::to_string(bytes) + " bytes failed");
+        }
+        *have = bytes;
+        return SLSGP_OK;
+    }
+
     // Second tier of the tensor sweep: the candidates sweep_finish_kernel listed (sigma^2 < tau * a) go through the IEEE-double
     // sweep in chunks and their results replace the tensor-path ones. One host synchronisation (the count); nothing to do in the
     // common case of candidates away from the data.
@@ -910,6 +939,36 @@ namespace
             CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_start, 0));
         }
 
+        // Host buffers in pageable memory (what a C++ caller's Eigen matrices are): cudaMemcpyAsync would stage them through the
+        // driver synchronously, shard after shard, with no overlap. Instead they go through a pinned ring of two shard-sized slots
+        // each way: this thread copies (memcpy) while the copy engines and the SMs work on the neighbouring shards.
+        const bool staged = (job.h_Xq || job.host_out) &&
+                            (is_pageable(job.h_Xq) || is_pageable(job.mu) || is_pageable(job.sigma) || is_pageable(job.val) || is_pageable(job.dmu) ||
+                             is_pageable(job.dsigma) || is_pageable(job.grad));
+        size_t out_off[7] = {0, 0, 0, 0, 0, 0, 0}; // slot layout in doubles: mu | sigma | val | dmu | dsigma | grad (requested ones only)
+        if (staged)
+        {
+            double* const outs[6] = {job.mu, job.sigma, job.val, job.dmu, job.dsigma, job.grad};
+            for (int i = 0; i < 6; ++i) out_off[i + 1] = out_off[i] + (outs[i] ? (size_t) cap * (i < 3 ? 1 : D) : 0);
+            if (job.h_Xq) TRY(ensure_pinned(ctx, &ctx->pin_in, &ctx->pin_in_bytes, 2 * sizeof(double) * (size_t) D * cap));
+            if (job.host_out && out_off[6]) TRY(ensure_pinned(ctx, &ctx->pin_out, &ctx->pin_out_bytes, 2 * sizeof(double) * out_off[6]));
+        }
+        // copy the results of shard s from its pinned slot to the caller's arrays once their transfer has completed
+        auto drain = [&](long long s) -> slsgp_status {
+            const int       b  = (int) (s & 1);
+            const long long m0 = s * cap, Mc = std::min<long long>(cap, job.M - m0);
+            CUDA_TRY(cudaEventSynchronize(ctx->ev_out[b]));
+            const double* slot = ctx->pin_out + (size_t) b * out_off[6];
+            double* const outs[6] = {job.mu, job.sigma, job.val, job.dmu, job.dsigma, job.grad};
+            for (int i = 0; i < 6; ++i)
+                if (outs[i])
+                {
+                    const size_t w = i < 3 ? 1 : (size_t) D;
+                    std::memcpy(outs[i] + (size_t) m0 * w, slot + out_off[i], sizeof(double) * (size_t) Mc * w);
+                }
+            return SLSGP_OK;
+        };
+
         auto xq_of = [&](long long s) -> const double* {
             return job.d_Xq ? job.d_Xq + (size_t) (s * cap) * D : dp(ctx->Xq) + (size_t) (s & 1) * D * cap;
         };
@@ -918,7 +977,16 @@ namespace
             const long long m0 = s * cap, Mc = std::min<long long>(cap, job.M - m0);
             if (s >= 2) CUDA_TRY(cudaStreamWaitEvent(pre, ctx->ev_main[b], 0)); // shard s - 2 no longer reads buffer b
             double* xq = dp(ctx->Xq) + (size_t) b * D * cap;
-            if (job.h_Xq)
+            if (job.h_Xq && staged)
+            {
+                // pageable caller memory: this thread copies the shard into the pinned slot (free once the transfer of shard
+                // s - 2 out of it has completed), the DMA engine takes it from there while earlier shards compute
+                if (s >= 2) CUDA_TRY(cudaEventSynchronize(ctx->ev_in[b]));
+                double* slot = ctx->pin_in + (size_t) b * D * cap;
+                std::memcpy(slot, job.h_Xq + (size_t) m0 * D, sizeof(double) * (size_t) Mc * D);
+                CUDA_TRY(cudaMemcpyAsync(xq, slot, sizeof(double) * (size_t) Mc * D, cudaMemcpyHostToDevice, pre));
+            }
+            else if (job.h_Xq)
                 CUDA_TRY(cudaMemcpyAsync(xq, job.h_Xq + (size_t) m0 * D, sizeof(double) * (size_t) Mc * D, cudaMemcpyHostToDevice, pre));
             else if (job.generate)
             {
@@ -927,7 +995,7 @@ namespace
             }
             // the k* generator rides on `pre` too: it co-resides with the persistent contraction CTAs (64 registers per thread)
             if (tensor && kstar_overlap) TRY(tensor_kstar(ctx, b, xq_of(s), Mc, pre, multi && s > 0));
-            if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
+            if (multi || staged) CUDA_TRY(cudaEventRecord(ctx->ev_in[b], pre));
             return SLSGP_OK;
         };
 
@@ -1001,6 +1069,17 @@ namespace
             {
                 if (multi) CUDA_TRY(cudaStreamWaitEvent(post, ctx->ev_main[b], 0));
                 const size_t sv = sizeof(double) * (size_t) Mc, sg = sv * D;
+                if (staged)
+                {
+                    if (s >= 2) TRY(drain(s - 2)); // frees pinned slot b (the host is at most two shards behind the device)
+                    double*       slot = ctx->pin_out + (size_t) b * out_off[6];
+                    const double* src[6] = {o.mu, o.sigma, o.val, o.dmu, o.dsigma, o.grad};
+                    double* const outs[6] = {job.mu, job.sigma, job.val, job.dmu, job.dsigma, job.grad};
+                    for (int i = 0; i < 6; ++i)
+                        if (outs[i]) CUDA_TRY(cudaMemcpyAsync(slot + out_off[i], src[i], i < 3 ? sv : sg, cudaMemcpyDeviceToHost, post));
+                    CUDA_TRY(cudaEventRecord(ctx->ev_out[b], post));
+                    continue;
+                }
                 if (job.mu) CUDA_TRY(cudaMemcpyAsync(job.mu + m0, o.mu, sv, cudaMemcpyDeviceToHost, post));
                 if (job.sigma) CUDA_TRY(cudaMemcpyAsync(job.sigma + m0, o.sigma, sv, cudaMemcpyDeviceToHost, post));
                 if (job.val) CUDA_TRY(cudaMemcpyAsync(job.val + m0, o.val, sv, cudaMemcpyDeviceToHost, post));
@@ -1010,7 +1089,9 @@ namespace
                 if (multi) CUDA_TRY(cudaEventRecord(ctx->ev_out[b], post));
             }
         }
-        if (job.host_out && multi)
+        if (job.host_out && staged)
+            for (long long s = std::max<long long>(0, n_shards - 2); s < n_shards; ++s) TRY(drain(s));
+        if (job.host_out && (multi || staged))
             for (long long s = std::max<long long>(0, n_shards - 2); s < n_shards; ++s)
                 CUDA_TRY(cudaStreamWaitEvent(main, ctx->ev_out[s & 1], 0));
         if (refine_on) TRY(refine_listed(ctx, job, refine_cap));
@@ -1228,6 +1309,8 @@ extern "C"
             for (auto& r : kv.second) ctx->prof_free.push_back(r);
         for (auto& r : ctx->prof_free) cudaEventDestroy(r.start), cudaEventDestroy(r.stop);
         if (ctx->pinned) cudaFreeHost(ctx->pinned);
+        if (ctx->pin_in) cudaFreeHost(ctx->pin_in);
+        if (ctx->pin_out) cudaFreeHost(ctx->pin_out);
         for (int b = 0; b < 2; ++b)
         {
             if (ctx->ev_in[b]) cudaEventDestroy(ctx->ev_in[b]);
