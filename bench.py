@@ -505,19 +505,15 @@ def main_graft(args):
             hreg = host.gpr_create(KERNEL_SE, X, y, theta, NOISE)
             reg = host.gpr_regressor(hreg)
             Mp = 1 << 20
-            Qp = [np.asfortranarray(np.random.default_rng(5 + b).random((DIM, Mp))) for b in range(2)]
             pageable = {}
             for name, mode in (("fp64", pkg.SWEEP_FP64), ("tensor", pkg.SWEEP_TENSOR)):
                 host.regressor_set_sweep_mode(reg, mode)
                 reps = 2 if name == "fp64" else max(3, min(args.steps, 6))
-                host.acq_values(reg, ACQ_EI, 1.0, Qp[0][:, :65536])
-                t0 = time.perf_counter()
-                for r in range(reps):
-                    v_p, g_p = host.acq_values(reg, ACQ_EI, 1.0, Qp[r % 2])
-                dt = time.perf_counter() - t0
-                pageable[name] = {"value": reps * Mp / dt, "unit": UNIT, "candidates_per_call": Mp, "calls": reps,
-                                  "api": "acquisition_func::CalcAcquisitionValues(GaussianProcessRegressor, Eigen::MatrixXd) through libsls_b200_host.so; "
-                                         "pageable buffers, host wall clock, includes the facade's copies into and out of Eigen storage"}
+                sec = host.time_acq_values(reg, DIM, Mp, ACQ_EI, 1.0, reps)
+                pageable[name] = {"value": Mp / sec, "unit": UNIT, "candidates_per_call": Mp, "calls": reps,
+                                  "h2d_bytes_per_call": Mp * DIM * 8, "d2h_bytes_per_call": Mp * (DIM + 1) * 8,
+                                  "api": "acquisition_func::CalcAcquisitionValues(GaussianProcessRegressor, Eigen::MatrixXd, .., &gradients) of libsls_b200_host.so, "
+                                         "timed inside the C++ layer: pageable Eigen storage in and out, result allocations included"}
             host.regressor_set_sweep_mode(reg, pkg.SWEEP_FP64)
             host.gpr_destroy(hreg)
         except Exception as e:  # the host layer is optional for the metric; say why it is missing

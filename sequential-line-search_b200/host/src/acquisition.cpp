@@ -159,10 +159,16 @@ namespace sequential_line_search
                                        const double hyperparam, MatrixXd* derivatives)
         {
             const long M = Xq.cols();
-            VectorXd   val = VectorXd::Zero(M);
-            if (derivatives) *derivatives = MatrixXd::Zero(Xq.rows(), M);
-            if (regressor.GetSmallY().rows() == 0 || M == 0) return val;
+            if (regressor.GetSmallY().rows() == 0 || M == 0) // the reference's "no data" answers (:176-179, :206-209)
+            {
+                if (derivatives) *derivatives = MatrixXd::Zero(Xq.rows(), M);
+                return VectorXd::Zero(M);
+            }
             if (!regressor.HasModel()) throw std::logic_error("the regressor holds no model");
+            // results are written by the device path: no zero fill (136 MB of page touches per 2^20 candidates at D = 16), and a
+            // gradient matrix of the right shape handed in by the caller is reused as it is
+            VectorXd val(M);
+            if (derivatives) derivatives->resize(Xq.rows(), M);
             device_acq(regressor, Xq.data(), M, func_type, hyperparam, val.data(), derivatives ? derivatives->data() : nullptr);
             return val;
         }

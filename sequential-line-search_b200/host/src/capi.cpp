@@ -9,7 +9,9 @@
 
 #include "optimizer.hpp"
 
+#include <chrono>
 #include <cmath>
+#include <cstdint>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -385,6 +387,40 @@ extern "C"
             },
             1);
     }
+    // Seconds per call of acquisition_func::CalcAcquisitionValues (values + gradients for M candidates held in an Eigen matrix,
+    // results returned as Eigen objects: pageable memory both ways, allocations included - what a C++ caller of the drop-in pays),
+    // mean over `reps` calls after one warm-up call. The candidate matrix is built once, outside the timed region.
+    double b200_time_acq_values(const void* r, int D, int M, int acq, double ucb_beta, int reps)
+    {
+        return guarded(
+            [&]() {
+                const auto* d = dynamic_cast<const DeviceRegressor*>(static_cast<const Regressor*>(r));
+                if (!d) throw std::invalid_argument("not a device-backed regressor");
+                MatrixXd Xq = MatrixXd::Zero(D, M);
+                uint64_t state = 0x9E3779B97F4A7C15ull;
+                for (long i = 0; i < (long) D * M; ++i)
+                {
+                    state        = state * 6364136223846793005ull + 1442695040888963407ull;
+                    Xq.data()[i] = (double) (state >> 11) * (1.0 / 9007199254740992.0);
+                }
+                MatrixXd grads;
+                double   sink = 0.0;
+                {
+                    const VectorXd v = acquisition_func::CalcAcquisitionValues(*d, Xq, acq_type(acq), ucb_beta, &grads);
+                    sink += v(0);
+                }
+                const auto t0 = std::chrono::steady_clock::now();
+                for (int i = 0; i < reps; ++i)
+                {
+                    const VectorXd v = acquisition_func::CalcAcquisitionValues(*d, Xq, acq_type(acq), ucb_beta, &grads);
+                    sink += v(M - 1) + grads(0, 0);
+                }
+                const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                return sink == 12345.678 ? -1.0 : dt / reps;
+            },
+            kNaN);
+    }
+
     int b200_find_next_point(const void* r, int D, unsigned n_global, unsigned n_local, int acq, double ucb_beta, double* x_out)
     {
         return guarded(
