@@ -29,7 +29,7 @@ namespace slsgp
     // site, plus the branches of its slow path); this one is 17 FP64 instructions with the coefficients read straight from the
     // constant bank: n = rint(x log2 e) by the magic-number add, r = x - n ln 2 in two FMAs (Cody-Waite), a degree-13 Taylor
     // polynomial on |r| <= ln 2 / 2 (truncation 4e-18), 2^n through the exponent field. Results below 2^-1021 flush to zero.
-    // Accuracy ~1 ulp on [-707, 0]; the Gram-matrix parity tests hold K to 1e-13 of the oracle through it.
+    // Accuracy ~1 ulp on [-707, 0]; the Gram-matrix parity tests hold K to 1e-13 of the CPU checker through it.
     __constant__ double c_exp_poly[14] = {1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,
                                           1.0 / 40320.0,      1.0 / 5040.0,      1.0 / 720.0,      1.0 / 120.0,     1.0 / 24.0,
                                           1.0 / 6.0,          0.5,               1.0,              1.0};
