@@ -632,7 +632,7 @@ namespace
                               int n_parts = 0, double x_shift = 0.0, int ldp = 0, RefineList refine = RefineList{nullptr, nullptr, 0, 0, 0.0, 0})
     {
         ProfScope ps(ctx, "sweep_finish");
-        sweep_finish_kernel<<<(unsigned) ((Mc + 255) / 256), 256, 0, ctx->stream>>>(
+        sweep_finish_kernel<<<(unsigned) ((Mc + FINISH_CPB - 1) / FINISH_CPB), 256, 0, ctx->stream>>>(
             d_Xq, ctx->D, Mc, ptr<double4>(ctx->stats), dp(ctx->P1), dp(ctx->P2), ldp ? ldp : ctx->Dp, dp(ctx->theta), dp(ctx->fbest),
             acq_type, ucb_beta, out, n_parts, ctx->Mcap, ptr<double2>(ctx->tc_qx), dp(ctx->tc_P2x), x_shift, refine);
         LAUNCH_CHECK();
@@ -650,7 +650,14 @@ namespace
         __half*         Gs    = Ks + (size_t) 2 * ctx->tc_Mcap * ldt; // Matern only
         __half*         Gs_lo = passes > 1 ? Ks + (size_t) 3 * ctx->tc_Mcap * ldt : nullptr;
         ProfScope       ps(ctx, "tc_kstar", st);
-        static const bool tiled = std::getenv("SLSGP_KSTAR_V1") && std::atoi(std::getenv("SLSGP_KSTAR_V1")) != 0; // A/B: the first generator
+        // The strip form needs >= 4 strips of 64 candidates per SM to fill the machine (one strip per CTA at a time); below that
+        // (shards under ~38 thousand candidates: the last shard of a job, the starts of slsgp_acq_maximize, small batches) the
+        // tiled form has 16 times as many CTAs and is the faster one (9472 candidates, N = 2048: 39 vs 56 us; 18944: 71 vs 76 us).
+        // SLSGP_KSTAR_V1=1 / 0 forces the tiled / strip form (A/B).
+        static const int  tiled_env = std::getenv("SLSGP_KSTAR_V1") ? std::atoi(std::getenv("SLSGP_KSTAR_V1")) : -1;
+        int               n_sm_k    = 0;
+        CUDA_TRY(cudaDeviceGetAttribute(&n_sm_k, cudaDevAttrMultiProcessorCount, ctx->device));
+        const bool        tiled = tiled_env >= 0 ? tiled_env != 0 : (!under_gemm && Mpad / 64 < 4LL * n_sm_k);
         static bool       kstar_attr_dev[64] = {};
         bool&             kstar_attr = kstar_attr_dev[ctx->device & 63];
         if (!kstar_attr) // D > 62 needs more than the 48 KB a kernel gets without opting in
@@ -673,8 +680,7 @@ namespace
         }
         else
         {
-            int n_sm = 0;
-            CUDA_TRY(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->device));
+            const int    n_sm     = n_sm_k;
             const size_t smem     = sizeof(float) * (size_t) (64 * ((D + 3) & ~3) + 2 * D * 64);
             const int    n_strips = (int) (Mpad / 64);
             const int    grid     = std::min(n_strips, (under_gemm ? 1 : 4) * n_sm);
