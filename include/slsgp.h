@@ -113,6 +113,19 @@ extern "C"
      * Uploads X (D x N, column-major, host memory) and invalidates every derived quantity. */
     slsgp_status slsgp_set_data(slsgp_ctx* ctx, const double* X, int N, int D);
 
+    /* Incremental refit across iterations (the reference rebuilds everything per SubmitFeedbackData,
+     * src/sequential-line-search.cpp:91-103). Like slsgp_set_data, but when the context holds a factored model and the first p >= 1
+     * columns of X are, bit for bit, its first p data points (same D, N within the padded size of the model, at most 8 columns
+     * beyond them: SLSGP_EXTEND_MAX_NEW) the model of those p points is kept - the leading blocks of K_y, L and L^-1 - and grown
+     * by the remaining N - p columns with the bordered update of slsgp_append_point (O(N^2) per point) under the hyper-parameters
+     * of the last slsgp_gram. (The data manager of the reference appends new points and, when it merges two coincident ones,
+     * removes both and appends their midpoint: src/preference-data-manager.cpp:14-141; so p is usually the position of the point
+     * that was merged away.) slsgp_gram called again with the same hyper-parameters, slsgp_factor and slsgp_inverse then find
+     * their results current and only copy them out (they always do: a context never recomputes a matrix it already holds).
+     * y, alpha and the preference tuples are dropped.
+     * n_kept_out (may be NULL): p when the model was extended, 0 when it was replaced (plain slsgp_set_data). */
+    slsgp_status slsgp_set_data_extend(slsgp_ctx* ctx, const double* X, int N, int D, int* n_kept_out);
+
     /* Frees the per-shard sweep workspaces of the context when they hold more than keep_bytes (they only ever grow with the
      * largest batch seen); the fitted model stays. For hosts that pool contexts. */
     slsgp_status slsgp_trim(slsgp_ctx* ctx, size_t keep_bytes);

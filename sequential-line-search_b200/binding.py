@@ -36,6 +36,7 @@ _API = [
     ("slsgp_set_stream", C.c_int, [C.c_void_p, C.c_void_p]),
     ("slsgp_synchronize", C.c_int, [C.c_void_p]),
     ("slsgp_set_data", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
+    ("slsgp_set_data_extend", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
     ("slsgp_gram", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_double, c_dp]),
     ("slsgp_factor", C.c_int, [C.c_void_p, c_dp, c_dp]),
     ("slsgp_inverse", C.c_int, [C.c_void_p, c_dp]),
@@ -157,6 +158,14 @@ class Context:
         X = _f64(X)
         self.D, self.N = X.shape
         self._check(self.lib.slsgp_set_data(self.h, _p(X), self.N, self.D))
+
+    def set_data_extend(self, X):
+        """slsgp_set_data_extend: returns the number of leading data points whose model was kept (0 = replaced)."""
+        X = _f64(X)
+        self.D, self.N = X.shape
+        kept = C.c_int(0)
+        self._check(self.lib.slsgp_set_data_extend(self.h, _p(X), self.N, self.D, C.byref(kept)))
+        return kept.value
 
     def gram(self, kernel_type, theta, noise, want=True):
         theta = _f64(theta)

@@ -69,6 +69,7 @@ struct slsgp_ctx
     bool   has_data = false, has_gram = false, has_factor = false, has_W = false, has_inverse = false,
          has_alpha = false;
     std::vector<double> theta_host;
+    std::vector<double> X_host; // host mirror of X (D x N), for slsgp_set_data_extend's prefix comparison
 
     DevBuf X, Xpad, XT1, theta, inv_l, K, L, W, Kinv, T, y, alpha, Kalpha, vec, scalars, info, fbest, fbest_idx, chol_flags;
     DevBuf pref_off, pref_idx, slot_off, slot_list, loglik, contrib, grad_y, Ymat, g_l;
@@ -1467,8 +1468,80 @@ extern "C"
                                                                      dp(ctx->Xpad), dp(ctx->XT1));
         LAUNCH_CHECK();
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        ctx->X_host.assign(X, X + (size_t) N * D);
         ctx->has_data = true;
         return SLSGP_OK;
+    }
+
+    // rows / columns >= p of an ld x ld matrix back to the identity padding every dense kernel relies on
+    __global__ void truncate_to_identity_kernel(double* __restrict__ A, double* __restrict__ B, double* __restrict__ C, int p, int ld)
+    {
+        const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+        if (i >= ld || (i < p && j < p)) return;
+        const double v = i == j ? 1.0 : 0.0;
+        const size_t e = (size_t) i + (size_t) j * ld;
+        A[e] = v, B[e] = v, C[e] = v;
+    }
+
+    slsgp_status slsgp_set_data_extend(slsgp_ctx* ctx, const double* X, int N, int D, int* n_kept_out)
+    {
+        if (n_kept_out) *n_kept_out = 0;
+        if (!ctx) return SLSGP_ERR_INVALID;
+        if (!X || N <= 0 || D <= 0) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_set_data_extend: X null or N, D not positive");
+        const int N_old = ctx->N;
+        int       p     = 0; // leading data points shared, bit for bit, by the model and the new data
+        if (ctx->has_data && ctx->has_factor && D == ctx->D && N <= ctx->ld && ctx->X_host.size() == (size_t) N_old * D)
+            while (p < std::min(N, N_old) && std::memcmp(X + (size_t) p * D, ctx->X_host.data() + (size_t) p * D, sizeof(double) * (size_t) D) == 0) ++p;
+        // each appended point is one bordered update (a handful of small launches); beyond a few of them the rebuild is cheaper
+        static const int max_new = std::getenv("SLSGP_EXTEND_MAX_NEW") ? std::atoi(std::getenv("SLSGP_EXTEND_MAX_NEW")) : 8;
+        if (p == 0 || N - p > max_new) return slsgp_set_data(ctx, X, N, D);
+        CUDA_TRY(cudaSetDevice(ctx->device));
+        ctx->has_alpha = false; // the observations go: no alpha update per appended point
+        if (p < N_old)
+        {
+            // Points beyond the common prefix have changed (the data manager merges coincident points: both leave their columns and
+            // the midpoint is appended, src/preference-data-manager.cpp:14-86). The leading p x p blocks of K_y, L and L^-1 ARE the
+            // model of the first p points; K_y^-1 is rebuilt from L^-1 on demand.
+            const int ld = ctx->ld;
+            TRY(do_trtri(ctx));
+            truncate_to_identity_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(dp(ctx->K), dp(ctx->L), dp(ctx->W), p, ld);
+            LAUNCH_CHECK();
+            logdet_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->L), p, ld, dp(ctx->scalars) + 8);
+            LAUNCH_CHECK();
+            double logdet = 0.0;
+            CUDA_TRY(cudaMemcpyAsync(&logdet, dp(ctx->scalars) + 8, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+            ctx->logdet_host = logdet;
+            ctx->N           = p;
+            ctx->X_host.resize((size_t) p * D);
+            ctx->has_inverse = false, ctx->tc_ready = false;
+            ctx->P = 0, ctx->pref_total = 0;
+            if (p == N) // nothing to append: the packed copies of X still describe N_old points
+            {
+                pack_x_kernel<<<(ld + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), ctx->N, D, ld, ctx->Dp, ctx->ldx, dp(ctx->Xpad), dp(ctx->XT1));
+                LAUNCH_CHECK();
+            }
+        }
+        for (int i = p; i < N; ++i)
+        {
+            const slsgp_status s = slsgp_append_point(ctx, X + (size_t) i * D, 0.0, nullptr, nullptr);
+            if (s == SLSGP_ERR_NOT_SPD) return slsgp_set_data(ctx, X, N, D); // e.g. a duplicated point with zero noise: let the rebuild report it
+            if (s != SLSGP_OK) return s;
+        }
+        // as after slsgp_set_data: no observations
+        CUDA_TRY(cudaMemsetAsync(ctx->y.p, 0, sizeof(double) * (size_t) ctx->ld, ctx->stream));
+        ctx->has_alpha = false;
+        if (n_kept_out) *n_kept_out = p;
+        return SLSGP_OK;
+    }
+
+    // K_y depends on (X, kernel, theta, noise) only. X changes through slsgp_set_data (clears has_gram) or slsgp_append_point /
+    // slsgp_set_data_extend (which update K_y, L, L^-1 and K_y^-1 consistently), and every internal rebuild (the MAP objectives)
+    // records its hyper-parameters in the context, so a request for the matrix the context already holds is answered from it.
+    static bool gram_is_current(const slsgp_ctx* ctx, int kernel_type, const double* theta, double noise)
+    {
+        if (!ctx->has_gram || kernel_type != ctx->kernel_type || noise != ctx->noise || (int) ctx->theta_host.size() != ctx->D + 1) return false;
+        return std::memcmp(theta, ctx->theta_host.data(), sizeof(double) * (size_t) (ctx->D + 1)) == 0;
     }
 
     slsgp_status slsgp_gram(slsgp_ctx* ctx, slsgp_kernel_type kernel_type, const double* theta, double noise,
@@ -1477,7 +1550,7 @@ extern "C"
         if (!ctx) return SLSGP_ERR_INVALID;
         if (!theta) return fail(ctx, SLSGP_ERR_INVALID, "slsgp_gram: theta is null");
         CUDA_TRY(cudaSetDevice(ctx->device));
-        TRY(do_gram(ctx, (int) kernel_type, theta, noise));
+        if (!gram_is_current(ctx, (int) kernel_type, theta, noise)) TRY(do_gram(ctx, (int) kernel_type, theta, noise));
         return copy_matrix_out(ctx, ctx->K, K_out, ctx->N);
     }
 
@@ -1485,7 +1558,12 @@ extern "C"
     {
         if (!ctx) return SLSGP_ERR_INVALID;
         CUDA_TRY(cudaSetDevice(ctx->device));
-        TRY(do_factor(ctx, logdet_out));
+        if (ctx->has_gram && ctx->has_factor) // the factor of the current K_y (do_gram clears has_factor)
+        {
+            if (logdet_out) *logdet_out = ctx->logdet_host;
+        }
+        else
+            TRY(do_factor(ctx, logdet_out));
         return copy_matrix_out(ctx, ctx->L, L_out, ctx->N);
     }
 
@@ -1591,6 +1669,7 @@ extern "C"
             if (had_alpha) TRY(do_alpha(ctx));
             CUDA_TRY(cudaStreamSynchronize(ctx->stream)); // the pinned staging area is reused by later calls
         }
+        if (ctx->X_host.size() == (size_t) N * D) ctx->X_host.insert(ctx->X_host.end(), x, x + D); // (the rebuild path went through slsgp_set_data)
         if (K_col_out)
             CUDA_TRY(cudaMemcpyAsync(K_col_out, dp(ctx->K) + (size_t) (ctx->N - 1) * ctx->ld, sizeof(double) * (size_t) ctx->N,
                                      cudaMemcpyDeviceToHost, ctx->stream));

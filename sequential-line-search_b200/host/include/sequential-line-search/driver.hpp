@@ -36,6 +36,15 @@ namespace sequential_line_search
     void             SetDevices(const std::vector<int>& device_ids);
     std::vector<int> GetDevices();
 
+    // Incremental refit across iterations (addition). With fixed hyper-parameters (use_map_hyperparams ==
+    // false) the optimisers hand the device model of the previous regressor to the next one, which grows K, its Cholesky factor and
+    // K^-1 by the columns AddNewPoints appended (slsgp_set_data_extend: O(N^2) per new point) instead of rebuilding them. Off by
+    // default: at the sizes the optimisers reach (N <= 600) a from-scratch Gram + factor + inverse costs 0.25-0.6 ms of a 30-60 ms
+    // iteration, three bordered updates 0.33 ms (profiles/r02n_incremental_refit_study.txt), and the extended factor differs from a
+    // rebuilt one in the last bits. Initial value: environment variable SLS_B200_INCREMENTAL=1.
+    void SetIncrementalRefit(bool on);
+    bool GetIncrementalRefit();
+
     bool         IsNloptAvailable();                // was the library built with NLopt?
     void         SetSearchDriver(SearchDriver mode); // throws std::runtime_error for Hybrid / Reference without NLopt
     SearchDriver GetSearchDriver();

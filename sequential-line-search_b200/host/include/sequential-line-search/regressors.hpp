@@ -111,6 +111,10 @@ namespace sequential_line_search
                           Eigen::MatrixXd*       mu_derivative    = nullptr,
                           Eigen::MatrixXd*       sigma_derivative = nullptr) const;
 
+        // Gives this regressor's device context (and the model on it) away, for the incremental refit of the next iteration
+        // (MapWarmStart::device). The regressor stays valid: like a fresh copy it rebuilds its model if it is used again.
+        std::shared_ptr<slsgp_ctx> HandOverDevice();
+
         bool       HasModel() const { return m_fitted || m_refit_pending; }
         slsgp_ctx* Device() const; // the context holding this regressor's model (rebuilt first if this is a fresh copy)
         std::mutex& DeviceMutex() const { return *m_mutex; } // calls on one context are serialised
@@ -190,6 +194,9 @@ namespace sequential_line_search
         Eigen::VectorXd y;                    // N_prev
         Eigen::VectorXd kernel_hyperparams;   // D + 1 (used when hyper-parameters are estimated)
         double          noise_hyperparam = 0.0;
+        // the previous regressor's device context (DeviceRegressor::HandOverDevice), or null: with fixed hyper-parameters the
+        // new regressor adopts it and extends the factored model by the new data points (slsgp_set_data_extend)
+        std::shared_ptr<slsgp_ctx> device;
     };
 
     class PreferenceRegressor : public DeviceRegressor
@@ -239,10 +246,14 @@ namespace sequential_line_search
         double EvaluateMapObjective(const Eigen::VectorXd& x, Eigen::VectorXd* gradient) const;
         // Diagnostics of the last MAP run
         unsigned GetNumMapEvaluations() const { return m_num_map_evaluations; }
+        // Incremental refit: the number of leading data points whose factored model was taken over from the previous regressor
+        int GetNumPointsKept() const { return m_num_points_kept; }
 
     private:
         Eigen::VectorXd m_y;
         unsigned        m_num_map_evaluations = 0;
+
+        int             m_num_points_kept = 0;
 
         void PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start);
         void RefitOnDevice() override;

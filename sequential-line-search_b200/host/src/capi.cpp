@@ -198,6 +198,7 @@ extern "C"
             kNaN);
     }
     unsigned b200_pref_num_map_evaluations(void* hv) { return static_cast<PreferenceRegressor*>(hv)->GetNumMapEvaluations(); }
+    int      b200_pref_num_points_kept(void* hv) { return static_cast<PreferenceRegressor*>(hv)->GetNumPointsKept(); }
     void     b200_pref_get_state(void* hv, double* y, double* theta, double* b, double* K, double* L)
     {
         const PreferenceRegressor& r = *static_cast<PreferenceRegressor*>(hv);
@@ -303,6 +304,9 @@ extern "C"
     {
         return guarded([&]() { return SetSearchDriver(mode == 0 ? SearchDriver::Native : mode == 1 ? SearchDriver::Hybrid : SearchDriver::Reference), 0; }, 1);
     }
+
+    int b200_get_incremental_refit() { return GetIncrementalRefit() ? 1 : 0; }
+    int b200_set_incremental_refit(int on) { return SetIncrementalRefit(on != 0), 0; }
 
     int b200_set_devices(const int* ids, int n)
     {
@@ -448,4 +452,11 @@ extern "C"
         return value;               \
     }
 #include "loop_capi.inl"
+    // incremental refit diagnostics (no reference counterpart): how many data points of the optimiser's current regressor kept
+    // the factored model of the previous iteration
+    int b200_sls_num_points_kept(void* h)
+    {
+        const auto r = static_cast<b200_SlsHandle*>(h)->opt->GetRegressor();
+        return r ? r->GetNumPointsKept() : 0;
+    }
 }

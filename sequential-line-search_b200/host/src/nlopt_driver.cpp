@@ -42,6 +42,17 @@ namespace sequential_line_search
         }
     } // namespace
 
+    namespace
+    {
+        std::atomic<int>& incremental_state()
+        {
+            static std::atomic<int> state(std::getenv("SLS_B200_INCREMENTAL") && std::atoi(std::getenv("SLS_B200_INCREMENTAL")) != 0 ? 1 : 0);
+            return state;
+        }
+    } // namespace
+    void SetIncrementalRefit(bool on) { incremental_state().store(on ? 1 : 0); }
+    bool GetIncrementalRefit() { return incremental_state().load() != 0; }
+
     bool IsNloptAvailable()
     {
 #ifdef SLS_B200_USE_NLOPT

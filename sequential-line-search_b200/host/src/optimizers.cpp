@@ -130,6 +130,8 @@ namespace sequential_line_search
             if (disabled || !r || r->GetSmallY().size() == 0) return nullptr;
             std::unique_ptr<MapWarmStart> w(new MapWarmStart);
             w->X = r->GetLargeX(), w->y = r->GetSmallY(), w->kernel_hyperparams = r->GetKernelHyperparams(), w->noise_hyperparam = r->GetNoiseHyperparam();
+            // incremental refit (driver.hpp): the old regressor is about to be replaced; its factored model moves on
+            if (GetIncrementalRefit() && !r->m_use_map_hyperparams) w->device = r->HandOverDevice();
             return w;
         }
     } // namespace

@@ -197,6 +197,19 @@ namespace sequential_line_search
         return *this;
     }
 
+    std::shared_ptr<slsgp_ctx> DeviceRegressor::HandOverDevice()
+    {
+        std::shared_ptr<slsgp_ctx> device;
+        {
+            std::lock_guard<std::mutex> lock(*m_mutex);
+            device.swap(m_device);
+        }
+        m_refit_pending  = m_fitted || m_refit_pending;
+        m_fitted         = false;
+        m_data_on_device = false;
+        return device;
+    }
+
     slsgp_ctx* DeviceRegressor::Device() const
     {
         if (m_refit_pending)
@@ -536,6 +549,10 @@ namespace sequential_line_search
     // fit is the reference's own LD_TNEWTON run (branch below).
     void PreferenceRegressor::PerformMapEstimation(const unsigned num_iters, const MapWarmStart* warm_start)
     {
+        // incremental refit: with fixed hyper-parameters K_y only gains rows and columns, so the previous regressor's context is
+        // adopted and its factored model extended (below) instead of rebuilt
+        const bool adopt = !m_use_map_hyperparams && warm_start && warm_start->device && !m_device;
+        if (adopt) m_device = warm_start->device;
         EnsureDevice();
         const int  N = (int) m_X.cols(), D = (int) m_X.rows();
         slsgp_ctx* c = m_device.get();
@@ -544,7 +561,10 @@ namespace sequential_line_search
         std::vector<uint32_t> offsets, indices;
         tuples_to_csr(m_D, (unsigned) N, offsets, indices);
         std::lock_guard<std::mutex> lock(*m_mutex);
-        check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
+        if (adopt)
+            check(c, slsgp_set_data_extend(c, m_X.data(), N, D, &m_num_points_kept), "slsgp_set_data_extend");
+        else
+            check(c, slsgp_set_data(c, m_X.data(), N, D), "slsgp_set_data");
         m_data_on_device = true;
         check(c, slsgp_set_preferences(c, offsets.data(), indices.data(), (int) m_D.size()), "slsgp_set_preferences");
 #ifdef SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION

@@ -40,12 +40,25 @@ def main():
     # whole iterations with fixed hyper-parameters: one long loop, iteration time sampled where N crosses the sizes above
     b200 = LS.LoopLib("b200")
     log = LS.run_sls_loop(b200, D, 300, 1, kt=LS.SE, use_map=False, hyper=(0.5, 0.5, 0.001, 0.1, 0.01))
+    # the wired path (sequential_line_search::SetIncrementalRefit): the same loop again with the previous regressor's model handed on
+    pkg.hostlib.set_incremental_refit(True)
+    log_inc = LS.run_sls_loop(b200, D, 300, 1, kt=LS.SE, use_map=False, hyper=(0.5, 0.5, 0.001, 0.1, 0.01))
+    pkg.hostlib.set_incremental_refit(False)
     print(f"search driver: {pkg.hostlib.get_search_driver()} (0 native, 1 hybrid, 2 reference); D = {D}, SE kernel, fixed hyper-parameters")
     print(f"{'N':>5s} {'3 x append_point ms':>20s} {'model rebuild ms':>18s} {'saving ms':>10s} {'SubmitFeedbackData ms':>22s} {'saving / iteration':>19s}")
     for N, (a, f) in rows.items():
         near = [r["ms"] for r in log if abs(r["n_points"] - N) <= 6]
         it = float(np.median(near)) if near else float("nan")
         print(f"{N:5d} {a:20.3f} {f:18.3f} {f - a:10.3f} {it:22.2f} {100 * (f - a) / it if near else float('nan'):18.1f}%")
+    print("\nwired: SequentialLineSearchOptimizer loop of 300 iterations, rebuild per iteration vs SetIncrementalRefit(true) (same seed and user)")
+    print(f"{'N':>5s} {'rebuild ms / iteration':>24s} {'incremental ms / iteration':>28s}")
+    for N in rows:
+        a = [r["ms"] for r in log if abs(r["n_points"] - N) <= 10]
+        b = [r["ms"] for r in log_inc if abs(r["n_points"] - N) <= 10]
+        if a and b:
+            print(f"{N:5d} {np.median(a):24.2f} {np.median(b):28.2f}")
+    print(f"whole loop: {sum(r['ms'] for r in log) / 1e3:.2f} s rebuilding, {sum(r['ms'] for r in log_inc) / 1e3:.2f} s incremental; "
+          f"final objective {log[-1]['objective']:.4f} / {log_inc[-1]['objective']:.4f}")
 
 
 if __name__ == "__main__":
