@@ -2038,7 +2038,7 @@ extern "C"
             job.val = dp(ctx->mx_val), job.grad = dp(ctx->mx_grad);
             st = run_sweep(ctx, job);
             if (st != SLSGP_OK) break;
-            ascent_update_kernel<<<(K + 127) / 128, 128, 0, ctx->stream>>>(K, D, dp(ctx->mx_val), dp(ctx->mx_grad), dp(ctx->mx_X),
+            ascent_update_kernel<<<(K + 3) / 4, 128, 0, ctx->stream>>>(K, D, dp(ctx->mx_val), dp(ctx->mx_grad), dp(ctx->mx_X),
                                                                           dp(ctx->mx_Xbest), dp(ctx->mx_Gbest),
                                                                           ptr<AscentState>(ctx->mx_state), 1.6, 0.35, 0.25);
             ++ctx->launches;

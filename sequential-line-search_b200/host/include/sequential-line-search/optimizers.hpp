@@ -93,8 +93,15 @@ namespace sequential_line_search
 
         // addition: the regressor of the last Submit (null before the first), for batched queries on the device
         std::shared_ptr<const PreferenceRegressor> GetRegressor() const { return m_regressor; }
+        // addition: where the last SubmitFeedbackData spent its time, in milliseconds of host wall clock
+        struct StepTimings
+        {
+            double map_fit = 0.0, search = 0.0, slider = 0.0;
+        };
+        StepTimings GetLastStepTimings() const { return m_last_timings; }
 
     private:
+        StepTimings                            m_last_timings;
         const bool                             m_use_slider_enlargement;
         const bool                             m_use_map_hyperparams;
         const CurrentBestSelectionStrategy     m_current_best_selection_strategy;

@@ -454,6 +454,14 @@ extern "C"
 #include "loop_capi.inl"
     // incremental refit diagnostics (no reference counterpart): how many data points of the optimiser's current regressor kept
     // the factored model of the previous iteration
+    // out: map_fit, search, slider (ms of the last SubmitFeedbackData) and the number of MAP objective evaluations
+    void b200_sls_last_step_timings(void* h, double* out)
+    {
+        const auto& o = *static_cast<b200_SlsHandle*>(h)->opt;
+        const auto  t = o.GetLastStepTimings();
+        const auto  r = o.GetRegressor();
+        out[0] = t.map_fit, out[1] = t.search, out[2] = t.slider, out[3] = r ? (double) r->GetNumMapEvaluations() : 0.0;
+    }
     int b200_sls_num_points_kept(void* h)
     {
         const auto r = static_cast<b200_SlsHandle*>(h)->opt->GetRegressor();

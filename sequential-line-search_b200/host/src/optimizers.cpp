@@ -7,6 +7,7 @@
 #include <sequential-line-search/optimizers.hpp>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 
@@ -222,16 +223,24 @@ namespace sequential_line_search
         const VectorXd x_chosen = CalcPointFromSliderPosition(slider_position);
         m_data->AddNewPoints(x_chosen, {m_slider->original_end_0, m_slider->original_end_1}, true);
 
+        const auto now = [] { return std::chrono::steady_clock::now(); };
+        const auto ms  = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+            return std::chrono::duration<double, std::milli>(b - a).count();
+        };
+        const auto t0 = now();
         const std::unique_ptr<MapWarmStart> warm = warm_start_of(m_regressor);
         m_regressor = std::make_shared<PreferenceRegressor>(m_data->GetX(), m_data->GetD(), m_use_map_hyperparams, m_kernel_signal_var,
                                                             m_kernel_length_scale, m_noise_level, m_kernel_hyperparams_prior_var, m_btl_scale,
                                                             (unsigned) num_map_estimation_iters, m_kernel_type, warm.get());
+        const auto t1 = now();
 
         const VectorXd x_plus = m_current_best_selection_strategy == CurrentBestSelectionStrategy::LargestExpectValue ? m_regressor->FindArgMax() : x_chosen;
         const VectorXd x_acquisition =
             acquisition_func::FindNextPoint(*m_regressor, (unsigned) num_global_search_iters, (unsigned) num_local_search_iters, m_acquisition_func_type,
                                             m_gaussian_process_upper_confidence_bound_hyperparam);
+        const auto t2 = now();
         m_slider = std::make_shared<Slider>(x_plus, x_acquisition, m_use_slider_enlargement);
+        m_last_timings.map_fit = ms(t0, t1), m_last_timings.search = ms(t1, t2), m_last_timings.slider = ms(t2, now());
     }
 
     std::pair<VectorXd, VectorXd> SequentialLineSearchOptimizer::GetSliderEnds() const { return {m_slider->end_0, m_slider->end_1}; }
