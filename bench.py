@@ -357,6 +357,7 @@ def main_graft(args):
 
     def fit():
         """What a regressor constructor does after its MAP fit (src/preference-regressor.cpp:289-290 + the cached quantities)."""
+        ctx.invalidate()  # a context does not recompute matrices it holds: every timed fit starts from the data alone
         ctx.gram(KERNEL_SE, theta, NOISE, want=False)
         ctx.factor()
         ctx.inverse(want=False)
@@ -645,6 +646,7 @@ def extra_configs(pkg, ctx, torch):
     ctx.set_data(X2)
 
     def fit2():
+        ctx.invalidate()
         ctx.gram(KERNEL_SE, th2, NOISE, want=False)
         ctx.factor()
         ctx.inverse(want=False)
@@ -719,6 +721,7 @@ def extra_configs(pkg, ctx, torch):
         ctx.set_data(Xg)
         yg = synth.make_y(Xg, seed=3)
         for _ in range(3):
+            ctx.invalidate()
             ctx.gram(KERNEL_SE, thg, NOISE, want=False)
             ctx.factor()
             ctx.inverse(want=False)

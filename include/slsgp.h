@@ -126,6 +126,11 @@ extern "C"
      * n_kept_out (may be NULL): p when the model was extended, 0 when it was replaced (plain slsgp_set_data). */
     slsgp_status slsgp_set_data_extend(slsgp_ctx* ctx, const double* X, int N, int D, int* n_kept_out);
 
+    /* Forgets every matrix derived from the data (K_y, its factor, the inverses, alpha) so that the next slsgp_gram / slsgp_factor
+     * / slsgp_inverse recompute them even for unchanged hyper-parameters; the data stay. For benchmarks that time the model build
+     * repeatedly: a context otherwise never recomputes a matrix it already holds (see slsgp_set_data_extend). */
+    slsgp_status slsgp_invalidate(slsgp_ctx* ctx);
+
     /* Frees the per-shard sweep workspaces of the context when they hold more than keep_bytes (they only ever grow with the
      * largest batch seen); the fitted model stays. For hosts that pool contexts. */
     slsgp_status slsgp_trim(slsgp_ctx* ctx, size_t keep_bytes);

@@ -37,6 +37,7 @@ _API = [
     ("slsgp_synchronize", C.c_int, [C.c_void_p]),
     ("slsgp_set_data", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int]),
     ("slsgp_set_data_extend", C.c_int, [C.c_void_p, c_dp, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    ("slsgp_invalidate", C.c_int, [C.c_void_p]),
     ("slsgp_gram", C.c_int, [C.c_void_p, C.c_int, c_dp, C.c_double, c_dp]),
     ("slsgp_factor", C.c_int, [C.c_void_p, c_dp, c_dp]),
     ("slsgp_inverse", C.c_int, [C.c_void_p, c_dp]),
@@ -166,6 +167,10 @@ class Context:
         kept = C.c_int(0)
         self._check(self.lib.slsgp_set_data_extend(self.h, _p(X), self.N, self.D, C.byref(kept)))
         return kept.value
+
+    def invalidate(self):
+        """slsgp_invalidate: the next gram / factor / inverse recompute even for unchanged hyper-parameters (timing loops)."""
+        self._check(self.lib.slsgp_invalidate(self.h))
 
     def gram(self, kernel_type, theta, noise, want=True):
         theta = _f64(theta)

@@ -1483,6 +1483,14 @@ extern "C"
         A[e] = v, B[e] = v, C[e] = v;
     }
 
+    slsgp_status slsgp_invalidate(slsgp_ctx* ctx)
+    {
+        if (!ctx) return SLSGP_ERR_INVALID;
+        ctx->has_gram = ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        ctx->tc_ready = false;
+        return SLSGP_OK;
+    }
+
     slsgp_status slsgp_set_data_extend(slsgp_ctx* ctx, const double* X, int N, int D, int* n_kept_out)
     {
         if (n_kept_out) *n_kept_out = 0;

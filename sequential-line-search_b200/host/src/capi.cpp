@@ -462,6 +462,29 @@ extern "C"
         const auto  r = o.GetRegressor();
         out[0] = t.map_fit, out[1] = t.search, out[2] = t.slider, out[3] = r ? (double) r->GetNumMapEvaluations() : 0.0;
     }
+    // The optimiser's current regressor against a deep copy of it (a copy rebuilds its device model from scratch out of X, y and the
+    // hyper-parameters): largest difference of mu, sigma and their gradients over the M query points (D x M). With the incremental
+    // refit the left side is an EXTENDED model, the right side a rebuilt one of the same data and the same goodness values.
+    double b200_sls_model_vs_rebuilt_copy(void* h, int D, int M, const double* Xq)
+    {
+        return guarded(
+            [&]() {
+                const auto r = static_cast<b200_SlsHandle*>(h)->opt->GetRegressor();
+                if (!r) return -1.0;
+                const PreferenceRegressor copy(*r);
+                double                    worst = 0.0;
+                for (int m = 0; m < M; ++m)
+                {
+                    const VectorXd x = vector(Xq + (size_t) m * D, D);
+                    worst            = std::max(worst, std::abs(r->PredictMu(x) - copy.PredictMu(x)));
+                    worst            = std::max(worst, std::abs(r->PredictSigma(x) - copy.PredictSigma(x)));
+                    const VectorXd dm = r->PredictMuDerivative(x) - copy.PredictMuDerivative(x), ds = r->PredictSigmaDerivative(x) - copy.PredictSigmaDerivative(x);
+                    for (int d = 0; d < D; ++d) worst = std::max(worst, std::max(std::abs(dm(d)), std::abs(ds(d))));
+                }
+                return worst;
+            },
+            kNaN);
+    }
     int b200_sls_num_points_kept(void* h)
     {
         const auto r = static_cast<b200_SlsHandle*>(h)->opt->GetRegressor();

@@ -15,7 +15,7 @@ c_dp = C.POINTER(C.c_double)
 c_up = C.POINTER(C.c_uint)
 _lib = None
 
-_DOUBLE = ("b200_time_acq_values", "b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value", "b200_utils_btl")
+_DOUBLE = ("b200_sls_model_vs_rebuilt_copy", "b200_time_acq_values", "b200_pref_objective", "b200_predict_mu", "b200_predict_sigma", "b200_acq_value", "b200_utils_btl")
 _POINTER = ("b200_gpr_copy", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_regressor", "b200_pref_create", "b200_pref_create_warm", "b200_pref_regressor")
 HOST_SYMBOLS = [
     "b200_last_error", "b200_kernel", "b200_calc_large_ky", "b200_gpr_create", "b200_gpr_create_map", "b200_gpr_destroy", "b200_gpr_append_point",
@@ -27,7 +27,7 @@ HOST_SYMBOLS = [
     "b200_utils_btl", "b200_utils_random_vector", "b200_utils_export_csv",
     "b200_nlopt_available", "b200_get_search_driver", "b200_set_search_driver", "b200_calc_small_k", "b200_calc_large_ky_theta_derivative",
     "b200_release_device_resources", "b200_gpr_copy", "b200_gpr_num_points", "b200_regressor_set_sweep_mode", "b200_set_devices", "b200_get_device_count", "b200_time_acq_values",
-    "b200_get_incremental_refit", "b200_set_incremental_refit", "b200_pref_num_points_kept", "b200_sls_num_points_kept", "b200_sls_last_step_timings",
+    "b200_get_incremental_refit", "b200_set_incremental_refit", "b200_pref_num_points_kept", "b200_sls_num_points_kept", "b200_sls_last_step_timings", "b200_sls_model_vs_rebuilt_copy",
 ] + ["b200_" + n for n in (
     # host/src/loop_capi.inl: optimiser front-ends and driver-dependent entry points (bound by tests/loop_support.py)
     "srand sls_create sls_destroy sls_set_hyperparams sls_set_ucb_hyperparam sls_submit sls_get_slider_ends sls_get_maximizer sls_calc_point "

@@ -38,7 +38,7 @@ def main():
         ms = timed(lambda: torch.matmul(A, B, out=C), reps=5 if n == 8192 else 20)
         print(f"cuBLAS DGEMM n={n}: {ms:8.3f} ms  {2.0 * n ** 3 / ms / 1e9:7.2f} TFLOP/s")
     ctx = pkg.Context(0)
-    for n in (2048, 8192):
+    for n in (512, 2048, 4096, 8192):
         X, theta = synth.make_X(n, 16, "uniform"), synth.make_theta(16, "default")
         ctx.set_data(X)
         K = torch.from_numpy(np.ascontiguousarray(ctx.gram(0, theta, 0.005))).to(dev)
@@ -47,6 +47,7 @@ def main():
         ms_potri = timed(lambda: torch.cholesky_inverse(L), reps=5)
         ours = {}
         for _ in range(3):
+            ctx.invalidate()
             ctx.gram(0, theta, 0.005, want=False)
             ctx.factor()
             ctx.lib.slsgp_inverse(ctx.h, None)

@@ -29,6 +29,7 @@ def main():
             ctx.set_data(X)
             t = []
             for it in range(25):
+                ctx.invalidate()
                 ctx.gram(args.kernel, theta, 0.005, want=False)
                 if it >= 5:
                     t.append(ctx.phase_ms("gram"))

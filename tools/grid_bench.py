@@ -55,6 +55,7 @@ for N in Ns:
         for kt in (0, 1):
             ctx.fit(X, kt, theta, 0.005, y)
             for it in range(3):
+                ctx.invalidate()
                 ctx.gram(kt, theta, 0.005, want=False)
                 ctx.factor()
                 ctx.inverse(want=False)

@@ -19,6 +19,7 @@ X, theta = S.make_X(N, D, "uniform"), S.make_theta(D, "default")
 y = S.make_y(X)
 ctx.set_data(X)
 for it in range(3):
+    ctx.invalidate()
     ctx.gram(0, theta, 0.005, want=False)
     ctx.factor()
     ctx.inverse(want=False)
