@@ -571,7 +571,7 @@ def main_graft(args):
         rooflines = {}
         if gram_n:
             ach = gram_bytes / (gram_ms / gram_n * 1e-3) / 1e9
-            rooflines["gram"] = {"bound": "hbm", "kernel": "gram_tile_kernel<0>", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            rooflines["gram"] = {"bound": "hbm", "kernel": "gram_sym_kernel<0> (lower 64 x 64 tiles, mirrored through shared memory)", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                  "frac": ach / peaks["hbm_gbs"], "algorithmic_bytes_per_launch": gram_bytes, "avg_launch_ms": gram_ms / gram_n,
                                  "launches_timed": gram_n, "peak_source": peak_src,
                                  "traffic": traffic_from_capture("gram_tile_kernel", {"n_obs": N_OBS, "dim": DIM})[0]}
