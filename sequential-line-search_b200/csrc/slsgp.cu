@@ -19,6 +19,7 @@
 #include "small.cuh"
 #include "maximize.cuh"
 #include "tc_sweep.cuh"
+#include "tc_kstar.cuh"
 #include "l1.cuh"
 
 #include <algorithm>
@@ -83,6 +84,11 @@ struct slsgp_ctx
     DevBuf      Bmat, Xt, Xs32, tcs, Ks, tc_err, comb, tc_qx, tc_P2x;
     DevBuf      mx_best, mx_X, mx_Xbest, mx_Gbest, mx_state, mx_val, mx_grad; // slsgp_acq_maximize
     CUtensorMap tmA, tmB;
+    // k* generator on the tensor pipe (tc_kstar.cuh): split-fp16 coordinates of the observations (per model) and of the candidates
+    // (per shard buffer), their squared norms, the TMA descriptors; kt_KP = 0 when D is too large for it (3 D > 128)
+    DevBuf      kt_Xh, kt_nx, kt_Qh, kt_nq;
+    CUtensorMap tmXh, tmQh;
+    int         kt_KP = 0;
     int         ldt = 0, XP = 0;
     bool        tc_ready = false; // Bmat / Xt / Xs32 / scales match the current model
     long long   tc_Mcap = 0;      // rows of Ks (multiple of 128 * tc_ncta)
@@ -469,6 +475,12 @@ namespace
             // passes), [2 cap, 3 cap) / [3 cap, 4 cap) the Matern gradient weight g16 and its residual
             TRY(ensure(ctx, ctx->Ks, sizeof(__half) * 8 * (size_t) cap * ctx->ldt));
             TRY(tensor_map_2d(ctx, &ctx->tmA, ctx->Ks.p, 8 * (uint64_t) cap, (uint64_t) ctx->ldt, TC_BM));
+            if (ctx->kt_KP)
+            {
+                TRY(ensure(ctx, ctx->kt_Qh, sizeof(__half) * 2 * (size_t) cap * ctx->kt_KP));
+                TRY(ensure(ctx, ctx->kt_nq, sizeof(float) * 2 * (size_t) cap));
+                TRY(tensor_map_2d(ctx, &ctx->tmQh, ctx->kt_Qh.p, 2 * (uint64_t) cap, (uint64_t) ctx->kt_KP, KT_BM));
+            }
             ctx->tc_Mcap = cap;
         }
         if (ctx->Mcap >= cap) return SLSGP_OK;
@@ -574,6 +586,19 @@ namespace
                                                                     ptr<float>(ctx->Xt), ptr<float>(ctx->Xs32));
         LAUNCH_CHECK();
         TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN / ctx->tc_ncta));
+        // operands of the tensor-pipe k* generator (tc_kstar.cuh): up to two 64-wide K slices, i.e. D <= 42
+        const int KP = kt_kp(ctx->D);
+        if (KP != ctx->kt_KP) ctx->tc_Mcap = 0; // the per-shard candidate operand has another width
+        ctx->kt_KP = KP <= 128 ? KP : 0;
+        if (ctx->kt_KP)
+        {
+            TRY(ensure(ctx, ctx->kt_Xh, sizeof(__half) * (size_t) ldt * KP));
+            TRY(ensure(ctx, ctx->kt_nx, sizeof(float) * (size_t) ldt));
+            tc_pack_xh_kernel<<<(ldt + 127) / 128, 128, 0, ctx->stream>>>(dp(ctx->X), ctx->N, ctx->D, ldt, KP, dp(ctx->inv_l), ptr<__half>(ctx->kt_Xh),
+                                                                         ptr<float>(ctx->kt_nx));
+            LAUNCH_CHECK();
+            TRY(tensor_map_2d(ctx, &ctx->tmXh, ctx->kt_Xh.p, (uint64_t) ldt, (uint64_t) KP, KT_BN));
+        }
         ctx->tc_ready = true;
         return SLSGP_OK;
     }
@@ -669,6 +694,49 @@ namespace
             CUDA_TRY(cudaFuncSetAttribute(kstar16_strip_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             CUDA_TRY(cudaFuncSetAttribute(kstar16_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             kstar_attr = true;
+        }
+        // Squared distances on the tensor pipe (tc_kstar.cuh) for D <= 42 when the generator has the GPU to itself (it allocates all of
+        // an SM's TMEM, as the contraction kernel does); SLSGP_KSTAR_TC=0 selects the FP32-pipe generators below (A/B).
+        static const int tc_env = std::getenv("SLSGP_KSTAR_TC") ? std::atoi(std::getenv("SLSGP_KSTAR_TC")) : 1;
+        if (tc_env != 0 && tiled_env < 0 && ctx->kt_KP && !under_gemm)
+        {
+            const int       KP = ctx->kt_KP, KS = KP / TC_BK;
+            const long long Mp128 = Mpad; // every row the contraction reads (a multiple of 128 or, for the CTA pair, 256)
+            __half*         Qh = ptr<__half>(ctx->kt_Qh) + (size_t) buf * ctx->tc_Mcap * KP;
+            float*          nq = ptr<float>(ctx->kt_nq) + (size_t) buf * ctx->tc_Mcap;
+            tc_pack_qh_kernel<<<(unsigned) ((Mp128 + 127) / 128), 128, 0, st>>>(d_Xq, Mc, Mp128, D, KP, dp(ctx->inv_l), Qh, nq);
+            LAUNCH_CHECK();
+            KstarTcParams prm;
+            prm.ldt = ldt, prm.ncb = ldt / KT_BN, prm.n_strips = (int) (Mp128 / KT_BM), prm.q_row0 = (int) ((long long) buf * ctx->tc_Mcap);
+            prm.stages = KS == 1 ? 3 : 1;
+            prm.nq = nq, prm.nx = ptr<float>(ctx->kt_nx), prm.sc = ptr<TcScales>(ctx->tcs);
+            prm.Ks = Ks, prm.Ks_lo = Ks_lo, prm.Gs = Gs, prm.Gs_lo = Gs_lo, prm.err = ptr<int>(ctx->tc_err);
+            const size_t smem = (size_t) prm.stages * KS * (KT_A_BYTES + KT_B_BYTES) + 1024 + KT_EPI_WARPS * 32 * 64 + KT_NX_SMEM * sizeof(float); // stages, alignment, transposing buffers, |x|^2
+            const int    grid = std::min(prm.n_strips * prm.ncb, n_sm_k);
+            static bool  kt_attr_dev[64] = {};
+            bool&        kt_attr = kt_attr_dev[ctx->device & 63];
+            if (!kt_attr)
+            {
+                const int big = 3 * (KT_A_BYTES + KT_B_BYTES) + 1024 + KT_EPI_WARPS * 32 * 64 + KT_NX_SMEM * (int) sizeof(float);
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                kt_attr = true;
+            }
+            if (ctx->kernel_type == 0)
+            {
+                if (KS == 1)
+                    kstar_tc_kernel<0, 1><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+                else
+                    kstar_tc_kernel<0, 2><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+            }
+            else if (KS == 1)
+                kstar_tc_kernel<1, 1><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+            else
+                kstar_tc_kernel<1, 2><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+            LAUNCH_CHECK();
+            return SLSGP_OK;
         }
         if (tiled)
         {
