@@ -933,6 +933,9 @@ namespace
             CUDA_TRY(cudaStreamSynchronize(main));
         }
         double*  base = dp(ctx->rf_out);
+        // the chunk results travel to the host as one block of Rc-sized arrays: entries past the chunk's count (and arrays the job
+        // does not ask for) are never written by the sweep, so give them a defined value
+        CUDA_TRY(cudaMemsetAsync(base, 0, sizeof(double) * (size_t) (3 + 3 * D) * Rc, main));
         SweepOut ro;
         ro.mu = base, ro.sigma = base + Rc, ro.val = base + 2 * (size_t) Rc;
         ro.dmu = base + 3 * (size_t) Rc, ro.dsigma = ro.dmu + (size_t) D * Rc, ro.grad = ro.dsigma + (size_t) D * Rc;
