@@ -586,10 +586,10 @@ namespace
                                                                     ptr<float>(ctx->Xt), ptr<float>(ctx->Xs32));
         LAUNCH_CHECK();
         TRY(tensor_map_2d(ctx, &ctx->tmB, ctx->Bmat.p, brows, (uint64_t) ldt, TC_BN / ctx->tc_ncta));
-        // operands of the tensor-pipe k* generator (tc_kstar.cuh): up to two 64-wide K slices, i.e. D <= 42
+        // operands of the tensor-pipe k* generator (tc_kstar.cuh): up to three 64-wide K slices, i.e. D <= 64
         const int KP = kt_kp(ctx->D);
         if (KP != ctx->kt_KP) ctx->tc_Mcap = 0; // the per-shard candidate operand has another width
-        ctx->kt_KP = KP <= 128 ? KP : 0;
+        ctx->kt_KP = KP <= 192 ? KP : 0;
         if (ctx->kt_KP)
         {
             TRY(ensure(ctx, ctx->kt_Xh, sizeof(__half) * (size_t) ldt * KP));
@@ -695,7 +695,7 @@ namespace
             CUDA_TRY(cudaFuncSetAttribute(kstar16_strip_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
             kstar_attr = true;
         }
-        // Squared distances on the tensor pipe (tc_kstar.cuh) for D <= 42 when the generator has the GPU to itself (it allocates all of
+        // Squared distances on the tensor pipe (tc_kstar.cuh) for D <= 64 when the generator has the GPU to itself (it allocates all of
         // an SM's TMEM, as the contraction kernel does); SLSGP_KSTAR_TC=0 selects the FP32-pipe generators below (A/B).
         static const int tc_env = std::getenv("SLSGP_KSTAR_TC") ? std::atoi(std::getenv("SLSGP_KSTAR_TC")) : 1;
         if (tc_env != 0 && tiled_env < 0 && ctx->kt_KP && !under_gemm)
@@ -708,7 +708,7 @@ namespace
             LAUNCH_CHECK();
             KstarTcParams prm;
             prm.ldt = ldt, prm.ncb = ldt / KT_BN, prm.n_strips = (int) (Mp128 / KT_BM), prm.q_row0 = (int) ((long long) buf * ctx->tc_Mcap);
-            prm.stages = KS == 1 ? 3 : 1;
+            prm.stages = KS == 1 ? 3 : 1; // 144 KB of operand tiles either way (KS = 2: 96 KB)
             prm.nq = nq, prm.nx = ptr<float>(ctx->kt_nx), prm.sc = ptr<TcScales>(ctx->tcs);
             prm.Ks = Ks, prm.Ks_lo = Ks_lo, prm.Gs = Gs, prm.Gs_lo = Gs_lo, prm.err = ptr<int>(ctx->tc_err);
             const size_t smem = (size_t) prm.stages * KS * (KT_A_BYTES + KT_B_BYTES) + 1024 + KT_EPI_WARPS * 32 * 64 + KT_NX_SMEM * sizeof(float); // stages, alignment, transposing buffers, |x|^2
@@ -722,19 +722,25 @@ namespace
                 CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<0, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
+                CUDA_TRY(cudaFuncSetAttribute(kstar_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
                 kt_attr = true;
             }
             if (ctx->kernel_type == 0)
             {
                 if (KS == 1)
                     kstar_tc_kernel<0, 1><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
-                else
+                else if (KS == 2)
                     kstar_tc_kernel<0, 2><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+                else
+                    kstar_tc_kernel<0, 3><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
             }
             else if (KS == 1)
                 kstar_tc_kernel<1, 1><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
-            else
+            else if (KS == 2)
                 kstar_tc_kernel<1, 2><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
+            else
+                kstar_tc_kernel<1, 3><<<grid, KT_THREADS, smem, st>>>(ctx->tmQh, ctx->tmXh, prm);
             LAUNCH_CHECK();
             return SLSGP_OK;
         }

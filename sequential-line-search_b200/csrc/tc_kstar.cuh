@@ -4,7 +4,7 @@
 // 38 issue slots per kernel value at D = 16, 19 % of a sweep step. Here
 //     r2 = |q|^2 + |x|^2 - 2 q.x
 // and the N x M x D contraction q.x runs as a split-fp16 UMMA (q = q_hi + q_lo, x = x_hi + x_lo, fp32 accumulation in TMEM):
-//     Qh[m] = [q_hi | q_hi | q_lo | 0],  Xh[j] = [x_hi | x_lo | x_hi | 0]   (K = 3 D padded to 64 or 128)
+//     Qh[m] = [q_hi | q_hi | q_lo | 0],  Xh[j] = [x_hi | x_lo | x_hi | 0]   (K = 3 D padded to 64, 128 or 192: D <= 64)
 // so that one 128 x 256 x 64 UMMA group per tile yields q_hi.x_hi + q_hi.x_lo + q_lo.x_hi (the dropped q_lo.x_lo term is 2^-22
 // relative): 3 D / N of the contraction work of the sweep itself (2 % at N = 2048). What is left per kernel value is the
 // epilogue: one TMEM column, two FMAs, ex2, the fp16 hi / residual split and the stores - about 8 issue slots.
