@@ -101,7 +101,10 @@ extern "C"
      * variance came out below tau * a (a = signal variance; these sit next to data points, where sigma^2 = a - k K^-1 k and the
      * sums behind grad sigma cancel and the fp16 / fp32 round-off is amplified by a / sigma^2) are re-evaluated through the
      * IEEE-double sweep and overwritten. tau in [0, 1]; 0 switches the second tier off; default 0.1 (environment variable
-     * SLSGP_REFINE_TAU). Costs one host synchronisation per call and nothing else when no candidate qualifies. */
+     * SLSGP_REFINE_TAU). Costs one host synchronisation per call and nothing else when no candidate qualifies. When more than half
+     * of a batch (>= 8192 candidates) qualifies - dense data: thousands of observations in a handful of dimensions, where
+     * sigma^2 << a almost everywhere - the context remembers it for that model and sweeps later batches in IEEE double directly
+     * (the tensor pass would be wasted work); the next model change resets this. */
     slsgp_status slsgp_set_refine_threshold(slsgp_ctx* ctx, double tau);
     /* Use a caller-owned CUDA stream (a cudaStream_t passed as void*) instead of the context's own; NULL restores
      * the context's stream. Lets a host framework order libslsgp work with its own copies and events. */

@@ -78,6 +78,7 @@ struct slsgp_ctx
     DevBuf Xq, Kstar, Gstar, Beta, P1, P2, stats, o_mu, o_sigma, o_dmu, o_dsigma, o_val, o_grad, am_part, am_acc;
     DevBuf rf_count, rf_index, rf_X, rf_out; // two-tier precision of the tensor sweep (RefineList)
     double refine_tau = 0.1;                // candidates with sigma^2 < tau * a are re-evaluated in IEEE double; 0 = off
+    uint64_t dense_version = ~0ull;         // model_version for which most candidates needed the second tier: swept in IEEE double directly
     long long Mcap = 0;
 
     // tensor-core sweep (SLSGP_SWEEP_TENSOR): fp16 operands + their TMA descriptors
@@ -921,6 +922,9 @@ namespace
         int          count = 0;
         CUDA_TRY(cudaMemcpyAsync(&count, ctx->rf_count.p, sizeof(int), cudaMemcpyDeviceToHost, main));
         CUDA_TRY(cudaStreamSynchronize(main)); // main has already waited for the last result copies of a host-buffer job
+        // Dense data (many observations in few dimensions): nearly every candidate sits close to a data point and is re-evaluated, so
+        // the tensor pass is wasted work. Remember it for this model: run_sweep then sweeps in IEEE double from the start.
+        if (job.M >= 8192 && 2LL * count > job.M) ctx->dense_version = ctx->model_version;
         const int R = (int) std::min<long long>(count, cap);
         if (R <= 0) return SLSGP_OK;
         const int Rc = (int) std::min<long long>(2048, ctx->Mcap); // P1 / P2 / stats hold Mcap candidates
@@ -1000,6 +1004,16 @@ namespace
 
     slsgp_status run_sweep(slsgp_ctx* ctx, const SweepJob& job)
     {
+        if (is_tensor_mode(ctx->sweep_mode) && ctx->refine_tau > 0.0 && job.slice_len == 0 && ctx->dense_version == ctx->model_version)
+        {
+            // the last sweep over this model sent most of its candidates to the second tier (refine_listed): skip the tensor pass
+            const int user_mode = ctx->sweep_mode;
+            ctx->sweep_mode     = SLSGP_SWEEP_FP64, ctx->Mcap = 0;
+            slsgp_status st     = ensure_sweep_workspace(ctx, job.M);
+            if (st == SLSGP_OK) st = run_sweep(ctx, job);
+            ctx->sweep_mode = user_mode, ctx->Mcap = 0; // the next call re-establishes the tensor workspace (buffers only ever grow)
+            return st;
+        }
         const bool      tensor = is_tensor_mode(ctx->sweep_mode);
         const int       D = ctx->D;
         const long long cap = ctx->Mcap, n_shards = (job.M + cap - 1) / cap;
@@ -1234,6 +1248,7 @@ namespace
             CUDA_TRY(cudaMemcpyPeerAsync(pc.to->p, dst->device, pc.from->p, ctx->device, pc.bytes, dst->stream));
         CUDA_TRY(cudaStreamSynchronize(dst->stream));
         // a replica serves sweeps only: no factor to update, no Gram matrix to read back
+        dst->dense_version = ~0ull; // a new model: the second-tier statistics of the old one do not carry over
         dst->has_data = true, dst->has_gram = false, dst->has_factor = false, dst->has_W = false, dst->has_inverse = true, dst->has_alpha = true;
         dst->replica_of = ctx->model_version;
         return SLSGP_OK;

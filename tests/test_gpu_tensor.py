@@ -252,3 +252,32 @@ def test_second_tier_re_evaluates_the_candidates_next_to_data_in_double(ctx, sls
     print(f"\ngrad UCB error vs FP64: second tier on {e_on:.2e}, off {e_off:.2e}")
     assert e_on <= e_off
     ctx.set_refine_threshold(0.1)
+
+
+def test_dense_data_goes_straight_to_the_double_sweep(ctx, slsb):
+    """Thousands of observations in a few dimensions: sigma^2 << a nearly everywhere, so the second tier re-evaluates almost every
+    candidate. After one such batch the context sweeps this model in IEEE double directly (no tensor pass), and a new model starts
+    over on the tensor path."""
+    D, N, M = 4, 600, 20000
+    X, theta = S.make_X(N, D, "uniform"), S.make_theta(D, "default")
+    ctx.fit(X, S.SE, theta, 0.005, S.make_y(X))
+    Q = S.make_queries(M, D)
+    v0, g0 = ctx.acq_batch(1, 2.0, Q)
+    ctx.set_sweep_mode(slsb.SWEEP_TENSOR)
+    ctx.profile_enable(True)
+    v1, g1 = ctx.acq_batch(1, 2.0, Q)     # tensor pass + second tier for most candidates
+    assert ctx.profile_read("tc_gemm")[1] > 0
+    v2, g2 = ctx.acq_batch(1, 2.0, Q)     # remembered: IEEE double from the start
+    assert ctx.profile_read("tc_gemm")[1] == 0 and ctx.profile_read("sweep_gemm")[1] > 0
+    np.testing.assert_array_equal(v2, v0)
+    np.testing.assert_array_equal(g2, g0)
+    check("UCB", v1, v0)
+    check("grad UCB", g1, g0)
+    # a sparse model on the same context: back on the tensor path
+    X2 = S.make_X(60, D, "uniform")
+    ctx.fit(X2, S.SE, theta, 0.005, S.make_y(X2))
+    ctx.set_sweep_mode(slsb.SWEEP_TENSOR)
+    ctx.profile_read("tc_gemm")
+    ctx.acq_batch(1, 2.0, Q)
+    assert ctx.profile_read("tc_gemm")[1] > 0
+    ctx.profile_enable(False)
