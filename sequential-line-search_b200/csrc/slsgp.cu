@@ -699,7 +699,9 @@ namespace
         // Squared distances on the tensor pipe (tc_kstar.cuh) for D <= 64 when the generator has the GPU to itself (it allocates all of
         // an SM's TMEM, as the contraction kernel does); SLSGP_KSTAR_TC=0 selects the FP32-pipe generators below (A/B).
         static const int tc_env = std::getenv("SLSGP_KSTAR_TC") ? std::atoi(std::getenv("SLSGP_KSTAR_TC")) : 1;
-        if (tc_env != 0 && tiled_env < 0 && ctx->kt_KP && !under_gemm)
+        // (from ~1000 observations on: below that a shard is a few tiles per SM and the FP32-pipe generators, whose cost shrinks
+        // with N, are the faster ones - N = 115, D = 64: 0.066 vs 0.101 ms per shard; SLSGP_KSTAR_TC=2 forces the tensor-pipe form)
+        if (tc_env != 0 && tiled_env < 0 && ctx->kt_KP && !under_gemm && (ldt >= 1024 || tc_env == 2))
         {
             const int       KP = ctx->kt_KP, KS = KP / TC_BK;
             const long long Mp128 = Mpad; // every row the contraction reads (a multiple of 128 or, for the CTA pair, 256)
