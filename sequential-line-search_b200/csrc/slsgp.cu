@@ -707,7 +707,7 @@ namespace
             const long long Mp128 = Mpad; // every row the contraction reads (a multiple of 128 or, for the CTA pair, 256)
             __half*         Qh = ptr<__half>(ctx->kt_Qh) + (size_t) buf * ctx->tc_Mcap * KP;
             float*          nq = ptr<float>(ctx->kt_nq) + (size_t) buf * ctx->tc_Mcap;
-            tc_pack_qh_kernel<<<(unsigned) ((Mp128 + 127) / 128), 128, 0, st>>>(d_Xq, Mc, Mp128, D, KP, dp(ctx->inv_l), Qh, nq);
+            tc_pack_qh_kernel<<<(unsigned) ((Mp128 * 32 + 255) / 256), 256, 0, st>>>(d_Xq, Mc, Mp128, D, KP, dp(ctx->inv_l), Qh, nq);
             LAUNCH_CHECK();
             KstarTcParams prm;
             prm.ldt = ldt, prm.ncb = ldt / KT_BN, prm.n_strips = (int) (Mp128 / KT_BM), prm.q_row0 = (int) ((long long) buf * ctx->tc_Mcap);

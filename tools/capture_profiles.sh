@@ -16,7 +16,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-fil
     python bench.py --steps 2 --warmup 1 --candidates 262144 --fp64-candidates 65536 --e2e-candidates 65536 --no-cpu-baseline --no-configs --no-pageable --no-mode-table > /dev/null 2>&1
 python tools/ncu_summary.py launches /tmp/ncu/launches.csv > $O/r02_launches_bench.txt 2>&1
 cap r02_tc_gemm tc_sweep_gemm 6 1 python tools/tc_bench.py 2048 16 3
-cap r02_kstar kstar16_strip 6 1 python tools/tc_bench.py 2048 16 3
+cap r02_kstar "kstar_tc|kstar16" 6 1 python tools/tc_bench.py 2048 16 3
 cap r02_finish sweep_finish 6 1 python tools/tc_bench.py 2048 16 3
 cap r02_gram_2048 gram_sym 8 1 python tools/gram_bench.py --sizes 2048 --dims 16
 cap r02_gram_8192 gram_sym 8 1 python tools/gram_bench.py --sizes 8192 --dims 16
