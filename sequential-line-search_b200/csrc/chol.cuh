@@ -107,6 +107,84 @@ namespace slsgp
         __syncthreads();
     }
 
+    // Same elimination, TWO pivots per barrier. Columns j = 2 m + 16 jq and j + 1 live in the two half-warps of warp m
+    // (ty = 2 m and 2 m + 1, lanes 0-15 and 16-31), so the owners of column j + 1 can apply pivot j to their own column with
+    // shuffles (d_j, S[j+1][j] and col_j[p] come from the other half-warp) before BOTH columns are broadcast through shared
+    // memory; everybody else then applies the two rank-1 updates back to back. Every entry sees the same operations in the same
+    // order as in potf2_inverse_regs (results are bit-identical), with 32 block-wide barriers instead of 64: the pivot chain
+    // (broadcast, barrier, reciprocal) is paid once per pair. colbuf is [2][2][TILE + 2] here.
+    __device__ __forceinline__ void potf2_inverse_regs_pair(double c[4][4], double* colbuf /* [2][2][TILE + 2] */, double* dv,
+                                                            double* rs, int* sbad, int tx, int ty, int diag0, int* info)
+    {
+        if (threadIdx.x == 0) *sbad = 0x7fffffff;
+        int       first_bad = 0x7fffffff;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, half = lane >> 4;
+#pragma unroll
+        for (int jq = 0; jq < 4; ++jq)
+        {
+            for (int m = 0; m < 8; ++m)
+            {
+                const int j    = 2 * m + 16 * jq; // pivots j and j + 1
+                double*   colA = colbuf + (m & 1) * 2 * (TILE + 2);
+                double*   colB = colA + (TILE + 2);
+                if (warp == m) // the 32 threads that own columns j (lanes 0-15) and j + 1 (lanes 16-31)
+                {
+                    const int    rj     = 2 * m; // row j = rj + 16 jq sits in lane rj of the first half-warp, register [jq][jq]
+                    const double dj     = __shfl_sync(0xffffffffu, c[jq][jq], rj);
+                    const double lj1    = __shfl_sync(0xffffffffu, c[jq][jq], rj + 1); // S[j+1][j]
+                    const double inv_dj = fast_reciprocal(dj);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        double a = c[i][jq];
+                        if (i == jq && lane == rj) a = 1.0; // col_j[j] := 1
+                        const double colj_p = __shfl_sync(0xffffffffu, a, tx);
+                        if (half) c[i][jq] = fma(-(colj_p * inv_dj), lj1, c[i][jq]); // pivot j applied to column j + 1 (all rows)
+                    }
+                    double* col = half ? colB : colA;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                    {
+                        double v = c[i][jq];
+                        if (i == jq && tx == rj + half) // the pivot of this half-warp's column
+                        {
+                            col[TILE] = v, dv[j + half] = v;
+                            if (!(v > 0.0)) first_bad = min(first_bad, j + half);
+                            v = 1.0;
+                        }
+                        col[tx + 16 * i] = v;
+                    }
+                }
+                __syncthreads();
+                const double inv_a = fast_reciprocal(colA[TILE]), inv_b = fast_reciprocal(colB[TILE]);
+                double       rowa[4], rowb[4], cola[4], colb[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) rowa[i] = colA[tx + 16 * i] * inv_a, rowb[i] = colB[tx + 16 * i] * inv_b;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) cola[q] = colA[ty + 16 * q], colb[q] = colB[ty + 16 * q];
+                // p = tx + 16 i, q = ty + 16 qq. Pivot j acts on q > j + 1 here (column j + 1 has it already), pivot j + 1 on q > j + 1.
+                const bool ty_gt = ty > 2 * m + 1, tx_ge_ty = tx >= ty, tx_le_j = tx <= 2 * m, tx_le_j1 = tx <= 2 * m + 1;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q)
+                    {
+                        const bool q_gt    = q > jq || (q == jq && ty_gt);
+                        const bool p_ge_q  = i > q || (i == q && tx_ge_ty);
+                        const bool p_le_j  = i < jq || (i == jq && tx_le_j);
+                        const bool p_le_j1 = i < jq || (i == jq && tx_le_j1);
+                        if (q_gt && (p_ge_q || p_le_j)) c[i][q] = fma(-rowa[i], cola[q], c[i][q]);
+                        if (q_gt && (p_ge_q || p_le_j1)) c[i][q] = fma(-rowb[i], colb[q], c[i][q]);
+                    }
+            }
+        }
+        if (first_bad != 0x7fffffff) atomicMin(sbad, first_bad);
+        __syncthreads();
+        if (threadIdx.x < TILE) rs[threadIdx.x] = rsqrt(dv[threadIdx.x]);
+        if (threadIdx.x == 0 && *sbad != 0x7fffffff) atomicCAS(info, 0, 1 + diag0 + *sbad);
+        __syncthreads();
+    }
+
     // acc += As^T Bs over k in [0, 64) on the FP64 tensor pipe: As[k][m], Bs[k][n]; warp w owns the 32 (m) x 16 (n) block at
     // (wm, wn) = ((w & 1) * 32, (w >> 1) * 16) as 4 x 2 DMMA tiles; acc[i][j][h] = element (wm + 8 i + lane / 4,
     // wn + 8 j + 2 (lane % 4) + h).
@@ -148,10 +226,33 @@ namespace slsgp
         }
     }
 
+    // Same tile, same layout, as an asynchronous copy (cp.async.cg, 16 bytes per request, 8 requests per thread): nothing passes
+    // through registers, so the copies of both operand tiles and the loads of the C tile are all in flight together and a CTA
+    // pays one memory latency per tile instead of three. Complete with chol_cp_async_wait_all() + __syncthreads().
+    __device__ __forceinline__ void load_tile_64_async(double (*dst)[CHOL_LDS], const double* src, int ld, int tid)
+    {
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+        {
+            const int      e = tid + r * 256, kk = e >> 5, m = (e & 31) * 2;
+            const uint32_t d = (uint32_t) __cvta_generic_to_shared(&dst[kk][m]);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src + (size_t) m + (size_t) kk * ld) : "memory");
+        }
+    }
+    __device__ __forceinline__ void chol_cp_async_wait_all()
+    {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+
     // grid: rem (rem + 1) / 2 CTAs for k >= 0, rem CTAs for k = -1 (rem = nb - k - 1); 256 threads;
     // dynamic shared memory CHOL_SMEM_BYTES.
-    __global__ void __launch_bounds__(256)
-        chol_step_kernel(double* L, double* W, int ld, int k, int nb, int* flags, int* info)
+    // Panel form (two-level factorisation of slsgp.cu:do_factor, N >= 4096): pe < nb restricts the trailing update to the block
+    // columns k + 1 .. pe - 1 of the current panel (grid: sum over those columns of nb - column); do_upd == 0 skips the update
+    // altogether (first step of a panel: its columns already carry every earlier panel through the SYRK launches; grid: rem).
+    template <bool PAIR>
+    __global__ void __launch_bounds__(256, 2)
+        chol_step_kernel(double* L, double* W, int ld, int k, int nb, int pe, int do_upd, int* flags, int* info)
     {
         extern __shared__ __align__(16) double csm[];
         double(*As)[CHOL_LDS] = reinterpret_cast<double(*)[CHOL_LDS]>(csm);
@@ -166,11 +267,18 @@ namespace slsgp
         int       tm, tn;
         if (t < rem)
             tm = k + 1 + t, tn = k + 1;
-        else
+        else if (pe >= nb)
         {
             int a, b;
             lower_tile(t - rem, a, b);
             tm = k + 2 + a, tn = k + 2 + b;
+        }
+        else
+        {
+            // panel form: only the block columns k + 2 .. pe - 1 of the current panel, column by column
+            int r = t - rem, col = k + 2;
+            while (r >= nb - col) r -= nb - col, ++col;
+            tm = col + r, tn = col;
         }
         double* Ct = L + (size_t) tm * TILE + (size_t) tn * TILE * ld;
 
@@ -181,6 +289,11 @@ namespace slsgp
 #pragma unroll
             for (int j = 0; j < 2; ++j) upd[i][j][0] = upd[i][j][1] = 0.0;
 
+        if (do_upd) // both operand tiles on their way before anything else is touched
+        {
+            load_tile_64_async(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid);
+            load_tile_64_async(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid);
+        }
         if (t >= rem) // plain trailing tile: C -= update, read and written in fragment layout
         {
             double cf[4][2][2];
@@ -190,8 +303,7 @@ namespace slsgp
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
                     for (int h = 0; h < 2; ++h) cf[i][j][h] = Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wn + j * 8 + lc * 2 + h) * ld];
-            load_tile_64(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid, false);
-            load_tile_64(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            chol_cp_async_wait_all();
             __syncthreads();
             tile_dmma_64(As, Bs, wm, wn, lane, upd);
 #pragma unroll
@@ -210,10 +322,9 @@ namespace slsgp
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int i = 0; i < 4; ++i) c[i][j] = Ct[(size_t) (tx + 16 * i) + (size_t) (ty + 16 * j) * ld];
-        if (k >= 0)
+        if (do_upd)
         {
-            load_tile_64(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid, false);
-            load_tile_64(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid, false);
+            chol_cp_async_wait_all();
             __syncthreads();
             tile_dmma_64(As, Bs, wm, wn, lane, upd);
             __syncthreads(); // operands consumed: As becomes the re-layout buffer, As[n][m] = update(m, n)
@@ -234,8 +345,8 @@ namespace slsgp
         if (t == 0)
         {
             // next diagonal tile: factorise + invert in registers, publish L, W and the flag
-            double* colbuf = csm;
-            double* dv     = csm + 2 * (TILE + 2);
+            double* colbuf = csm; // [2][2][TILE + 2]
+            double* dv     = csm + 4 * (TILE + 2);
             double* rs     = dv + TILE;
             int*    sbad   = reinterpret_cast<int*>(rs + TILE);
 #pragma unroll
@@ -243,7 +354,10 @@ namespace slsgp
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (ty + 16 * j > tx + 16 * i) c[i][j] = 0.0;
-            potf2_inverse_regs(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
+            if (PAIR)
+                potf2_inverse_regs_pair(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
+            else
+                potf2_inverse_regs(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
             double* Wt = W + (size_t) tn * TILE * ((size_t) ld + 1);
             // L[p][q] = S[p][q] rs[q] for q <= p (the diagonal is d * d^-1/2), 0 above; written straight from registers
 #pragma unroll

@@ -58,6 +58,13 @@ struct slsgp_ctx
     // shard pipeline (run_sweep): candidates in + k* on `pre`, contraction + finish on `stream`, results out on `post`
     cudaStream_t pre_stream = nullptr, post_stream = nullptr;
     cudaEvent_t  ev_start = nullptr, ev_in[2] = {nullptr, nullptr}, ev_main[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    // two-level Cholesky (do_factor, nb >= chol_two_level_from): critical-path stream, look-ahead stream, their events (lazy)
+    cudaStream_t chol_hi = nullptr, chol_side = nullptr;
+    cudaEvent_t  ev_chol[3] = {nullptr, nullptr, nullptr};
+    int          chol_two_level_from = 96; // block columns (N >= 6144; below, the step chain hides the single-level update); SLSGP_CHOL_TWO_LEVEL_FROM
+    int          chol_panel          = 8;  // block columns per panel; SLSGP_CHOL_PANEL
+    bool         chol_look_ahead     = true; // SLSGP_CHOL_LOOKAHEAD=0: everything on the critical stream
+    bool         chol_pair           = true; // SLSGP_CHOL_PAIR=0: one pivot per barrier in the diagonal tile (A/B)
     std::string  err;
     unsigned     compat     = SLSGP_COMPAT_SE_XGRAD_2X;
     int          sweep_mode = SLSGP_SWEEP_FP64;
@@ -232,14 +239,15 @@ namespace
         return SLSGP_OK;
     }
 
-    template <bool TA, bool TB> slsgp_status launch_gemm(slsgp_ctx* ctx, const GemmArgs& g, int batch = 1)
+    template <bool TA, bool TB> slsgp_status launch_gemm(slsgp_ctx* ctx, const GemmArgs& g, int batch = 1, cudaStream_t st = nullptr)
     {
         dim3 grid(g.m / TILE, g.n / TILE, batch);
+        if (!st) st = ctx->stream;
         static const bool simt = std::getenv("SLSGP_FP64_GEMM") && std::string(std::getenv("SLSGP_FP64_GEMM")) == "simt";
         if (simt)
-            gemm64_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g);      // DFMA reference implementation
+            gemm64_kernel<TA, TB><<<grid, 256, 0, st>>>(g);      // DFMA reference implementation
         else
-            gemm64_dmma_kernel<TA, TB><<<grid, 256, 0, ctx->stream>>>(g); // FP64 tensor pipe (mma.sync m8n8k4)
+            gemm64_dmma_kernel<TA, TB><<<grid, 256, 0, st>>>(g); // FP64 tensor pipe (mma.sync m8n8k4)
         LAUNCH_CHECK();
         return SLSGP_OK;
     }
@@ -353,23 +361,103 @@ namespace
         static bool chol_attr[64] = {}; // function attributes are per device
         if (!chol_attr[ctx->device & 63])
         {
-            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
             chol_attr[ctx->device & 63] = true;
         }
-        // launch k finishes block column k+1 (diagonal factor + panel) while updating the rest of the trailing matrix
-        for (int k = -1; k <= nb - 2; ++k)
-        {
+        // one step: launch k finishes block column k+1 (diagonal factor + panel) while updating the trailing block columns
+        // k+2 .. pe-1 (pe = nb: the whole trailing matrix)
+        const auto step = [&](int k, int pe, int upd, cudaStream_t st) -> slsgp_status {
             const int rem  = nb - k - 1;
-            const int grid = k < 0 ? rem : rem * (rem + 1) / 2;
-            ProfScope           ps(ctx, "chol_step");
+            int       grid = rem;
+            if (upd)
+            {
+                if (pe >= nb)
+                    grid = rem * (rem + 1) / 2;
+                else
+                    for (int c = k + 2; c < pe; ++c) grid += nb - c;
+            }
+            ProfScope           ps(ctx, "chol_step", st);
             cudaLaunchConfig_t  cfg = {};
             cudaLaunchAttribute attr[1];
-            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(256), cfg.dynamicSmemBytes = CHOL_SMEM_BYTES, cfg.stream = ctx->stream;
+            cfg.gridDim = dim3(grid), cfg.blockDim = dim3(256), cfg.dynamicSmemBytes = CHOL_SMEM_BYTES, cfg.stream = st;
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // overlap this launch with the tail of the previous step
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr, cfg.numAttrs = 1;
-            CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel, L, W, ld, k, nb, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
+            if (ctx->chol_pair)
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<true>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
+            else
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<false>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
             LAUNCH_CHECK();
+            return SLSGP_OK;
+        };
+        if (nb < ctx->chol_two_level_from)
+        {
+            for (int k = -1; k <= nb - 2; ++k) TRY(step(k, nb, k >= 0, ctx->stream));
+        }
+        else
+        {
+            // Two-level form for large N. The right-looking sweep above moves the whole trailing matrix through L2 once per
+            // 64 columns (4 flop per byte); here a PANEL of pw block columns is factored with the same step kernel restricted to
+            // the panel, and the trailing matrix receives the panel in ONE rank-(64 pw) update C -= P P^T (gemm64_dmma_kernel).
+            // Look-ahead: the update of the NEXT panel's columns runs on the critical stream, the rest of the trailing matrix on a
+            // second, lower-priority stream under the next panel's factorisation:
+            //   hi  : steps(p) . [ev_panel] . wait(ev_side of p-1) . update(next panel's columns)            . steps(p+1) ...
+            //   side:              wait(ev_panel) . update(columns beyond the next panel) . [ev_side]
+            // (both updates of panel p-1 / p that touch the same columns are ordered by ev_side).
+            if (!ctx->chol_hi)
+            {
+                int lo = 0, hi = 0;
+                CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CUDA_TRY(cudaStreamCreateWithPriority(&ctx->chol_hi, cudaStreamNonBlocking, hi));
+                CUDA_TRY(cudaStreamCreateWithPriority(&ctx->chol_side, cudaStreamNonBlocking, lo));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chol[0], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chol[1], cudaEventDisableTiming));
+                CUDA_TRY(cudaEventCreateWithFlags(&ctx->ev_chol[2], cudaEventDisableTiming));
+            }
+            cudaStream_t hi = ctx->chol_hi, side = ctx->chol_look_ahead ? ctx->chol_side : ctx->chol_hi;
+            cudaEvent_t  ev_panel = ctx->ev_chol[0], ev_side = ctx->ev_chol[1], ev_done = ctx->ev_chol[2];
+            CUDA_TRY(cudaEventRecord(ev_done, ctx->stream)); // L = K, cleared flags
+            CUDA_TRY(cudaStreamWaitEvent(hi, ev_done, 0));
+            if (side != hi) CUDA_TRY(cudaStreamWaitEvent(side, ev_done, 0));
+            const int PB = ctx->chol_panel;
+            const auto syrk = [&](int c0, int pw, int r0, int ncols, cudaStream_t st) -> slsgp_status {
+                // C[r0.., r0 .. r0+ncols) -= P[r0.., :] P[r0 .. r0+ncols, :]^T, P = block columns c0 .. c0+pw-1 of L, lower tiles only
+                ProfScope ps(ctx, "chol_syrk", st);
+                const double* P = L + (size_t) r0 * TILE + (size_t) c0 * TILE * ld;
+                GemmArgs      g = gemm_args(P, P, L + (size_t) r0 * TILE * ((size_t) ld + 1), (nb - r0) * TILE, ncols * TILE, pw * TILE, ld, ld, ld, -1.0, 1.0);
+                g.lower_only    = 1;
+                return launch_gemm<false, true>(ctx, g, 1, st);
+            };
+            bool side_pending = false;
+            for (int c0 = 0; c0 < nb; c0 += PB)
+            {
+                const int pw = std::min(PB, nb - c0), pe = c0 + pw;
+                TRY(step(c0 - 1, pe, 0, hi));
+                for (int k = c0; k <= pe - 2; ++k) TRY(step(k, pe, 1, hi));
+                if (pe >= nb) break;
+                const int pw2 = std::min(PB, nb - pe), r1 = pe + pw2;
+                if (side != hi && r1 < nb) CUDA_TRY(cudaEventRecord(ev_panel, hi));
+                if (side_pending)
+                {
+                    CUDA_TRY(cudaStreamWaitEvent(hi, ev_side, 0));
+                    side_pending = false;
+                }
+                TRY(syrk(c0, pw, pe, pw2, hi));
+                if (r1 < nb)
+                {
+                    if (side != hi) CUDA_TRY(cudaStreamWaitEvent(side, ev_panel, 0));
+                    TRY(syrk(c0, pw, r1, nb - r1, side));
+                    if (side != hi)
+                    {
+                        CUDA_TRY(cudaEventRecord(ev_side, side));
+                        side_pending = true;
+                    }
+                }
+            }
+            if (side_pending) CUDA_TRY(cudaStreamWaitEvent(hi, ev_side, 0));
+            CUDA_TRY(cudaEventRecord(ev_done, hi));
+            CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_done, 0));
         }
         zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
         LAUNCH_CHECK();
@@ -1342,6 +1430,10 @@ extern "C"
                  cudaEventCreateWithFlags(&ctx->ev_main[b], cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&ctx->ev_out[b], cudaEventDisableTiming) == cudaSuccess;
         if (const char* e = std::getenv("SLSGP_TC_PAIR")) ctx->tc_ncta = std::atoi(e) ? 2 : 1;
+        if (const char* e = std::getenv("SLSGP_CHOL_TWO_LEVEL_FROM")) ctx->chol_two_level_from = std::max(2, std::atoi(e));
+        if (const char* e = std::getenv("SLSGP_CHOL_PANEL")) ctx->chol_panel = std::min(16, std::max(2, std::atoi(e)));
+        if (const char* e = std::getenv("SLSGP_CHOL_LOOKAHEAD")) ctx->chol_look_ahead = std::atoi(e) != 0;
+        if (const char* e = std::getenv("SLSGP_CHOL_PAIR")) ctx->chol_pair = std::atoi(e) != 0;
         if (const char* e = std::getenv("SLSGP_REFINE_TAU")) ctx->refine_tau = std::min(1.0, std::max(0.0, std::atof(e)));
         ctx->pinned_bytes = 1 << 16;
         ok                = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;
@@ -1419,6 +1511,10 @@ extern "C"
             if (ctx->ev_out[b]) cudaEventDestroy(ctx->ev_out[b]);
         }
         if (ctx->ev_start) cudaEventDestroy(ctx->ev_start);
+        for (int b = 0; b < 3; ++b)
+            if (ctx->ev_chol[b]) cudaEventDestroy(ctx->ev_chol[b]);
+        if (ctx->chol_hi) cudaStreamDestroy(ctx->chol_hi);
+        if (ctx->chol_side) cudaStreamDestroy(ctx->chol_side);
         if (ctx->pre_stream) cudaStreamDestroy(ctx->pre_stream);
         if (ctx->post_stream) cudaStreamDestroy(ctx->post_stream);
         if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

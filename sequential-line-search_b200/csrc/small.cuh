@@ -97,7 +97,7 @@ namespace slsgp
         static_assert(TILE == SMALL_N, "potf2_inverse_regs works on 64 x 64 tiles");
         if (N >= SMALL_REGS_FROM)
         {
-            // ---- factor and triangular inverse in registers (potf2_inverse_regs, chol.cuh: one barrier per pivot) -----------
+            // ---- factor and triangular inverse in registers (potf2_inverse_regs_pair, chol.cuh: one barrier per two pivots) -----------
             const int tx = tid & 15, ty = tid >> 4;
             double    c[4][4];
             __syncthreads(); // Kb complete
@@ -109,7 +109,8 @@ namespace slsgp
                     const int p = tx + 16 * iq, q = ty + 16 * jq;
                     c[iq][jq]   = q <= p ? Kb[q * SMALL_LD + p] : 0.0;
                 }
-            potf2_inverse_regs(c, part, part + 2 * (TILE + 2), dg, bad, tx, ty, 0, a.info); // dg = d^-1/2
+            // column buffers + pivots live in Wb, which is only written after the factorisation
+            potf2_inverse_regs_pair(c, Wb, Wb + 4 * (TILE + 2), dg, bad, tx, ty, 0, a.info); // dg = d^-1/2
             if (*bad != 0x7fffffff)
             {
                 if (tid == 0) a.out[4] = (double) (*bad + 1);
