@@ -373,6 +373,8 @@ def main_graft(args):
                 phases[k].append(ctx.phase_ms(k))
     aux = {k + "_ms": float(np.median(v)) for k, v in phases.items()}
     aux["gram_chol_ms"] = aux["gram_ms"] + aux["factor_ms"]
+    if rank == 0:
+        aux["cusolver_potrf_ms"] = cusolver_potrf_ms(torch, ctx.gram(KERNEL_SE, theta, NOISE, want=True))
 
     # ---- device-resident candidates: 2 distinct batches per rank, rotated (each far larger than the 126 MB L2)
     nb = 2
@@ -581,9 +583,11 @@ def main_graft(args):
             # programmatic dependent launches and serialise them (measured inside the steps: chol_ms / chol_n * nb64)
             per_factor_ms = aux["factor_ms"]
             ach = N_OBS ** 3 / 3.0 / (per_factor_ms * 1e-3) / 1e12
-            rooflines["cholesky"] = {"bound": "tensor", "kernel": f"chol_step_kernel x {nb64} dependent launches (FP64 DMMA trailing update)", "achieved": ach,
+            rooflines["cholesky"] = {"bound": "tensor", "kernel": f"chol_step_kernel<pair> x {nb64} dependent launches (FP64 DMMA trailing update, two pivots per barrier in the diagonal tile)", "achieved": ach,
                                      "peak": dgemm_tflops, "unit": "TFLOP/s", "frac": ach / dgemm_tflops, "algorithmic_flop": N_OBS ** 3 / 3.0,
                                      "ms_per_factorisation": per_factor_ms, "launches_timed": chol_n,
+                                     "cusolver_potrf_ms": aux.get("cusolver_potrf_ms"),
+                                     "note": "latency chain of N / 64 dependent steps, not a throughput kernel at this size; cusolver_potrf_ms = torch.linalg.cholesky on the same matrix in this run",
                                      "peak_source": "cuBLAS DGEMM 8192^3 measured in this run", "traffic": None}
         line = {
             "metric": METRIC, "value": Mtot * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -631,6 +635,25 @@ def main_graft(args):
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def cusolver_potrf_ms(torch, K_host, reps=7):
+    """cuSOLVER potrf through torch.linalg.cholesky on the same Gram matrix, CUDA events, median: the library point the
+    factorisation is read against (not on the product path; torch allocates the output inside the timed call)."""
+    K = torch.from_numpy(np.ascontiguousarray(K_host)).cuda()
+    for _ in range(3):
+        torch.linalg.cholesky(K)
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        torch.linalg.cholesky(K)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    del K
+    return float(np.median(ts))
 
 
 def extra_configs(pkg, ctx, torch):
@@ -736,6 +759,7 @@ def extra_configs(pkg, ctx, torch):
             ctx.inverse(want=False)
             ctx.solve_alpha(yg)
         row = {"n_obs": Ng, "dim": DIM, "gram_ms": ctx.phase_ms("gram"), "cholesky_ms": ctx.phase_ms("factor"), "inverse_ms": ctx.phase_ms("inverse")}
+        row["cusolver_potrf_ms"] = cusolver_potrf_ms(torch, ctx.gram(KERNEL_SE, thg, NOISE, want=True), reps=5)
         Mg = 1 << 18
         qg = torch.rand((Mg, DIM), dtype=torch.float64, device="cuda")
         vg, gg = torch.empty(Mg, dtype=torch.float64, device="cuda"), torch.empty((Mg, DIM), dtype=torch.float64, device="cuda")

@@ -189,11 +189,11 @@ namespace slsgp
     // (wm, wn) = ((w & 1) * 32, (w >> 1) * 16) as 4 x 2 DMMA tiles; acc[i][j][h] = element (wm + 8 i + lane / 4,
     // wn + 8 j + 2 (lane % 4) + h).
     __device__ __forceinline__ void tile_dmma_64(double (*As)[CHOL_LDS], double (*Bs)[CHOL_LDS], int wm, int wn, int lane,
-                                                 double acc[4][2][2])
+                                                 double acc[4][2][2], int k_end = TILE)
     {
         const int lr = lane >> 2, lc = lane & 3;
 #pragma unroll 4
-        for (int ks = 0; ks < TILE; ks += 4)
+        for (int ks = 0; ks < k_end; ks += 4)
         {
             double a[4], b[2];
 #pragma unroll
@@ -250,7 +250,7 @@ namespace slsgp
     // Panel form (two-level factorisation of slsgp.cu:do_factor, N >= 4096): pe < nb restricts the trailing update to the block
     // columns k + 1 .. pe - 1 of the current panel (grid: sum over those columns of nb - column); do_upd == 0 skips the update
     // altogether (first step of a panel: its columns already carry every earlier panel through the SYRK launches; grid: rem).
-    template <bool PAIR>
+    template <int PIV> // pivots per barrier in the diagonal tile: 2, or 1 (A/B; same layout, bit-identical results)
     __global__ void __launch_bounds__(256, 2)
         chol_step_kernel(double* L, double* W, int ld, int k, int nb, int pe, int do_upd, int* flags, int* info)
     {
@@ -354,21 +354,13 @@ namespace slsgp
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     if (ty + 16 * j > tx + 16 * i) c[i][j] = 0.0;
-            if (PAIR)
+            if (PIV == 2)
                 potf2_inverse_regs_pair(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
             else
                 potf2_inverse_regs(c, colbuf, dv, rs, sbad, tx, ty, tn * TILE, info);
             double* Wt = W + (size_t) tn * TILE * ((size_t) ld + 1);
-            // L[p][q] = S[p][q] rs[q] for q <= p (the diagonal is d * d^-1/2), 0 above; written straight from registers
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                {
-                    const int p = tx + 16 * i, q = ty + 16 * j;
-                    Ct[(size_t) p + (size_t) q * ld] = q <= p ? c[i][j] * rs[q] : 0.0;
-                }
-            // W[q][p] = R[q][p] rs[q] = S[p][q] rs[q] for p < q: transpose through shared memory so the store coalesces
+            // W first: it is all the panel CTAs below are waiting for. W[q][p] = R[q][p] rs[q] = S[p][q] rs[q] for p < q:
+            // transposed through shared memory so the store coalesces
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -387,6 +379,16 @@ namespace slsgp
             __threadfence();
             __syncthreads();
             if (tid == 0) atomicExch(&flags[tn], 1);
+            // then L[p][q] = S[p][q] rs[q] for q <= p (the diagonal is d * d^-1/2), 0 above; written straight from registers.
+            // Nobody inside the factorisation reads the diagonal tile of L again (the panels use W).
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                {
+                    const int p = tx + 16 * i, q = ty + 16 * j;
+                    Ct[(size_t) p + (size_t) q * ld] = q <= p ? c[i][j] * rs[q] : 0.0;
+                }
             return;
         }
 
@@ -397,7 +399,14 @@ namespace slsgp
             for (int i = 0; i < 4; ++i) As[ty + 16 * j][tx + 16 * i] = c[i][j]; // As[n][m] = C(m, n)
         if (tid == 0)
         {
-            while (atomicAdd(&flags[tn], 0) == 0) __nanosleep(32);
+            // acquire loads, not atomics: up to nb - 1 CTAs poll this word and read-modify-writes on one address would queue up in
+            // front of the publisher's store
+            int seen;
+            do
+            {
+                asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(flags + tn) : "memory");
+                if (!seen) __nanosleep(20);
+            } while (!seen);
             __threadfence();
         }
         __syncthreads();
@@ -409,12 +418,15 @@ namespace slsgp
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        tile_dmma_64(As, Bs, wm, wn, lane, acc);
+        // W is lower-triangular: output columns [wc, wc + 16) need the contraction range [0, wc + 16) only. The four column
+        // strips are dealt so that the two warps of each scheduler (warp and warp + 4) hold 16 + 64 or 32 + 48 rows of it.
+        const int wsel = warp >> 1, wc = wsel == 2 ? 48 : (wsel == 3 ? 32 : wsel * 16);
+        tile_dmma_64(As, Bs, wm, wc, lane, acc, wc + 16);
 #pragma unroll
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int j = 0; j < 2; ++j)
 #pragma unroll
-                for (int h = 0; h < 2; ++h) Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wn + j * 8 + lc * 2 + h) * ld] = acc[i][j][h];
+                for (int h = 0; h < 2; ++h) Ct[(size_t) (wm + i * 8 + lr) + (size_t) (wc + j * 8 + lc * 2 + h) * ld] = acc[i][j][h];
     }
 } // namespace slsgp

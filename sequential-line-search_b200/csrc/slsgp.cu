@@ -64,7 +64,8 @@ struct slsgp_ctx
     int          chol_two_level_from = 96; // block columns (N >= 6144; below, the step chain hides the single-level update); SLSGP_CHOL_TWO_LEVEL_FROM
     int          chol_panel          = 8;  // block columns per panel; SLSGP_CHOL_PANEL
     bool         chol_look_ahead     = true; // SLSGP_CHOL_LOOKAHEAD=0: everything on the critical stream
-    bool         chol_pair           = true; // SLSGP_CHOL_PAIR=0: one pivot per barrier in the diagonal tile (A/B)
+    int          chol_switch_rem     = 48; // two-level only while more than this many block columns remain; SLSGP_CHOL_SWITCH_REM
+    int          chol_pivots         = 2;  // pivots per barrier in the diagonal tile (2, or 1 for A/B); SLSGP_CHOL_PIVOTS
     std::string  err;
     unsigned     compat     = SLSGP_COMPAT_SE_XGRAD_2X;
     int          sweep_mode = SLSGP_SWEEP_FP64;
@@ -361,8 +362,8 @@ namespace
         static bool chol_attr[64] = {}; // function attributes are per device
         if (!chol_attr[ctx->device & 63])
         {
-            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
-            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
+            CUDA_TRY(cudaFuncSetAttribute(chol_step_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, CHOL_SMEM_BYTES));
             chol_attr[ctx->device & 63] = true;
         }
         // one step: launch k finishes block column k+1 (diagonal factor + panel) while updating the trailing block columns
@@ -384,10 +385,10 @@ namespace
             attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // overlap this launch with the tail of the previous step
             attr[0].val.programmaticStreamSerializationAllowed = 1;
             cfg.attrs = attr, cfg.numAttrs = 1;
-            if (ctx->chol_pair)
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<true>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
+            if (ctx->chol_pivots >= 2)
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<2>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
             else
-                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<false>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
+                CUDA_TRY(cudaLaunchKernelEx(&cfg, chol_step_kernel<1>, L, W, ld, k, nb, pe, upd, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info)));
             LAUNCH_CHECK();
             return SLSGP_OK;
         };
@@ -432,6 +433,19 @@ namespace
             bool side_pending = false;
             for (int c0 = 0; c0 < nb; c0 += PB)
             {
+                if (nb - c0 <= ctx->chol_switch_rem)
+                {
+                    // the rest is chain-bound: the single-level sweep hides its (small) trailing updates behind the diagonal tiles
+                    // and pays no per-panel launches. Its first step factors column c0 as it stands (every panel is in already).
+                    if (side_pending)
+                    {
+                        CUDA_TRY(cudaStreamWaitEvent(hi, ev_side, 0));
+                        side_pending = false;
+                    }
+                    TRY(step(c0 - 1, nb, 0, hi));
+                    for (int k = c0; k <= nb - 2; ++k) TRY(step(k, nb, 1, hi));
+                    break;
+                }
                 const int pw = std::min(PB, nb - c0), pe = c0 + pw;
                 TRY(step(c0 - 1, pe, 0, hi));
                 for (int k = c0; k <= pe - 2; ++k) TRY(step(k, pe, 1, hi));
@@ -1433,7 +1447,8 @@ extern "C"
         if (const char* e = std::getenv("SLSGP_CHOL_TWO_LEVEL_FROM")) ctx->chol_two_level_from = std::max(2, std::atoi(e));
         if (const char* e = std::getenv("SLSGP_CHOL_PANEL")) ctx->chol_panel = std::min(16, std::max(2, std::atoi(e)));
         if (const char* e = std::getenv("SLSGP_CHOL_LOOKAHEAD")) ctx->chol_look_ahead = std::atoi(e) != 0;
-        if (const char* e = std::getenv("SLSGP_CHOL_PAIR")) ctx->chol_pair = std::atoi(e) != 0;
+        if (const char* e = std::getenv("SLSGP_CHOL_SWITCH_REM")) ctx->chol_switch_rem = std::max(0, std::atoi(e));
+        if (const char* e = std::getenv("SLSGP_CHOL_PIVOTS")) ctx->chol_pivots = std::atoi(e);
         if (const char* e = std::getenv("SLSGP_REFINE_TAU")) ctx->refine_tau = std::min(1.0, std::max(0.0, std::atof(e)));
         ctx->pinned_bytes = 1 << 16;
         ok                = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;

@@ -131,9 +131,9 @@ def test_factor_and_inverse_identities_at_large_n(N):
     assert e_llt < 1e-13 and e_inv < 1e-9 and e_sym < 1e-12 and e_ld < 1e-12
 
 
-@pytest.mark.parametrize("panel,look_ahead", [(2, 1), (4, 1), (4, 0), (3, 1)])
+@pytest.mark.parametrize("panel,look_ahead,switch_rem", [(2, 1, 0), (4, 1, 0), (4, 0, 0), (3, 1, 0), (2, 1, 5), (3, 1, 7), (4, 0, 6)])
 @pytest.mark.parametrize("N", [700, 1100])
-def test_two_level_cholesky_equals_the_single_level_one(monkeypatch, oracle, N, panel, look_ahead):
+def test_two_level_cholesky_equals_the_single_level_one(monkeypatch, oracle, N, panel, look_ahead, switch_rem):
     """The two-level factorisation (panels + one rank-64p update per panel on two streams, slsgp.cu:do_factor) is the default from
     N = 4096 on; forced here at sizes the plain-C oracle factors in a second. Same matrix, same 64-wide block columns: L differs
     from the single-level sweep only by the summation order inside the trailing update (checked at 1e-13 against it, and
@@ -145,6 +145,7 @@ def test_two_level_cholesky_equals_the_single_level_one(monkeypatch, oracle, N, 
         monkeypatch.setenv("SLSGP_CHOL_TWO_LEVEL_FROM", "3" if two_level else "100000")
         monkeypatch.setenv("SLSGP_CHOL_PANEL", str(panel))
         monkeypatch.setenv("SLSGP_CHOL_LOOKAHEAD", str(look_ahead))
+        monkeypatch.setenv("SLSGP_CHOL_SWITCH_REM", str(switch_rem))  # block columns left to the single-level sweep at the end
         ctx = pkg.Context(0)
         try:
             ctx.set_data(X)
@@ -161,34 +162,34 @@ def test_two_level_cholesky_equals_the_single_level_one(monkeypatch, oracle, N, 
     e_o = _err(got[1][1], L_o)
     e_l = _err(got[1][1], got[0][1])
     e_i = _err(got[1][2], got[0][2])
-    print(f"\nN={N} panel={panel} look-ahead={look_ahead}: L vs oracle {e_o:.1e}, vs single level {e_l:.1e}, K^-1 vs single level {e_i:.1e}")
+    print(f"\nN={N} panel={panel} look-ahead={look_ahead} switch={switch_rem}: L vs oracle {e_o:.1e}, vs single level {e_l:.1e}, K^-1 vs single level {e_i:.1e}")
     assert e_o < 1e-9 and e_l < 1e-13 and e_i < 1e-9
     assert abs(got[1][0] - got[0][0]) <= 1e-12 * abs(got[0][0])
     assert not np.triu(got[1][1], 1).any()
 
 
 def test_pair_pivot_tile_is_bit_identical_to_the_single_pivot_tile(monkeypatch):
-    """potf2_inverse_regs_pair (two pivots per barrier) performs the same operations in the same order on every entry as
-    potf2_inverse_regs; the factors must agree bit for bit, including the first non-positive pivot it reports."""
+    """potf2_inverse_regs_pair (two pivots per barrier, the default) performs the same operations in the same order on every
+    entry as potf2_inverse_regs; the factors must agree bit for bit, including the first non-positive pivot it reports."""
     kt, D, N = S.SE, 8, 448
     X, theta, noise = S.make_X(N, D, "uniform"), S.make_theta(D, "default"), 0.005
     got = {}
-    for pair in (0, 1):
-        monkeypatch.setenv("SLSGP_CHOL_PAIR", str(pair))
+    for piv in (1, 2):
+        monkeypatch.setenv("SLSGP_CHOL_PIVOTS", str(piv))
         ctx = pkg.Context(0)
         try:
             ctx.set_data(X)
             ctx.gram(kt, theta, noise, want=False)
             logdet, L = ctx.factor(want_L=True)
-            got[pair] = (logdet, L, ctx.inverse(want=True))
+            got[piv] = (logdet, L, ctx.inverse(want=True))
             Xd = X.copy()
             Xd[:, 100] = Xd[:, 37]  # duplicated point, slightly negative noise: the Schur complement at 100 is negative
             ctx.set_data(Xd)
             ctx.gram(kt, theta, -1e-3, want=False)
             with pytest.raises(pkg.SlsgpError) as ei:
                 ctx.factor()
-            got[pair] += (str(ei.value),)
+            got[piv] += (str(ei.value),)
         finally:
             ctx.close()
-    assert got[0][0] == got[1][0] and np.array_equal(got[0][1], got[1][1]) and np.array_equal(got[0][2], got[1][2])
-    assert got[0][3] == got[1][3] and "pivot" in got[1][3]
+    assert got[1][0] == got[2][0] and np.array_equal(got[1][1], got[2][1]) and np.array_equal(got[1][2], got[2][2])
+    assert got[1][3] == got[2][3] and "pivot" in got[2][3]

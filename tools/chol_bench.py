@@ -1,6 +1,6 @@
 """Cholesky factor time of libslsgp under its A/B switches next to cuSOLVER potrf (torch.linalg.cholesky) on the same Gram matrix.
 
-Settings (environment, read when a context is created): SLSGP_CHOL_PAIR (two pivots per barrier in the diagonal tile),
+Settings (environment, read when a context is created): SLSGP_CHOL_PIVOTS (1 or 2 pivots per barrier in the diagonal tile),
 SLSGP_CHOL_TWO_LEVEL_FROM (block columns from which the two-level form is used), SLSGP_CHOL_PANEL (block columns per panel),
 SLSGP_CHOL_LOOKAHEAD (trailing update beyond the next panel on a second stream). Times: `factor` phase of the library (copy K -> L,
 all steps, zeroing of the upper triangle, log-determinant), median of `reps` factorisations; not part of the product path."""
@@ -20,7 +20,7 @@ pkg = importlib.import_module("sequential-line-search_b200")
 
 
 def factor_ms(n, env, reps=7):
-    for k in ("SLSGP_CHOL_PAIR", "SLSGP_CHOL_TWO_LEVEL_FROM", "SLSGP_CHOL_PANEL", "SLSGP_CHOL_LOOKAHEAD"):
+    for k in ("SLSGP_CHOL_PIVOTS", "SLSGP_CHOL_TWO_LEVEL_FROM", "SLSGP_CHOL_PANEL", "SLSGP_CHOL_LOOKAHEAD", "SLSGP_CHOL_SWITCH_REM"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ctx = pkg.Context(0)
@@ -63,16 +63,20 @@ def main():
         del K
         print(f"N={n}: cuSOLVER potrf {np.median(ts):7.3f} ms", flush=True)
         off = "100000"
-        settings = [("single level, 1 pivot / barrier", {"SLSGP_CHOL_PAIR": "0", "SLSGP_CHOL_TWO_LEVEL_FROM": off}),
-                    ("single level, 2 pivots / barrier", {"SLSGP_CHOL_TWO_LEVEL_FROM": off})]
+        settings = [("single level, 1 pivot / barrier", {"SLSGP_CHOL_PIVOTS": "1", "SLSGP_CHOL_TWO_LEVEL_FROM": off}),
+                    ("single level, 2 pivots / barrier", {"SLSGP_CHOL_PIVOTS": "2", "SLSGP_CHOL_TWO_LEVEL_FROM": off})]
         if n >= 1024:
-            for pb in ((4, 8, 16) if n >= 4096 else (4, 8)):
-                settings.append((f"two-level, panel {pb}, look-ahead", {"SLSGP_CHOL_TWO_LEVEL_FROM": "3", "SLSGP_CHOL_PANEL": str(pb)}))
-            settings.append(("two-level, panel 4, one stream", {"SLSGP_CHOL_TWO_LEVEL_FROM": "3", "SLSGP_CHOL_PANEL": "4", "SLSGP_CHOL_LOOKAHEAD": "0"}))
+            for pb in ((8, 16) if n >= 4096 else (4, 8)):
+                settings.append((f"two-level to the end, panel {pb}", {"SLSGP_CHOL_TWO_LEVEL_FROM": "3", "SLSGP_CHOL_PANEL": str(pb), "SLSGP_CHOL_SWITCH_REM": "0"}))
+            settings.append(("two-level to the end, panel 4, one stream", {"SLSGP_CHOL_TWO_LEVEL_FROM": "3", "SLSGP_CHOL_PANEL": "4", "SLSGP_CHOL_LOOKAHEAD": "0", "SLSGP_CHOL_SWITCH_REM": "0"}))
+        if n >= 4096:
+            for pb in (8,):
+                for sw in (32, 48):
+                    settings.append((f"two-level, panel {pb}, single level for the last {sw}", {"SLSGP_CHOL_TWO_LEVEL_FROM": "3", "SLSGP_CHOL_PANEL": str(pb), "SLSGP_CHOL_SWITCH_REM": str(sw)}))
         settings.append(("library default", {}))
         for name, env in settings:
             f, i = factor_ms(n, env)
-            print(f"    {name:36s} factor {f:7.3f} ms   inverse {i:7.3f} ms", flush=True)
+            print(f"    {name:52s} factor {f:7.3f} ms   inverse {i:7.3f} ms", flush=True)
 
 
 if __name__ == "__main__":
