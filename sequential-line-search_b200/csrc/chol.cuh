@@ -245,6 +245,31 @@ namespace slsgp
         asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
 
+    // Start of a factorisation in ONE launch (it used to be a device-to-device copy, two memsets and, at the end, a kernel
+    // zeroing the upper triangle): L = lower tiles of K, zeros in the tiles above the diagonal (the diagonal tiles get their zeros
+    // from the step kernel), flags and info cleared. grid: (nb, nb) tiles, 256 threads.
+    __global__ void __launch_bounds__(256)
+        chol_prepare_kernel(const double* __restrict__ K, double* __restrict__ L, int ld, int nb, int* __restrict__ flags, int* __restrict__ info)
+    {
+        const int tm = blockIdx.x, tn = blockIdx.y, tid = threadIdx.x;
+        if (tm == 0 && tn == 0)
+        {
+            for (int i = tid; i < nb; i += 256) flags[i] = 0;
+            if (tid == 0) *info = 0;
+        }
+        const size_t base = (size_t) tm * TILE + (size_t) tn * TILE * ld;
+        const bool   copy = tn <= tm;
+#pragma unroll
+        for (int r = 0; r < 8; ++r)
+        {
+            const int    e = tid + r * 256, row = (e & 31) * 2, col = e >> 5;
+            const size_t o = base + (size_t) row + (size_t) col * ld;
+            double2      v = make_double2(0.0, 0.0);
+            if (copy) v = *reinterpret_cast<const double2*>(K + o);
+            *reinterpret_cast<double2*>(L + o) = v;
+        }
+    }
+
     // grid: rem (rem + 1) / 2 CTAs for k >= 0, rem CTAs for k = -1 (rem = nb - k - 1); 256 threads;
     // dynamic shared memory CHOL_SMEM_BYTES.
     // Panel form (two-level factorisation of slsgp.cu:do_factor, N >= 4096): pe < nb restricts the trailing update to the block

@@ -237,14 +237,6 @@ namespace slsgp
                 }
     }
 
-    // Zero the strict upper triangle of an n x n matrix (after the blocked factorisation the upper tiles still hold
-    // the Gram matrix).
-    __global__ void zero_upper_kernel(double* __restrict__ A, int n, int lda)
-    {
-        const int r = blockIdx.x * blockDim.x + threadIdx.x, c = blockIdx.y;
-        if (r < n && r < c) A[(size_t) r + (size_t) c * lda] = 0.0;
-    }
-
     // Mirror the lower triangle into the upper one (64 x 64 tiles through shared memory so both sides coalesce).
     __global__ void __launch_bounds__(256) symmetrize_kernel(double* __restrict__ A, int lda)
     {

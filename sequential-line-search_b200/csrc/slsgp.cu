@@ -77,6 +77,8 @@ struct slsgp_ctx
     double logdet_host = 0.0;
     bool   has_data = false, has_gram = false, has_factor = false, has_W = false, has_inverse = false,
          has_alpha = false;
+    bool   factor_pending = false; // do_factor(defer_check): has_factor is provisional until the caller has read info
+
     std::vector<double> theta_host;
     std::vector<double> X_host; // host mirror of X (D x N), for slsgp_set_data_extend's prefix comparison
 
@@ -344,21 +346,22 @@ namespace
         return SLSGP_OK;
     }
 
-    slsgp_status do_factor(slsgp_ctx* ctx, double* logdet_out)
+    // defer_check: enqueue only. The pivot check and the log-determinant stay on the device (info, scalars[8]) and the caller
+    // collects them with its own results after ONE synchronisation (factor_pending; slsgp_map_objective_pref).
+    slsgp_status do_factor(slsgp_ctx* ctx, double* logdet_out, bool defer_check = false)
     {
         if (!ctx->has_gram) return fail(ctx, SLSGP_ERR_STATE, "slsgp_factor before slsgp_gram");
         const int    ld = ctx->ld, nb = ld / TILE;
-        const size_t mat = sizeof(double) * (size_t) ld * ld;
-        ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+        ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = ctx->factor_pending = false;
         TRY(phase_begin(ctx, "factor"));
-        CUDA_TRY(cudaMemcpyAsync(ctx->L.p, ctx->K.p, mat, cudaMemcpyDeviceToDevice, ctx->stream));
         // W is written tile by tile (diagonal tiles by the factorisation, the blocks below them by do_trtri); every reader
         // prunes its k-range to the lower blocks, so W needs no clearing
-        CUDA_TRY(cudaMemsetAsync(ctx->info.p, 0, sizeof(int), ctx->stream));
         double* L = dp(ctx->L);
         double* W = dp(ctx->W);
         TRY(ensure(ctx, ctx->chol_flags, sizeof(int) * (size_t) nb));
-        CUDA_TRY(cudaMemsetAsync(ctx->chol_flags.p, 0, sizeof(int) * (size_t) nb, ctx->stream));
+        // L = lower tiles of K, zero tiles above, flags and info cleared: one launch
+        chol_prepare_kernel<<<dim3(nb, nb), 256, 0, ctx->stream>>>(dp(ctx->K), L, ld, nb, ptr<int>(ctx->chol_flags), ptr<int>(ctx->info));
+        LAUNCH_CHECK();
         static bool chol_attr[64] = {}; // function attributes are per device
         if (!chol_attr[ctx->device & 63])
         {
@@ -473,11 +476,14 @@ namespace
             CUDA_TRY(cudaEventRecord(ev_done, hi));
             CUDA_TRY(cudaStreamWaitEvent(ctx->stream, ev_done, 0));
         }
-        zero_upper_kernel<<<dim3((ld + 255) / 256, ld), 256, 0, ctx->stream>>>(L, ld, ld);
-        LAUNCH_CHECK();
         logdet_kernel<<<1, 256, 0, ctx->stream>>>(L, ctx->N, ld, dp(ctx->scalars) + 8);
         LAUNCH_CHECK();
         TRY(phase_end(ctx, "factor"));
+        if (defer_check)
+        {
+            ctx->has_factor = ctx->factor_pending = true;
+            return SLSGP_OK;
+        }
         int    info = 0;
         double logdet = 0.0;
         CUDA_TRY(cudaMemcpyAsync(&info, ctx->info.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -1450,7 +1456,7 @@ extern "C"
         if (const char* e = std::getenv("SLSGP_CHOL_SWITCH_REM")) ctx->chol_switch_rem = std::max(0, std::atoi(e));
         if (const char* e = std::getenv("SLSGP_CHOL_PIVOTS")) ctx->chol_pivots = std::atoi(e);
         if (const char* e = std::getenv("SLSGP_REFINE_TAU")) ctx->refine_tau = std::min(1.0, std::max(0.0, std::atof(e)));
-        ctx->pinned_bytes = 1 << 16;
+        ctx->pinned_bytes = 1 << 17; // second half: results of the one-synchronisation MAP objective (kMapOutOffset)
         ok                = ok && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) == cudaSuccess;
         if (!ok)
         {
@@ -2424,6 +2430,81 @@ extern "C"
         }
     }
 
+    // Results of one MAP objective evaluation on the general path, in the second half of the pinned staging area, so that the
+    // whole evaluation needs ONE stream synchronisation (device-to-host copies into pageable memory synchronise by themselves):
+    //   [0..2] y.alpha, alpha.alpha, tr K^-1   [3] logdet   [4] info (int)   [5] BTL log-likelihood   [8 .. 8 + D) d/dl   [256 .. 256 + N) d/dy
+    constexpr int kMapOutOffset = 8192, kMapOutGl = 8, kMapOutGy = 256, kMapOutMaxD = 248, kMapOutMaxN = 8192 - 256;
+
+    static slsgp_status gp_term_kernels(slsgp_ctx* ctx, bool want_hyper)
+    {
+        const int ld = ctx->ld, N = ctx->N, D = ctx->D;
+        TRY(do_alpha(ctx));
+        gp_scalars_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->y), dp(ctx->alpha), dp(ctx->Kinv), N, ld, dp(ctx->scalars));
+        LAUNCH_CHECK();
+        if (want_hyper)
+        {
+            const int nt = ld / TILE;
+            gram_tile_kernel<1><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(
+                dp(ctx->X), N, D, ld, dp(ctx->theta), dp(ctx->inv_l), ctx->noise, ctx->kernel_type, dp(ctx->T),
+                dp(ctx->Kinv), dp(ctx->alpha));
+            LAUNCH_CHECK();
+            GemmArgs g = gemm_args(dp(ctx->T), dp(ctx->XT1), dp(ctx->Ymat), ld, ctx->ldx, ld, ld, ld, ld, 1.0, 0.0);
+            TRY((launch_gemm<false, false>(ctx, g)));
+            lengthscale_grad_kernel<<<D, 256, 0, ctx->stream>>>(dp(ctx->XT1), dp(ctx->Ymat), N, ld, D, dp(ctx->theta), dp(ctx->g_l));
+            LAUNCH_CHECK();
+        }
+        return SLSGP_OK;
+    }
+
+    // All results of one evaluation gathered by ONE small kernel that writes the pinned result block directly (pinned host memory
+    // is device-addressable): no device-to-host copy operations at all, where the multi-copy form paid ~5 us for each of six.
+    __global__ void __launch_bounds__(256)
+        map_pack_kernel(const double* __restrict__ scalars, const int* __restrict__ info, const double* __restrict__ g_l,
+                        const double* __restrict__ grad_y, int D, int N, int want_hyper, int want_gy, double* __restrict__ out)
+    {
+        const int i = blockIdx.x * 256 + threadIdx.x;
+        if (i < 3) out[i] = scalars[i];                               // y.alpha, alpha.alpha, tr K^-1 (gp_scalars_kernel)
+        if (i == 3) out[3] = scalars[8];                              // log-determinant (logdet_kernel)
+        if (i == 4) *reinterpret_cast<int*>(out + 4) = *info;         // pivot check of the factorisation
+        if (i == 5) out[5] = scalars[4];                              // BTL log-likelihood (sum_kernel)
+        if (want_hyper && i < D) out[kMapOutGl + i] = g_l[i];
+        if (want_gy && i < N) out[kMapOutGy + i] = grad_y[i];
+    }
+
+    // Enqueue form of gp_term: kernels only; map_results_enqueue (after the BTL kernels) sends everything home.
+    static slsgp_status gp_term_enqueue(slsgp_ctx* ctx, bool want_hyper) { return gp_term_kernels(ctx, want_hyper); }
+
+    static slsgp_status map_results_enqueue(slsgp_ctx* ctx, bool want_hyper, bool want_gy)
+    {
+        double* out_dev = nullptr;
+        CUDA_TRY(cudaHostGetDevicePointer(reinterpret_cast<void**>(&out_dev), ctx->pinned + kMapOutOffset, 0));
+        const int n = std::max(std::max(want_gy ? ctx->N : 0, want_hyper ? ctx->D : 0), 8);
+        map_pack_kernel<<<(n + 255) / 256, 256, 0, ctx->stream>>>(dp(ctx->scalars), ptr<int>(ctx->info), dp(ctx->g_l), dp(ctx->grad_y), ctx->D, ctx->N,
+                                                                  want_hyper ? 1 : 0, want_gy ? 1 : 0, out_dev);
+        LAUNCH_CHECK();
+        return SLSGP_OK;
+    }
+
+    // After the synchronisation: the deferred pivot check of do_factor(defer_check), then the host part of the GP term.
+    static slsgp_status gp_term_collect(slsgp_ctx* ctx, double* logdet, bool want_hyper, double* value, double* g_hyper)
+    {
+        const double* out = ctx->pinned + kMapOutOffset;
+        if (ctx->factor_pending)
+        {
+            ctx->factor_pending = false;
+            const int info = *reinterpret_cast<const int*>(out + 4);
+            if (info != 0)
+            {
+                ctx->has_factor = ctx->has_W = ctx->has_inverse = ctx->has_alpha = false;
+                return fail(ctx, SLSGP_ERR_NOT_SPD,
+                            "Cholesky: non-positive pivot at index " + std::to_string(info - 1) + " (K_y is not SPD)");
+            }
+            ctx->logdet_host = *logdet = out[3];
+        }
+        gp_term_host(ctx, *logdet, out, out + kMapOutGl, want_hyper, value, g_hyper);
+        return SLSGP_OK;
+    }
+
     static slsgp_status gp_term(slsgp_ctx* ctx, double logdet, bool want_hyper, double* value, double* g_hyper)
     {
         const int ld = ctx->ld, N = ctx->N, D = ctx->D;
@@ -2536,6 +2617,10 @@ extern "C"
         double              logdet = 0.0, gp = 0.0;
         std::vector<double> gh((size_t) D + 2);
         const bool          want_hyper = grad_out && use_map, small = use_map && small_model_applies(ctx);
+        // general path: every result travels through the pinned block and the evaluation synchronises once (SLSGP_MAP_ONE_SYNC=0: A/B)
+        static const bool one_sync_enabled = !(std::getenv("SLSGP_MAP_ONE_SYNC") && std::atoi(std::getenv("SLSGP_MAP_ONE_SYNC")) == 0);
+        const bool        one_sync = one_sync_enabled && !small && D <= kMapOutMaxD && N <= kMapOutMaxN;
+        if (ctx->factor_pending) ctx->factor_pending = ctx->has_factor = false; // left over from a call that failed half-way
         // SLSGP_COMPAT_NOISELESS: the reference's SEQUENTIAL_LINE_SEARCH_USE_NOISELESS_FORMULATION build (:48-52, 139, 178-192, 237):
         // K = K_f (b fixed at 0 whatever x holds), no prior on b, d/db = 0
         const bool   noiseless = use_map && (ctx->compat & SLSGP_COMPAT_NOISELESS);
@@ -2550,9 +2635,12 @@ extern "C"
             else
             {
                 TRY(do_gram(ctx, (int) kernel_type, theta.data(), b_used));
-                TRY(do_factor(ctx, &logdet));
+                TRY(do_factor(ctx, &logdet, one_sync));
                 CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-                TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
+                if (one_sync)
+                    TRY(gp_term_enqueue(ctx, want_hyper));
+                else
+                    TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
             }
         }
         else
@@ -2561,8 +2649,12 @@ extern "C"
                 return fail(ctx, SLSGP_ERR_STATE, "use_map_hyperparams == 0 needs slsgp_gram + slsgp_factor first");
             logdet = ctx->logdet_host;
             CUDA_TRY(cudaMemcpyAsync(ctx->y.p, x, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-            TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
+            if (one_sync)
+                TRY(gp_term_enqueue(ctx, want_hyper));
+            else
+                TRY(gp_term(ctx, logdet, want_hyper, &gp, gh.data()));
         }
+        double* const map_out = ctx->pinned + kMapOutOffset;
 
         // BTL likelihood of the tuples (the small-model launch above already holds them)
         double loglik = 0.0;
@@ -2574,7 +2666,7 @@ extern "C"
             LAUNCH_CHECK();
             sum_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->loglik), ctx->P, dp(ctx->scalars) + 4);
             LAUNCH_CHECK();
-            CUDA_TRY(cudaMemcpyAsync(&loglik, dp(ctx->scalars) + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (!one_sync) CUDA_TRY(cudaMemcpyAsync(&loglik, dp(ctx->scalars) + 4, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
         }
         if (grad_out && !small)
         {
@@ -2582,10 +2674,17 @@ extern "C"
                 dp(ctx->contrib), ptr<uint32_t>(ctx->slot_off), ptr<uint32_t>(ctx->slot_list), dp(ctx->alpha), N,
                 dp(ctx->grad_y));
             LAUNCH_CHECK();
-            CUDA_TRY(cudaMemcpyAsync(grad_out, ctx->grad_y.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
+            if (!one_sync) CUDA_TRY(cudaMemcpyAsync(grad_out, ctx->grad_y.p, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
         }
+        if (one_sync) TRY(map_results_enqueue(ctx, want_hyper, grad_out != nullptr));
         TRY(phase_end(ctx, "map"));
         CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        if (one_sync)
+        {
+            TRY(gp_term_collect(ctx, &logdet, want_hyper, &gp, gh.data()));
+            if (ctx->P > 0) loglik = map_out[5];
+            if (grad_out) std::memcpy(grad_out, map_out + kMapOutGy, sizeof(double) * (size_t) N);
+        }
         if (small)
         {
             TRY(small_model_collect(ctx, want_hyper, &logdet, &gp, gh.data()));
@@ -2730,10 +2829,21 @@ extern "C"
         }
         else
         {
+            static const bool one_sync_enabled = !(std::getenv("SLSGP_MAP_ONE_SYNC") && std::atoi(std::getenv("SLSGP_MAP_ONE_SYNC")) == 0);
+            const bool        one_sync = one_sync_enabled && D <= kMapOutMaxD; // as in slsgp_map_objective_pref
+            if (ctx->factor_pending) ctx->factor_pending = ctx->has_factor = false;
             TRY(do_gram(ctx, (int) kernel_type, theta.data(), x[1]));
-            TRY(do_factor(ctx, &logdet));
+            TRY(do_factor(ctx, &logdet, one_sync));
             CUDA_TRY(cudaMemcpyAsync(ctx->y.p, y, sizeof(double) * N, cudaMemcpyHostToDevice, ctx->stream));
-            TRY(gp_term(ctx, logdet, grad_out != nullptr, &gp, gh.data()));
+            if (one_sync)
+            {
+                TRY(gp_term_enqueue(ctx, grad_out != nullptr));
+                TRY(map_results_enqueue(ctx, grad_out != nullptr, false));
+                CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+                TRY(gp_term_collect(ctx, &logdet, grad_out != nullptr, &gp, gh.data()));
+            }
+            else
+                TRY(gp_term(ctx, logdet, grad_out != nullptr, &gp, gh.data()));
         }
         TRY(phase_end(ctx, "map"));
         // fixed log-normal priors of src/gaussian-process-regressor.cpp:18-24

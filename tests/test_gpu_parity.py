@@ -428,3 +428,31 @@ def test_small_model_kernel_reports_a_matrix_that_is_not_spd(ctx, slsb):
     with pytest.raises(slsb.SlsgpError) as e:
         ctx.map_objective_gpr(S.SE, np.zeros(6), np.array([0.5, 0.0, 0.5, 0.5, 0.5, 0.5]))
     assert "SPD" in str(e.value)
+
+
+def test_general_map_path_reports_a_matrix_that_is_not_spd_and_recovers(ctx, slsb, oracle):
+    """The general-path MAP objectives (N > 64) synchronise once per evaluation: the pivot check of the factorisation is collected
+    with the results (do_factor(defer_check)). A singular K_y must still be reported, and the next evaluation on the same context
+    must be a clean one."""
+    N, D = 80, 4
+    X = np.tile(np.linspace(0.1, 0.9, D)[:, None], (1, N))   # identical points, (almost) no noise: singular
+    ctx.set_data(X)
+    hyper = np.concatenate([[0.5, 0.0], np.full(D, 0.5)])
+    with pytest.raises(slsb.SlsgpError) as e:
+        ctx.map_objective_gpr(S.SE, np.zeros(N), hyper)
+    assert "SPD" in str(e.value) and e.value.status == slsb.ERR_NOT_SPD
+    off, idx = S.make_tuples(X)
+    ctx.set_preferences(off, idx)
+    with pytest.raises(slsb.SlsgpError) as e:
+        ctx.map_objective_pref(S.SE, np.concatenate([np.zeros(N), hyper]), True, 0.5, 0.5, 0.005, 0.25, 0.01)
+    assert e.value.status == slsb.ERR_NOT_SPD
+    with pytest.raises(slsb.SlsgpError):
+        ctx.acq_batch(0, 1.0, S.make_queries(4, D))  # no model was left behind
+    X = S.make_X(N, D, "uniform")
+    y = S.make_y(X)
+    hyper[1] = 0.005
+    ctx.set_data(X)
+    f, g = ctx.map_objective_gpr(S.SE, y, hyper)
+    want_f, want_g = oracle.map_objective_gpr(S.SE, X, y, hyper)
+    assert abs(f - want_f) <= 1e-9 * abs(want_f)
+    check("gradient", g, want_g, 1e-7)
