@@ -161,15 +161,19 @@ namespace slsgp
     // One block per t; deterministic.
     __global__ void __launch_bounds__(256)
         lengthscale_grad_kernel(const double* __restrict__ XT1, const double* __restrict__ Y, int N, int ld, int D,
-                                const double* __restrict__ theta, double* __restrict__ g_l)
+                                const double* __restrict__ theta, double* __restrict__ g_l, int splits, size_t split_stride)
     {
+        // Y arrives as `splits` partial products (slices of the contraction), split_stride elements apart
         __shared__ double part[256];
         const int         t = blockIdx.x;
         double            s = 0.0;
         for (int i = threadIdx.x; i < N; i += 256)
         {
             const double x = XT1[(size_t) i + (size_t) t * ld];
-            s += x * x * Y[(size_t) i + (size_t) D * ld] - x * Y[(size_t) i + (size_t) t * ld];
+            double       yd = 0.0, yt = 0.0;
+            for (int z = 0; z < splits; ++z)
+                yd += Y[z * split_stride + (size_t) i + (size_t) D * ld], yt += Y[z * split_stride + (size_t) i + (size_t) t * ld];
+            s += x * x * yd - x * yt;
         }
         part[threadIdx.x] = s;
         __syncthreads();

@@ -309,7 +309,7 @@ namespace
         TRY(ensure(ctx, ctx->Kalpha, sizeof(double) * ld));
         TRY(ensure(ctx, ctx->vec, sizeof(double) * ld));
         TRY(ensure(ctx, ctx->grad_y, sizeof(double) * ld));
-        TRY(ensure(ctx, ctx->Ymat, sizeof(double) * ld * ctx->ldx));
+        TRY(ensure(ctx, ctx->Ymat, sizeof(double) * ld * ctx->ldx * 8)); // up to 8 partial products (map_y_splits)
         TRY(ensure(ctx, ctx->g_l, sizeof(double) * D));
         TRY(ensure(ctx, ctx->scalars, sizeof(double) * 32));
         TRY(ensure(ctx, ctx->info, sizeof(int)));
@@ -2435,6 +2435,14 @@ extern "C"
     //   [0..2] y.alpha, alpha.alpha, tr K^-1   [3] logdet   [4] info (int)   [5] BTL log-likelihood   [8 .. 8 + D) d/dl   [256 .. 256 + N) d/dy
     constexpr int kMapOutOffset = 8192, kMapOutGl = 8, kMapOutGy = 256, kMapOutMaxD = 248, kMapOutMaxN = 8192 - 256;
 
+    // slices of the contraction Y = Wm XT1 (nt = ld / 64 tiles along it): as many as divide nt, at most 8
+    static int map_y_splits(int nt)
+    {
+        for (int s = 8; s > 1; --s)
+            if (nt % s == 0) return s;
+        return 1;
+    }
+
     static slsgp_status gp_term_kernels(slsgp_ctx* ctx, bool want_hyper)
     {
         const int ld = ctx->ld, N = ctx->N, D = ctx->D;
@@ -2448,9 +2456,14 @@ extern "C"
                 dp(ctx->X), N, D, ld, dp(ctx->theta), dp(ctx->inv_l), ctx->noise, ctx->kernel_type, dp(ctx->T),
                 dp(ctx->Kinv), dp(ctx->alpha));
             LAUNCH_CHECK();
-            GemmArgs g = gemm_args(dp(ctx->T), dp(ctx->XT1), dp(ctx->Ymat), ld, ctx->ldx, ld, ld, ld, ld, 1.0, 0.0);
-            TRY((launch_gemm<false, false>(ctx, g)));
-            lengthscale_grad_kernel<<<D, 256, 0, ctx->stream>>>(dp(ctx->XT1), dp(ctx->Ymat), N, ld, D, dp(ctx->theta), dp(ctx->g_l));
+            // Y = Wm XT1 has ld / 64 x 1 output tiles only: the contraction is split into `splits` slices (batch index), each
+            // CTA writes its own partial Y and lengthscale_grad_kernel adds them up in a fixed order
+            const int splits = map_y_splits(nt), kc = ld / splits;
+            GemmArgs  g      = gemm_args(dp(ctx->T), dp(ctx->XT1), dp(ctx->Ymat), ld, ctx->ldx, kc, ld, ld, ld, 1.0, 0.0);
+            g.sA = (long long) kc * ld, g.sB = kc, g.sC = (long long) ld * ctx->ldx;
+            TRY((launch_gemm<false, false>(ctx, g, splits)));
+            lengthscale_grad_kernel<<<D, 256, 0, ctx->stream>>>(dp(ctx->XT1), dp(ctx->Ymat), N, ld, D, dp(ctx->theta), dp(ctx->g_l), splits,
+                                                                (size_t) ld * ctx->ldx);
             LAUNCH_CHECK();
         }
         return SLSGP_OK;
@@ -2507,22 +2520,8 @@ extern "C"
 
     static slsgp_status gp_term(slsgp_ctx* ctx, double logdet, bool want_hyper, double* value, double* g_hyper)
     {
-        const int ld = ctx->ld, N = ctx->N, D = ctx->D;
-        TRY(do_alpha(ctx));
-        gp_scalars_kernel<<<1, 256, 0, ctx->stream>>>(dp(ctx->y), dp(ctx->alpha), dp(ctx->Kinv), N, ld, dp(ctx->scalars));
-        LAUNCH_CHECK();
-        if (want_hyper)
-        {
-            const int nt = ld / TILE;
-            gram_tile_kernel<1><<<nt * (nt + 1) / 2, 256, 0, ctx->stream>>>(
-                dp(ctx->X), N, D, ld, dp(ctx->theta), dp(ctx->inv_l), ctx->noise, ctx->kernel_type, dp(ctx->T),
-                dp(ctx->Kinv), dp(ctx->alpha));
-            LAUNCH_CHECK();
-            GemmArgs g = gemm_args(dp(ctx->T), dp(ctx->XT1), dp(ctx->Ymat), ld, ctx->ldx, ld, ld, ld, ld, 1.0, 0.0);
-            TRY((launch_gemm<false, false>(ctx, g)));
-            lengthscale_grad_kernel<<<D, 256, 0, ctx->stream>>>(dp(ctx->XT1), dp(ctx->Ymat), N, ld, D, dp(ctx->theta), dp(ctx->g_l));
-            LAUNCH_CHECK();
-        }
+        const int D = ctx->D;
+        TRY(gp_term_kernels(ctx, want_hyper));
         double sc[3];
         CUDA_TRY(cudaMemcpyAsync(sc, ctx->scalars.p, sizeof(sc), cudaMemcpyDeviceToHost, ctx->stream));
         std::vector<double> gl((size_t) D);
