@@ -188,10 +188,16 @@ namespace slsgp
     // acc += As^T Bs over k in [0, 64) on the FP64 tensor pipe: As[k][m], Bs[k][n]; warp w owns the 32 (m) x 16 (n) block at
     // (wm, wn) = ((w & 1) * 32, (w >> 1) * 16) as 4 x 2 DMMA tiles; acc[i][j][h] = element (wm + 8 i + lane / 4,
     // wn + 8 j + 2 (lane % 4) + h).
+    // lower: only the 8 x 8 DMMA tiles that touch the lower triangle (row tile >= column tile) are computed, the others stay 0.
     __device__ __forceinline__ void tile_dmma_64(double (*As)[CHOL_LDS], double (*Bs)[CHOL_LDS], int wm, int wn, int lane,
-                                                 double acc[4][2][2], int k_end = TILE)
+                                                 double acc[4][2][2], int k_end = TILE, bool lower = false)
     {
         const int lr = lane >> 2, lc = lane & 3;
+        bool      need[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 2; ++j) need[i][j] = !lower || wm + 8 * i >= wn + 8 * j;
 #pragma unroll 4
         for (int ks = 0; ks < k_end; ks += 4)
         {
@@ -203,7 +209,8 @@ namespace slsgp
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 2; ++j) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+                for (int j = 0; j < 2; ++j)
+                    if (need[i][j]) dmma_8x8x4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
         }
     }
 
@@ -314,10 +321,10 @@ namespace slsgp
 #pragma unroll
             for (int j = 0; j < 2; ++j) upd[i][j][0] = upd[i][j][1] = 0.0;
 
-        if (do_upd) // both operand tiles on their way before anything else is touched
+        if (do_upd) // both operand tiles on their way before anything else is touched (the diagonal tile has one: tm == tn)
         {
             load_tile_64_async(As, L + (size_t) tm * TILE + (size_t) k * TILE * ld, ld, tid);
-            load_tile_64_async(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid);
+            if (t != 0) load_tile_64_async(Bs, L + (size_t) tn * TILE + (size_t) k * TILE * ld, ld, tid);
         }
         if (t >= rem) // plain trailing tile: C -= update, read and written in fragment layout
         {
@@ -351,14 +358,21 @@ namespace slsgp
         {
             chol_cp_async_wait_all();
             __syncthreads();
-            tile_dmma_64(As, Bs, wm, wn, lane, upd);
+            // The update of the DIAGONAL tile is symmetric and only its lower triangle is used: 36 of the 64 DMMA tiles. The eight
+            // 32 x 16 warp blocks hold 8, 8, 7, 7, 3, 3, 0, 0 of them; they are dealt so that the two warps of each scheduler
+            // (warp, warp + 4) hold 8 + 0 or 7 + 3 (blocks by warp: (32,0) (32,16) (0,0) (32,32) | (0,32) (0,48) (0,16) (32,48)).
+            const int bm = t == 0 ? ((0x8B >> warp) & 1) * 32 : wm, bn = t == 0 ? ((0xDE84 >> (2 * warp)) & 3) * 16 : wn;
+            if (t == 0)
+                tile_dmma_64(As, As, bm, bn, lane, upd, TILE, true);
+            else
+                tile_dmma_64(As, Bs, bm, bn, lane, upd);
             __syncthreads(); // operands consumed: As becomes the re-layout buffer, As[n][m] = update(m, n)
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 2; ++j)
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) As[wn + j * 8 + lc * 2 + h][wm + i * 8 + lr] = upd[i][j][h];
+                    for (int h = 0; h < 2; ++h) As[bn + j * 8 + lc * 2 + h][bm + i * 8 + lr] = upd[i][j][h];
             __syncthreads();
 #pragma unroll
             for (int j = 0; j < 4; ++j)
