@@ -717,6 +717,23 @@ def extra_configs(pkg, ctx, torch):
                       "what": "slsgp_map_objective_pref with hyper-parameters (Gram, Cholesky, inverse, alpha, BTL, all D + 2 + N gradient entries), "
                               "host wall clock per call incl. the copies of x and the gradient"}
 
+    # ---- the same objective at the sizes an optimiser run actually sees (N = 3 ... a few hundred): latency per evaluation
+    lat = []
+    for Nl, Dl in ((30, 6), (64, 6), (80, 6), (128, 16), (200, 6), (400, 16), (400, 64)):
+        Xl = synth.make_X(Nl, Dl, "uniform", seed=1)
+        offl, idxl = synth.make_tuples(Xl)
+        ctx.set_data(Xl)
+        ctx.set_preferences(offl, idxl)
+        xl = np.concatenate([0.05 * rng.standard_normal(Nl), [0.5, 0.005], np.full(Dl, 0.5)])
+        for it in range(5):
+            ctx.map_objective_pref(KERNEL_SE, xl * (1.0 + 1e-3 * it), True, 0.5, 0.5, 0.005, 0.25, 0.01)
+        t0 = time.perf_counter()
+        for it in range(40):
+            ctx.map_objective_pref(KERNEL_SE, xl * (1.0 + 1e-4 * it), True, 0.5, 0.5, 0.005, 0.25, 0.01)
+        lat.append({"n_obs": Nl, "dim": Dl, "us_per_objective_and_gradient": (time.perf_counter() - t0) / 40 * 1e6})
+    out["map_objective_latency"] = {"rows": lat, "what": "slsgp_map_objective_pref with hyper-parameters, host wall clock per call (mean of 40): N <= 64 is the "
+                                    "single-launch small-model kernel, above it the general path with one stream synchronisation per evaluation"}
+
     # ---- configs 1 and 5: the optimiser loops through the C++ host layer (default search driver), simulated user of the nd demo
     try:
         sys.path.insert(0, os.path.join(ROOT, "tests"))
