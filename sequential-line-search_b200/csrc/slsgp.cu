@@ -171,13 +171,26 @@ namespace
         if (b.bytes >= bytes && b.p) return SLSGP_OK;
         if (b.p) CUDA_TRY(cudaFree(b.p));
         b.p = nullptr, b.bytes = 0;
-        cudaError_t e = cudaMalloc(&b.p, bytes);
+        // Buffers of small and mid-size models get twice what was asked for: an optimiser run grows its model by two or three
+        // points per iteration, the leading dimension by 64 at a time, and every growth step used to free and re-allocate some
+        // forty buffers in each pooled context (150 - 300 ms per crossing in the D = 64 loop, tools/config5_outliers.py). With
+        // the headroom the N x N buffers are re-allocated at 128, 192, 320, 512, ... instead of at every multiple of 64.
+        const size_t cap = bytes <= ((size_t) 64 << 20) ? 2 * bytes : bytes;
+        cudaError_t  e   = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess && cap != bytes)
+        {
+            cudaGetLastError();
+            e = cudaMalloc(&b.p, bytes);
+            if (e == cudaSuccess) b.bytes = bytes;
+        }
+        else if (e == cudaSuccess)
+            b.bytes = cap;
         if (e != cudaSuccess)
         {
             cudaGetLastError();
+            b.p = nullptr;
             return fail(ctx, SLSGP_ERR_NOMEM, "cudaMalloc of " + std::to_string(bytes) + " bytes failed");
         }
-        b.bytes = bytes;
         return SLSGP_OK;
     }
     template <typename T> T* ptr(const DevBuf& b) { return static_cast<T*>(b.p); }
