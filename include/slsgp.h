@@ -161,7 +161,10 @@ extern "C"
      * K_y = L L^T: Eigen::LLT at src/preference-regressor.cpp:162,290,370; logdet = 2 sum log L_ii:
      * mathtoolbox CalcLogDetOfSymmetricPositiveDefiniteMatrix (src/log-determinant.cpp:8-11).
      * L_out: N x N lower triangle (upper part zero) or NULL. Returns SLSGP_ERR_NOT_SPD on a bad pivot (the
-     * reference never checks LLT::info()). */
+     * reference never checks LLT::info()).
+     * From N = 6144 on the factorisation runs in its two-level form on two streams of the context's own (panels on a
+     * high-priority stream, rank-k trailing updates on a second one); both are ordered against the context's stream by
+     * events on entry and exit, so callers see ordinary stream semantics (slsgp_set_stream included). */
     slsgp_status slsgp_factor(slsgp_ctx* ctx, double* logdet_out, double* L_out);
 
     /* ---- K3: factor application --------------------------------------------------------------------------------
